@@ -1,0 +1,145 @@
+/* leniax_b200 — C ABI of the B200-native Lenia simulation hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json names.  The reference (morgangiraud/leniax) is pure
+ * Python on JAX and has no FFI of its own; every entry point below cites the Python interface it replaces
+ * (file:line in the reference checkout).  INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer marked "device" is a CUDA device pointer owned by the caller
+ *     (PyTorch on the Python side).  The library allocates nothing persistent except plan-owned memory.
+ *   - every call returns 0 (LNX_OK) or a negative lnx_status; the message is available through lnx_last_error()
+ *     (thread local).  No C++ exception crosses the ABI.
+ *   - launches go to the CUDA stream passed as `stream` (a cudaStream_t cast to void*; NULL = default stream).
+ *     Calls are asynchronous like JAX dispatch; errors of asynchronous work surface at the caller's next sync.
+ *   - a plan is immutable after creation: concurrent calls on different streams are safe.
+ */
+#ifndef LENIAX_B200_H
+#define LENIAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNX_VERSION 100 /* 0.1.0 */
+#define LNX_MAX_CHANNELS 8
+#define LNX_MAX_KERNELS 32
+#define LNX_NB_STATS 11 /* scalar statistics per world-step, order = lnx_stat_key */
+
+typedef enum {
+    LNX_OK = 0,
+    LNX_ERR_INVALID = -1,     /* bad argument / unsupported configuration (Python side raises ValueError) */
+    LNX_ERR_UNSUPPORTED = -2, /* valid leniax configuration that this build cannot run (NotImplementedError) */
+    LNX_ERR_CUDA = -3,        /* CUDA runtime error (RuntimeError) */
+    LNX_ERR_NO_DEVICE = -4    /* no usable sm_100 device: there is NO CPU fallback */
+} lnx_status;
+
+/* growth functions: leniax/growth_functions.py:256-264 (register) */
+typedef enum {
+    LNX_GF_POLY_QUAD4 = 0, LNX_GF_GAUSSIAN = 1, LNX_GF_GAUSSIAN_TARGET = 2, LNX_GF_STEP = 3,
+    LNX_GF_STAIRCASE = 4, LNX_GF_TRIANGLE = 5, LNX_GF_IDENTITY = 6
+} lnx_growth_fn;
+
+/* state update functions: leniax/core.py:322-326 (register) */
+typedef enum { LNX_STATE_V1 = 0, LNX_STATE_V2 = 1, LNX_STATE_SIMPLE = 2 } lnx_state_fn;
+
+/* scalar statistics, leniax/statistics.py:102-115 (channel_mass is returned separately, shape [..., C]) */
+typedef enum {
+    LNX_ST_MASS = 0, LNX_ST_MASS_VOLUME, LNX_ST_MASS_DENSITY, LNX_ST_GROWTH, LNX_ST_GROWTH_VOLUME,
+    LNX_ST_GROWTH_DENSITY, LNX_ST_MASS_SPEED, LNX_ST_MASS_ANGLE_SPEED, LNX_ST_MASS_GROWTH_DIST, LNX_ST_INERTIA,
+    LNX_ST_POTENTIAL_VOLUME
+} lnx_stat_key;
+
+/* run flags */
+#define LNX_RUN_EARLY_STOP 1u /* stop a world once its stop criteria fired and >= 128 stat rows exist (rows after
+                                 the stop are left untouched); default off = bit-for-bit [max_run_iter] rows like
+                                 runner.py:207-213 */
+#define LNX_RUN_NO_STATS 2u   /* reserved */
+#define LNX_RUN_ASSUME_FINITE 0x100u /* caller checked that no growth s == 0 and no weight row sums to 0: NaN cannot
+                                        appear, the fused kernel may use min/max clamps that do not propagate NaN */
+
+/* Static description of the update + statistics functions.  Replaces the callables built by
+ * helpers.build_update_fn (leniax/helpers.py:401-427: slugs + tc_indices + mean/sum) and
+ * statistics.build_compute_stats_fn (leniax/statistics.py:11-33: R, dt = 1/T of the build-time config). */
+typedef struct {
+    int32_t nb_dims;                     /* world dimensions (2) */
+    int32_t dims[3];                     /* world size per dimension (128, 128) */
+    int32_t nb_channels;                 /* C */
+    int32_t nb_kernels;                  /* K = number of true kernels (after tc_indices) */
+    int32_t nb_slots;                    /* C * max_k_per_channel = leading size of the reference's K tensor */
+    int32_t slot[LNX_MAX_KERNELS];       /* tc_indices: slot of kernel k inside [C * max_k] (helpers.py:449-456) */
+    int32_t c_in[LNX_MAX_KERNELS];       /* input channel of kernel k ( = slot / max_k, kernels.py:122-143) */
+    int32_t gf_id[LNX_MAX_KERNELS];      /* lnx_growth_fn of kernel k (mapping.cin_gfs flattened) */
+    int32_t state_fn;                    /* lnx_state_fn (world_params.get_state_fn_slug) */
+    int32_t weighted_average;            /* 1: core.weighted_mean, 0: core.weighted_sum (core.py:202-242) */
+    float R;                             /* world_params.R used by the statistics (statistics.py:23) */
+    float stats_dt;                      /* 1 / world_params.T of the build-time config (statistics.py:24) */
+    uint32_t flags;                      /* reserved, 0 */
+} lnx_desc;
+
+typedef struct lnx_plan lnx_plan;
+
+int lnx_version(void);
+const char* lnx_last_error(void);
+
+/* Number of CUDA devices usable by this library (compute capability 10.x); 0 when none.  */
+int lnx_device_count(void);
+
+int lnx_plan_create(const lnx_desc* desc, lnx_plan** out);
+int lnx_plan_destroy(lnx_plan* plan);
+
+/* Size in bytes of the prepared kernel-spectrum table for ONE solution (all K kernels). */
+size_t lnx_kernel_table_bytes(const lnx_plan* plan);
+
+/* Re-pack the reference's FFT kernels (kernels.get_kernels_and_mapping, leniax/kernels.py:145-149:
+ * K = fftn(fftshift(padded kernels)), complex64 [n_sols][nb_slots][H][W], device) into the engine's per-thread
+ * half-spectrum layout (scaled by 1/(2 H W)).  table: device, n_sols * lnx_kernel_table_bytes(). */
+int lnx_kernels_prepare(const lnx_plan* plan, int32_t n_sols, const void* K_fft, void* table, void* stream);
+
+/* Forward 2-D FFT of real images: images float32 [n][H][W] (device) -> spectra complex64 [n][H][W] (device), same
+ * convention as jnp.fft.fftn.  Used by the Python layer to build K = fftn(fftshift(kernels)) (leniax/kernels.py:145-149)
+ * with the engine's own butterflies (no cuFFT). */
+int lnx_rfft2(const lnx_plan* plan, int32_t n_images, const float* images, void* spectra, void* stream);
+
+/* Measure the FP32 FMA throughput of the current device with a register-resident FMA loop (iters x 128 FMA per thread,
+ * 4 CTAs of 512 threads per SM).  Synchronous.  This is the denominator of the FP32 roofline bench.py reports. */
+int lnx_measure_fp32_peak(int32_t iters, double* tflops, double* ms, void* stream);
+
+/* Bytes of device scratch needed by lnx_run_scan for this plan (independent of the number of worlds; the fused
+ * single-channel kernel only uses the first 256 bytes).  Concurrent calls must use distinct workspaces. */
+size_t lnx_workspace_bytes(const lnx_plan* plan);
+
+/* The scan: replaces runner.run_scan / runner.run_scan_mem_optimized (leniax/runner.py:119-215) including
+ * _scan_fn (295-334), core.update (core.py:13-49), compute_stats (statistics.py:36-126) and
+ * check_heuristics (statistics.py:134-205).
+ *
+ * World w = sol * n_init + init.  All arrays are float32 device pointers, C-contiguous:
+ *   cells0        [n_sols][n_init][C][H][W]                      initial states
+ *   table         lnx_kernels_prepare output for the n_sols solutions
+ *   gf_params     [n_sols][K][2]                                 (m, s) per kernel
+ *   weights       [n_sols][C][K]                                 kernels_weight_per_channel
+ *   dt            [n_sols]                                       1 / T per solution (runner.py:307)
+ *   stats         [LNX_NB_STATS][n_sols][max_run_iter][n_init]   out
+ *   channel_mass  [n_sols][max_run_iter][n_init][C]              out
+ *   n_alive       [n_sols][n_init]                               out: stats['N'] (runner.py:161-162, 212-213)
+ *   final_cells   [n_sols][n_init][C][H][W]                      out, may be NULL
+ *   cells_out / field_out   [n_sols][max_run_iter][n_init][C][H][W], potential_out [..][K][H][W]
+ *                                                                out, each may be NULL (run_scan keeps them,
+ *                                                                run_scan_mem_optimized does not)
+ *   workspace     lnx_workspace_bytes() bytes of device scratch (contents undefined afterwards)
+ */
+int lnx_run_scan(const lnx_plan* plan, int32_t n_sols, int32_t n_init, int32_t max_run_iter, uint32_t run_flags,
+                 const float* cells0, const void* table, const float* gf_params, const float* weights, const float* dt,
+                 float* stats, float* channel_mass, float* n_alive, float* final_cells, float* cells_out, float* field_out,
+                 float* potential_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Name of the CUDA kernel lnx_run_scan would launch for this plan/arguments ("fused" or "generic"), for tests. */
+const char* lnx_run_scan_variant(const lnx_plan* plan, int32_t with_trajectory);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LENIAX_B200_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of libleniax_b200.so (C ABI: include/leniax_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  Nothing here falls back to another
+implementation: a missing library or a missing GPU raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_size_t, c_uint32, c_void_p
+
+LNX_MAX_CHANNELS = 8
+LNX_MAX_KERNELS = 32
+LNX_NB_STATS = 11
+
+LNX_RUN_EARLY_STOP = 1
+LNX_RUN_ASSUME_FINITE = 0x100
+
+LNX_OK, LNX_ERR_INVALID, LNX_ERR_UNSUPPORTED, LNX_ERR_CUDA, LNX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
+
+# order of the scalar statistics planes written by lnx_run_scan (lnx_stat_key)
+STAT_KEYS = ('mass', 'mass_volume', 'mass_density', 'growth', 'growth_volume', 'growth_density', 'mass_speed',
+             'mass_angle_speed', 'mass_growth_dist', 'inertia', 'potential_volume')
+
+
+class LeniaxB200Error(RuntimeError):
+    pass
+
+
+class LnxDesc(Structure):
+    _fields_ = [
+        ('nb_dims', c_int32),
+        ('dims', c_int32 * 3),
+        ('nb_channels', c_int32),
+        ('nb_kernels', c_int32),
+        ('nb_slots', c_int32),
+        ('slot', c_int32 * LNX_MAX_KERNELS),
+        ('c_in', c_int32 * LNX_MAX_KERNELS),
+        ('gf_id', c_int32 * LNX_MAX_KERNELS),
+        ('state_fn', c_int32),
+        ('weighted_average', c_int32),
+        ('R', c_float),
+        ('stats_dt', c_float),
+        ('flags', c_uint32),
+    ]
+
+
+EXPORTS = {
+    'lnx_version': (ctypes.c_int, []),
+    'lnx_last_error': (c_char_p, []),
+    'lnx_device_count': (ctypes.c_int, []),
+    'lnx_plan_create': (ctypes.c_int, [POINTER(LnxDesc), POINTER(c_void_p)]),
+    'lnx_plan_destroy': (ctypes.c_int, [c_void_p]),
+    'lnx_kernel_table_bytes': (c_size_t, [c_void_p]),
+    'lnx_kernels_prepare': (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    'lnx_rfft2': (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    'lnx_measure_fp32_peak': (ctypes.c_int, [c_int32, POINTER(ctypes.c_double), POINTER(ctypes.c_double), c_void_p]),
+    'lnx_workspace_bytes': (c_size_t, [c_void_p]),
+    'lnx_run_scan': (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_uint32] + [c_void_p] * 12 + [c_void_p, c_size_t, c_void_p]),
+    'lnx_run_scan_variant': (c_char_p, [c_void_p, c_int32]),
+}
+
+_LIB = None
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libleniax_b200.so')
+
+
+def load_library():
+    """Load libleniax_b200.so (once).  Raises LeniaxB200Error when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise LeniaxB200Error(
+                f'{path} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a). leniax_b200 has no CPU fallback.'
+            )
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def check(status: int):
+    """Map an lnx_status to the exception the reference would raise for the same misuse."""
+    if status == LNX_OK:
+        return
+    msg = load_library().lnx_last_error().decode('utf-8', 'replace')
+    if status == LNX_ERR_INVALID:
+        raise ValueError(msg)
+    if status == LNX_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise LeniaxB200Error(msg)

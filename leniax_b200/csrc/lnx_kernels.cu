@@ -1,0 +1,812 @@
+// leniax_b200 CUDA kernels (sm_100a) + C ABI (include/leniax_b200.h).
+//
+// Two persistent kernels, one CTA per world, 256 compute threads + 1 statistics warp:
+//   world128_fused   : 1 channel, 1 kernel, stats only (run_scan_mem_optimized hot path, BASELINE config B).
+//                      State, work buffer and kernel spectrum stay in shared memory for the whole run;
+//                      only the statistics rows go to HBM.
+//   world128_generic : any C <= 8, K <= 32, all growth/state functions, optional full trajectory output
+//                      (run_scan, core.update); channel states / spectra / field accumulators live in a per-CTA
+//                      global scratch that stays L2 resident.
+// There is no CPU fallback anywhere in this file.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/leniax_b200.h"
+#include "lnx_step.cuh"
+
+namespace lnx {
+
+constexpr int NTHREADS = NT + 32;   // 256 compute threads + 1 statistics warp
+constexpr int BAR_COMPUTE = 1;      // named barrier: the 256 compute threads
+constexpr int BAR_PARTIALS = 2;     // compute arrive  -> statistics warp sync   (partials of step t are in smem)
+constexpr int BAR_CARRY = 3;        // statistics warp arrive -> compute sync    (shift / stop flag of step t ready)
+constexpr int KT_F4 = 16 * NT;      // float4 per kernel table (complex multipliers)
+constexpr int KPQ_F4 = 32 * 4;      // float4 per packed-column table
+constexpr int KTAB_F4 = KT_F4 + KPQ_F4;
+constexpr int NPART_FUSED = PT_FIXED + 1;
+constexpr int NPART_MAX = PT_FIXED + MAX_C;
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__constant__ float2 c_tw128[128];
+
+struct Ctrl {
+    int world;
+    int shift0, shift1;
+    int stop;
+};
+
+struct RunArgs {
+    const float* cells0;
+    const float4* table;
+    const float* gf_params;
+    const float* weights;
+    const float* dt;
+    float* stats;
+    float* channel_mass;
+    float* n_alive;
+    float* final_cells;
+    float* cells_out;
+    float* field_out;
+    float* potential_out;
+    float4* scratch;
+    int* queue;
+    int n_sols, n_init, max_iter;
+    int C, K;
+    int state_fn, mean;
+    float R, stats_dt;
+    unsigned flags;
+    int c_in[MAX_K];
+    int gf_id[MAX_K];
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel-spectrum table builder: K_fft [n_sols][nb_slots][128][128] complex64 -> per-thread multipliers
+// ---------------------------------------------------------------------------------------------------------------------
+struct PrepArgs {
+    const float2* K_fft;
+    float4* table;
+    int K, nb_slots;
+    int slot[MAX_K];
+};
+__global__ void __launch_bounds__(NT) lnx_prepare_kernel(PrepArgs P) {
+    const int sol = blockIdx.x / P.K, k = blockIdx.x % P.K, tid = threadIdx.x;
+    const float2* Kf = P.K_fft + ((size_t)sol * P.nb_slots + P.slot[k]) * (WS * WS);
+    float4* tab = P.table + ((size_t)sol * P.K + k) * KTAB_F4;
+    const float scale = 1.0f / (2.0f * WS * WS);
+    const int col = t_col(tid);
+    for (int i = 0; i < 16; ++i) {
+        float2 v[2];
+        for (int e = 0; e < 2; ++e) {
+            const int m = p3_slot_m(tid, 2 * i + e);
+            v[e] = col == 0 ? make_float2(0.f, 0.f) : Kf[m * WS + col];
+        }
+        tab[i * NT + tid] = make_float4(v[0].x * scale, v[0].y * scale, v[1].x * scale, v[1].y * scale);
+    }
+    if (tid < 4) {
+        for (int s = 0; s < 32; ++s) {
+            const int m = p3_slot_m(tid, s);
+            const float2 k0 = Kf[m * WS], k64 = Kf[m * WS + 64];
+            const float h = 0.5f * scale;
+            tab[KT_F4 + s * 4 + tid] = make_float4((k0.x + k64.x) * h, (k0.y + k64.y) * h, (k0.x - k64.x) * h, (k0.y - k64.y) * h);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// plain 2-D FFT of real 128x128 images -> full complex spectrum (used to build K = fftn(fftshift(kernel)) like
+// leniax/kernels.py:145-149 without cuFFT).  One CTA per image, phases P1..P3a of the resident pipeline.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool B0, int S>
+__device__ __forceinline__ void rfft2_col0(const float2* v, float2* out, int tid) {
+    if constexpr (S < 32) {
+        const int m = p3_slot_m(tid, S);
+        const float2 g = v[S], gp = v[col0_partner(B0, S)];
+        // v = 2 (F0 + i F64):  F0 = (G + conj G')/4, F64 = -i (G - conj G')/4
+        out[m * WS] = make_float2((g.x + gp.x) * 0.25f, (g.y - gp.y) * 0.25f);
+        out[m * WS + 64] = make_float2((g.y + gp.y) * 0.25f, (gp.x - g.x) * 0.25f);
+        rfft2_col0<B0, S + 1>(v, out, tid);
+    }
+}
+__global__ void __launch_bounds__(NT) lnx_rfft2_kernel(const float* __restrict__ images, float2* __restrict__ spectra) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float2* W = reinterpret_cast<float2*>(smem);
+    const int tid = threadIdx.x, l = t_sub(tid) & 3;
+    const float* img = images + (size_t)blockIdx.x * (WS * WS);
+    float2* out = spectra + (size_t)blockIdx.x * (WS * WS);
+    Regs R;
+    init_twiddles(tid, R, c_tw128);
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) R.v[j] = make_float2(img[cell_row(tid, 0) * WS + 4 * j + l], img[cell_row(tid, 1) * WS + 4 * j + l]);
+    phase1(tid, R, W);
+    __syncthreads();
+    phase2_load(tid, R, W);
+    __syncthreads();
+    phase2_compute_store(tid, R, W);
+    __syncthreads();
+    phase3_load_fft(tid, R, W);
+    const int col = t_col(tid);
+    if (col != 0) {
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const int m = p3_slot_m(tid, s);
+            const float2 v = make_float2(R.v[s].x * 0.5f, R.v[s].y * 0.5f);
+            out[m * WS + col] = v;
+            out[((WS - m) & (WS - 1)) * WS + (WS - col)] = make_float2(v.x, -v.y);
+        }
+    } else if (tid == 0) {
+        rfft2_col0<true, 0>(R.v, out, tid);
+    } else {
+        rfft2_col0<false, 0>(R.v, out, tid);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FP32 FMA-throughput probe: the roofline denominator for the resident kernels (MEASURED_PEAKS.json has no FP32 entry)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) lnx_fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456f) out[0] = r;  // never true in practice; keeps the loop alive
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// shared helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_state_regs(Regs& R, const float4* A4, int tid) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 c0 = A4[i * NT + tid], c1 = A4[(8 + i) * NT + tid];
+        R.v[4 * i + 0] = make_float2(c0.x, c1.x);
+        R.v[4 * i + 1] = make_float2(c0.y, c1.y);
+        R.v[4 * i + 2] = make_float2(c0.z, c1.z);
+        R.v[4 * i + 3] = make_float2(c0.w, c1.w);
+    }
+}
+// gather one channel image [128][128] (row major, global) into the thread-private state layout
+__device__ __forceinline__ void gather_state(float4* A4, const float* img, int tid) {
+    const int l = t_sub(tid) & 3;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const float* row = img + cell_row(tid, i >> 3) * WS + 16 * (i & 7) + l;
+        A4[i * NT + tid] = make_float4(__ldg(row), __ldg(row + 4), __ldg(row + 8), __ldg(row + 12));
+    }
+}
+__device__ __forceinline__ void scatter_state(float* img, const float4* A4, int tid) {
+    const int l = t_sub(tid) & 3;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        float* row = img + cell_row(tid, i >> 3) * WS + 16 * (i & 7) + l;
+        const float4 c = A4[i * NT + tid];
+        row[0] = c.x;
+        row[4] = c.y;
+        row[8] = c.z;
+        row[12] = c.w;
+    }
+}
+
+// statistics warp: reduce the partials of one step and finalise (all lanes redundantly, lane 0 publishes)
+__device__ __forceinline__ float stats_step(const RunArgs& P, const float* part, int npart, int lane, int t, int sol, int init,
+                                            StatsCarry& S) {
+    float totals[NPART_MAX];
+#pragma unroll
+    for (int k = 0; k < NPART_MAX; ++k) {
+        float a = 0.f;
+        if (k < npart) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a += part[k * NT + lane + 32 * i];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        }
+        totals[k] = a;
+    }
+    float row[ST_COUNT], cm[MAX_C];
+    const float sc = stats_finalize(totals, P.C, t, P.R, P.stats_dt, S, row, cm);
+    if (lane == 0) {
+        const size_t plane = (size_t)P.n_sols * P.max_iter * P.n_init;
+        const size_t idx = ((size_t)sol * P.max_iter + t) * P.n_init + init;
+#pragma unroll
+        for (int k = 0; k < ST_COUNT; ++k) P.stats[k * plane + idx] = row[k];
+        for (int c = 0; c < P.C; ++c) P.channel_mass[idx * P.C + c] = cm[c];
+    }
+    return sc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fused kernel: C = K = 1
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FUSED_SMEM = 65536 * 3 + KPQ_F4 * 16 + NPART_FUSED * NT * 4 + 64;
+
+template <int GF, int SF, bool NP>
+__global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float2* W = reinterpret_cast<float2*>(smem);
+    float4* A4 = reinterpret_cast<float4*>(smem + 65536);
+    float4* Kt = reinterpret_cast<float4*>(smem + 131072);
+    float4* Kpq = reinterpret_cast<float4*>(smem + 196608);
+    float* part = reinterpret_cast<float*>(smem + 196608 + KPQ_F4 * 16);
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 196608 + KPQ_F4 * 16 + NPART_FUSED * NT * 4);
+
+    const int tid = threadIdx.x;
+    const int n_worlds = P.n_sols * P.n_init;
+    const bool early = (P.flags & LNX_RUN_EARLY_STOP) != 0;
+    Regs R;
+    if (tid < NT) init_twiddles(tid, R, c_tw128);
+    int loaded_sol = -1;
+
+    for (;;) {
+        if (tid == NT) {
+            ctrl->world = atomicAdd(P.queue, 1);
+            ctrl->shift0 = ctrl->shift1 = 0;
+            ctrl->stop = 0;
+        }
+        __syncthreads();
+        const int world = ctrl->world;
+        if (world >= n_worlds) break;
+        const int sol = world / P.n_init, init = world - sol * P.n_init;
+
+        if (tid < NT) {
+            // ------------------------------------------------ compute threads ------------------------------------------
+            gather_state(A4, P.cells0 + (size_t)world * (WS * WS), tid);
+            if (sol != loaded_sol) {
+                const float4* src = P.table + (size_t)sol * KTAB_F4;
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) Kt[i * NT + tid] = __ldg(src + i * NT + tid);
+                if (tid < KPQ_F4) Kpq[tid] = __ldg(src + KT_F4 + tid);
+                loaded_sol = sol;
+            }
+            FusedConsts fc;
+            {
+                const float m = __ldg(P.gf_params + (size_t)sol * 2), s = __ldg(P.gf_params + (size_t)sol * 2 + 1);
+                fc.gf = gf_prepare(GF, m, s);
+                fc.w = __ldg(P.weights + sol);
+                fc.inv_wsum = P.mean ? 1.0f / fc.w : 1.0f;
+                fc.dt = __ldg(P.dt + sol);
+            }
+            bar_sync(BAR_COMPUTE, NT);  // Kt / Kpq visible to every compute thread
+
+            bool stopped = false;
+            for (int t = 0; t < P.max_iter; ++t) {
+                load_state_regs(R, A4, tid);
+                __syncwarp();  // previous step's phase5 reads of this group's region are complete
+                phase1(tid, R, W);
+                __syncwarp();
+                phase2_load(tid, R, W);
+                __syncwarp();
+                phase2_compute_store(tid, R, W);
+                bar_sync(BAR_COMPUTE, NT);
+                phase3_load_fft(tid, R, W);
+                phase3_multiply(tid, R, Kt, Kpq);
+                phase3_ifft_store(tid, R, W);
+                bar_sync(BAR_COMPUTE, NT);
+                phase4_load(tid, R, W);
+                __syncwarp();
+                phase4_compute_store(tid, R, W);
+                __syncwarp();
+                phase5_load(tid, R, W);
+                phase5_ifft(R);
+                if (t > 0) {
+                    bar_sync(BAR_CARRY, NTHREADS);  // statistics of step t-1 are final: shift carry + stop flag
+                    if (ctrl->stop) {
+                        stopped = true;
+                        break;
+                    }
+                }
+                cells_fused<GF, SF, NP>(tid, R.v, A4, fc, ctrl->shift0, ctrl->shift1, part);
+                __threadfence_block();
+                bar_arrive(BAR_PARTIALS, NTHREADS);
+            }
+            if (!stopped) bar_sync(BAR_CARRY, NTHREADS);
+            if (P.final_cells) scatter_state(P.final_cells + (size_t)world * (WS * WS), A4, tid);
+        } else {
+            // ------------------------------------------------ statistics warp ------------------------------------------
+            const int lane = tid - NT;
+            StatsCarry S;
+            S.reset();
+            for (int t = 0; t < P.max_iter; ++t) {
+                bar_sync(BAR_PARTIALS, NTHREADS);
+                const float sc = stats_step(P, part, NPART_FUSED, lane, t, sol, init, S);
+                const int stop = (early && sc == 0.f && t + 1 >= 128) ? 1 : 0;
+                if (lane == 0) {
+                    ctrl->shift0 = S.shift[0];
+                    ctrl->shift1 = S.shift[1];
+                    ctrl->stop = stop;
+                }
+                __threadfence_block();
+                bar_arrive(BAR_CARRY, NTHREADS);
+                if (stop) break;
+            }
+            if (lane == 0) P.n_alive[world] = S.n_alive;
+        }
+        __syncthreads();  // world done: ctrl / part / A4 can be reused
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// generic kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct GenericConsts {
+    GfConst gf[MAX_K];
+    float w[MAX_C * MAX_K];
+    float inv_wsum[MAX_C];
+    float dt;
+};
+constexpr int GENERIC_SMEM = 65536 + NPART_MAX * NT * 4 + 64 + (int)sizeof(GenericConsts);
+constexpr int PLANE_F4 = 16 * NT;  // float4 per thread-private image
+
+__global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArgs P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float2* W = reinterpret_cast<float2*>(smem);
+    float* part = reinterpret_cast<float*>(smem + 65536);
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 65536 + NPART_MAX * NT * 4);
+    GenericConsts* gc = reinterpret_cast<GenericConsts*>(smem + 65536 + NPART_MAX * NT * 4 + 64);
+
+    const int tid = threadIdx.x;
+    const int C = P.C, K = P.K;
+    const int n_worlds = P.n_sols * P.n_init;
+    const int npart = PT_FIXED + C;
+    const bool early = (P.flags & LNX_RUN_EARLY_STOP) != 0;
+    float4* Ast = P.scratch + (size_t)blockIdx.x * (3 * C) * PLANE_F4;  // [C] states
+    float4* Sp = Ast + (size_t)C * PLANE_F4;                            // [C] forward spectra (P3 layout)
+    float4* Fa = Sp + (size_t)C * PLANE_F4;                             // [C] field accumulators
+    Regs R;
+    if (tid < NT) init_twiddles(tid, R, c_tw128);
+
+    for (;;) {
+        if (tid == NT) {
+            ctrl->world = atomicAdd(P.queue, 1);
+            ctrl->shift0 = ctrl->shift1 = 0;
+            ctrl->stop = 0;
+        }
+        __syncthreads();
+        const int world = ctrl->world;
+        if (world >= n_worlds) break;
+        const int sol = world / P.n_init, init = world - sol * P.n_init;
+        if (tid < K) gc->gf[tid] = gf_prepare(P.gf_id[tid], P.gf_params[((size_t)sol * K + tid) * 2], P.gf_params[((size_t)sol * K + tid) * 2 + 1]);
+        if (tid < C * K) gc->w[tid] = P.weights[(size_t)sol * C * K + tid];
+        if (tid < C) {
+            float sum = 0.f;
+            for (int k = 0; k < K; ++k) sum += P.weights[((size_t)sol * C + tid) * K + k];
+            gc->inv_wsum[tid] = P.mean ? 1.0f / sum : 1.0f;
+        }
+        if (tid == 0) gc->dt = P.dt[sol];
+        __syncthreads();
+
+        if (tid < NT) {
+            const float dt = gc->dt;
+            const int l = t_sub(tid) & 3;
+            for (int c = 0; c < C; ++c) gather_state(Ast + (size_t)c * PLANE_F4, P.cells0 + ((size_t)world * C + c) * (WS * WS), tid);
+            const float4* tab = P.table + (size_t)sol * K * KTAB_F4;
+            bool stopped = false;
+            for (int t = 0; t < P.max_iter; ++t) {
+                const size_t tstep = ((size_t)sol * P.max_iter + t) * P.n_init + init;  // index of this world-step in trajectories
+                // ---- forward transforms of every channel ----
+                for (int c = 0; c < C; ++c) {
+                    load_state_regs(R, Ast + (size_t)c * PLANE_F4, tid);
+                    __syncwarp();
+                    phase1(tid, R, W);
+                    __syncwarp();
+                    phase2_load(tid, R, W);
+                    __syncwarp();
+                    phase2_compute_store(tid, R, W);
+                    bar_sync(BAR_COMPUTE, NT);
+                    phase3_load_fft(tid, R, W);
+                    float4* sp = Sp + (size_t)c * PLANE_F4;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) sp[i * NT + tid] = make_float4(R.v[2 * i].x, R.v[2 * i].y, R.v[2 * i + 1].x, R.v[2 * i + 1].y);
+                    bar_sync(BAR_COMPUTE, NT);
+                }
+                // ---- one inverse transform per kernel, growth, accumulate into the target channels ----
+                unsigned touched = 0;
+                float cnt_p = 0.f;
+                for (int k = 0; k < K; ++k) {
+                    const float4* sp = Sp + (size_t)P.c_in[k] * PLANE_F4;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 s4 = sp[i * NT + tid];
+                        R.v[2 * i] = make_float2(s4.x, s4.y);
+                        R.v[2 * i + 1] = make_float2(s4.z, s4.w);
+                    }
+                    phase3_multiply(tid, R, tab + (size_t)k * KTAB_F4, tab + (size_t)k * KTAB_F4 + KT_F4);
+                    phase3_ifft_store(tid, R, W);
+                    bar_sync(BAR_COMPUTE, NT);
+                    phase4_load(tid, R, W);
+                    __syncwarp();
+                    phase4_compute_store(tid, R, W);
+                    __syncwarp();
+                    phase5_load(tid, R, W);
+                    bar_sync(BAR_COMPUTE, NT);  // W is free for the next kernel's spectrum
+                    phase5_ifft(R);
+                    if (P.potential_out) {
+                        float* img = P.potential_out + (tstep * K + k) * (WS * WS);
+#pragma unroll 8
+                        for (int j = 0; j < 32; ++j) {
+                            img[cell_row(tid, 0) * WS + 4 * j + l] = R.v[j].x;
+                            img[cell_row(tid, 1) * WS + 4 * j + l] = R.v[j].y;
+                        }
+                    }
+                    const GfConst g = gc->gf[k];
+                    const int gf = P.gf_id[k];
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j) {
+                        cnt_p += (R.v[j].x > EPS ? 1.f : 0.f) + (R.v[j].y > EPS ? 1.f : 0.f);
+                        R.v[j].x = growth_dyn<true>(gf, R.v[j].x, g);
+                        R.v[j].y = growth_dyn<true>(gf, R.v[j].y, g);
+                    }
+                    for (int c = 0; c < C; ++c) {
+                        const float w = gc->w[c * K + k];
+                        if (w == 0.f) continue;
+                        float4* fa = Fa + (size_t)c * PLANE_F4;
+                        const bool first = !(touched & (1u << c));
+                        touched |= 1u << c;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+                            if (!first) {
+                                f0 = fa[i * NT + tid];
+                                f1 = fa[(8 + i) * NT + tid];
+                            }
+                            f0.x += w * R.v[4 * i + 0].x; f0.y += w * R.v[4 * i + 1].x; f0.z += w * R.v[4 * i + 2].x; f0.w += w * R.v[4 * i + 3].x;
+                            f1.x += w * R.v[4 * i + 0].y; f1.y += w * R.v[4 * i + 1].y; f1.z += w * R.v[4 * i + 2].y; f1.w += w * R.v[4 * i + 3].y;
+                            fa[i * NT + tid] = f0;
+                            fa[(8 + i) * NT + tid] = f1;
+                        }
+                    }
+                }
+                if (t > 0) {
+                    bar_sync(BAR_CARRY, NTHREADS);
+                    if (ctrl->stop) {
+                        stopped = true;
+                        break;
+                    }
+                }
+                // ---- state update + statistics partials ----
+                const int sh0 = ctrl->shift0, sh1 = ctrl->shift1;
+                const float xr0 = rolled_coord(cell_row(tid, 0), sh0), xr1 = rolled_coord(cell_row(tid, 1), sh0);
+                const float cbase = (float)(((l - sh1) & (WS - 1)) - WS / 2);
+                float mx_r = 0.f, mx2_r = 0.f, gx_r = 0.f, mxc = 0.f, mx2c = 0.f, gxc = 0.f, cnt_a = 0.f, cnt_g = 0.f, g00 = 0.f;
+                for (int c = 0; c < C; ++c) {
+                    float4* st = Ast + (size_t)c * PLANE_F4;
+                    const float4* fa = Fa + (size_t)c * PLANE_F4;
+                    const float inv = gc->inv_wsum[c];
+                    const bool has = (touched >> c) & 1u;
+                    float* cimg = P.cells_out ? P.cells_out + (tstep * C + c) * (WS * WS) : nullptr;
+                    float* fimg = P.field_out ? P.field_out + (tstep * C + c) * (WS * WS) : nullptr;
+                    CellAcc A;
+                    A.clear();
+#pragma unroll 2
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 c0 = st[i * NT + tid], c1 = st[(8 + i) * NT + tid];
+                        float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+                        if (has) {
+                            f0 = fa[i * NT + tid];
+                            f1 = fa[(8 + i) * NT + tid];
+                        }
+                        const float a0[4] = {c0.x, c0.y, c0.z, c0.w}, a1[4] = {c1.x, c1.y, c1.z, c1.w};
+                        const float q0[4] = {f0.x * inv, f0.y * inv, f0.z * inv, f0.w * inv}, q1[4] = {f1.x * inv, f1.y * inv, f1.z * inv, f1.w * inv};
+                        float n0[4], n1[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * i + e;
+                            acc_cells(A, col_coord(cbase, j), a0[e], a1[e], q0[e], q1[e]);
+                            n0[e] = state_update_dyn<true>(P.state_fn, a0[e], q0[e], dt);
+                            n1[e] = state_update_dyn<true>(P.state_fn, a1[e], q1[e], dt);
+                            if (cimg) {
+                                cimg[cell_row(tid, 0) * WS + 4 * j + l] = a0[e];
+                                cimg[cell_row(tid, 1) * WS + 4 * j + l] = a1[e];
+                            }
+                            if (fimg) {
+                                fimg[cell_row(tid, 0) * WS + 4 * j + l] = q0[e];
+                                fimg[cell_row(tid, 1) * WS + 4 * j + l] = q1[e];
+                            }
+                        }
+                        st[i * NT + tid] = make_float4(n0[0], n0[1], n0[2], n0[3]);
+                        st[(8 + i) * NT + tid] = make_float4(n1[0], n1[1], n1[2], n1[3]);
+                    }
+                    part[(PT_M00_C0 + c) * NT + tid] = A.sa0 + A.sa1;
+                    mx_r += xr0 * A.sa0 + xr1 * A.sa1;
+                    mx2_r += (xr0 * xr0) * A.sa0 + (xr1 * xr1) * A.sa1;
+                    gx_r += xr0 * A.sg0 + xr1 * A.sg1;
+                    mxc += A.mxc;
+                    mx2c += A.mx2c;
+                    gxc += A.gxc;
+                    cnt_a += A.cnt_a;
+                    cnt_g += A.cnt_g;
+                    g00 += A.sg0 + A.sg1;
+                }
+                part[PT_CNT_A * NT + tid] = cnt_a;
+                part[PT_G00 * NT + tid] = g00;
+                part[PT_CNT_G * NT + tid] = cnt_g;
+                part[PT_CNT_P * NT + tid] = cnt_p;
+                part[PT_MX_R * NT + tid] = mx_r;
+                part[PT_MX_C * NT + tid] = mxc;
+                part[PT_MX2_R * NT + tid] = mx2_r;
+                part[PT_MX2_C * NT + tid] = mx2c;
+                part[PT_GX_R * NT + tid] = gx_r;
+                part[PT_GX_C * NT + tid] = gxc;
+                __threadfence_block();
+                bar_arrive(BAR_PARTIALS, NTHREADS);
+            }
+            if (!stopped) bar_sync(BAR_CARRY, NTHREADS);
+            if (P.final_cells)
+                for (int c = 0; c < C; ++c) scatter_state(P.final_cells + ((size_t)world * C + c) * (WS * WS), Ast + (size_t)c * PLANE_F4, tid);
+        } else {
+            const int lane = tid - NT;
+            StatsCarry S;
+            S.reset();
+            for (int t = 0; t < P.max_iter; ++t) {
+                bar_sync(BAR_PARTIALS, NTHREADS);
+                const float sc = stats_step(P, part, npart, lane, t, sol, init, S);
+                const int stop = (early && sc == 0.f && t + 1 >= 128) ? 1 : 0;
+                if (lane == 0) {
+                    ctrl->shift0 = S.shift[0];
+                    ctrl->shift1 = S.shift[1];
+                    ctrl->stop = stop;
+                }
+                __threadfence_block();
+                bar_arrive(BAR_CARRY, NTHREADS);
+                if (stop) break;
+            }
+            if (lane == 0) P.n_alive[world] = S.n_alive;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace lnx
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+using namespace lnx;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define LNX_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return fail(LNX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct lnx_plan {
+    lnx_desc d;
+    int device;
+    int sm_count;
+};
+
+// one-time per-device setup: architecture check (no fallback), twiddle constants, dynamic shared memory opt-in
+static int ensure_device_init(int* dev_out, int* sms_out) {
+    static bool done[64] = {false};
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LNX_ERR_NO_DEVICE, "no CUDA device: %s (leniax_b200 has no CPU fallback)", cudaGetErrorString(e));
+    }
+    if (dev < 0 || dev >= 64) return fail(LNX_ERR_INVALID, "device index %d out of range", dev);
+    if (!done[dev]) {
+        cudaDeviceProp prop;
+        LNX_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10)
+            return fail(LNX_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", dev, prop.major,
+                        prop.minor);
+        float2 tw[128];
+        for (int k = 0; k < 128; ++k) tw[k] = make_float2(Tw128::c[k], Tw128::s[k]);
+        LNX_CUDA(cudaMemcpyToSymbol(c_tw128, tw, sizeof(tw)));
+        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, GENERIC_SMEM));
+        LNX_CUDA(cudaFuncSetAttribute(lnx_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        sms[dev] = prop.multiProcessorCount;
+        done[dev] = true;
+    }
+    if (dev_out) *dev_out = dev;
+    if (sms_out) *sms_out = sms[dev];
+    return LNX_OK;
+}
+
+extern "C" {
+
+int lnx_version(void) { return LNX_VERSION; }
+const char* lnx_last_error(void) { return g_err; }
+
+int lnx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int lnx_plan_create(const lnx_desc* d, lnx_plan** out) {
+    if (!d || !out) return fail(LNX_ERR_INVALID, "lnx_plan_create: null argument");
+    *out = nullptr;
+    if (d->nb_dims != 2 || d->dims[0] != WS || d->dims[1] != WS)
+        return fail(LNX_ERR_UNSUPPORTED, "only 2-D %dx%d worlds are built in this version (got nb_dims=%d, dims=%d x %d)", WS, WS,
+                    d->nb_dims, d->dims[0], d->dims[1]);
+    if (d->nb_channels < 1 || d->nb_channels > MAX_C) return fail(LNX_ERR_INVALID, "nb_channels must be in [1, %d]", MAX_C);
+    if (d->nb_kernels < 1 || d->nb_kernels > MAX_K) return fail(LNX_ERR_INVALID, "nb_kernels must be in [1, %d]", MAX_K);
+    if (d->nb_slots < d->nb_kernels) return fail(LNX_ERR_INVALID, "nb_slots < nb_kernels");
+    for (int k = 0; k < d->nb_kernels; ++k) {
+        if (d->c_in[k] < 0 || d->c_in[k] >= d->nb_channels) return fail(LNX_ERR_INVALID, "c_in[%d] out of range", k);
+        if (d->slot[k] < 0 || d->slot[k] >= d->nb_slots) return fail(LNX_ERR_INVALID, "slot[%d] out of range", k);
+        if (d->gf_id[k] < 0 || d->gf_id[k] >= GF_COUNT) return fail(LNX_ERR_INVALID, "gf_id[%d]: unknown growth function", k);
+    }
+    if (d->state_fn < 0 || d->state_fn >= SF_COUNT) return fail(LNX_ERR_INVALID, "unknown state function %d", d->state_fn);
+    if (!(d->R > 0.f) || !(d->stats_dt > 0.f)) return fail(LNX_ERR_INVALID, "R and stats_dt must be positive");
+
+    int dev = 0, sms = 0;
+    const int rc = ensure_device_init(&dev, &sms);
+    if (rc != LNX_OK) return rc;
+    lnx_plan* p = new (std::nothrow) lnx_plan;
+    if (!p) return fail(LNX_ERR_INVALID, "out of host memory");
+    p->d = *d;
+    p->device = dev;
+    p->sm_count = sms;
+    *out = p;
+    return LNX_OK;
+}
+
+int lnx_plan_destroy(lnx_plan* p) {
+    if (!p) return LNX_OK;
+    delete p;
+    return LNX_OK;
+}
+
+size_t lnx_kernel_table_bytes(const lnx_plan* p) { return p ? (size_t)p->d.nb_kernels * KTAB_F4 * sizeof(float4) : 0; }
+
+size_t lnx_workspace_bytes(const lnx_plan* p) {
+    if (!p) return 0;
+    // 256 B header (world queue counter) + per-CTA scratch of the generic kernel: [3][C] thread-private images
+    return 256 + (size_t)p->sm_count * 3 * p->d.nb_channels * PLANE_F4 * sizeof(float4);
+}
+
+int lnx_kernels_prepare(const lnx_plan* p, int32_t n_sols, const void* K_fft, void* table, void* stream) {
+    if (!p || !K_fft || !table || n_sols < 1) return fail(LNX_ERR_INVALID, "lnx_kernels_prepare: bad argument");
+    PrepArgs a;
+    a.K_fft = static_cast<const float2*>(K_fft);
+    a.table = static_cast<float4*>(table);
+    a.K = p->d.nb_kernels;
+    a.nb_slots = p->d.nb_slots;
+    for (int k = 0; k < a.K; ++k) a.slot[k] = p->d.slot[k];
+    lnx_prepare_kernel<<<n_sols * a.K, NT, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    LNX_CUDA(cudaGetLastError());
+    return LNX_OK;
+}
+
+int lnx_rfft2(const lnx_plan* p, int32_t n_images, const float* images, void* spectra, void* stream) {
+    (void)p;  // the plan is optional here
+    if (!images || !spectra || n_images < 1) return fail(LNX_ERR_INVALID, "lnx_rfft2: bad argument");
+    const int rc = ensure_device_init(nullptr, nullptr);
+    if (rc != LNX_OK) return rc;
+    lnx_rfft2_kernel<<<n_images, NT, 65536, static_cast<cudaStream_t>(stream)>>>(images, static_cast<float2*>(spectra));
+    LNX_CUDA(cudaGetLastError());
+    return LNX_OK;
+}
+
+int lnx_measure_fp32_peak(int32_t iters, double* tflops, double* ms, void* stream) {
+    if (iters < 1 || !tflops) return fail(LNX_ERR_INVALID, "lnx_measure_fp32_peak: bad argument");
+    int dev = 0, sms = 0;
+    const int rc = ensure_device_init(&dev, &sms);
+    if (rc != LNX_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* d_out = nullptr;
+    LNX_CUDA(cudaMalloc(&d_out, 64));
+    cudaEvent_t e0, e1;
+    LNX_CUDA(cudaEventCreate(&e0));
+    LNX_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 4, block = 512;
+    lnx_fp32_peak_kernel<<<grid, block, 0, st>>>(d_out, iters / 8 + 1, 0.999f, 0.001f);  // warm-up
+    LNX_CUDA(cudaEventRecord(e0, st));
+    lnx_fp32_peak_kernel<<<grid, block, 0, st>>>(d_out, iters, 0.999f, 0.001f);
+    LNX_CUDA(cudaEventRecord(e1, st));
+    LNX_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    LNX_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    const double flops = 2.0 * 128.0 * (double)iters * (double)grid * (double)block;
+    *tflops = flops / ((double)t * 1e-3) / 1e12;
+    if (ms) *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return LNX_OK;
+}
+
+static bool use_fused(const lnx_plan* p, bool trajectory) {
+    const lnx_desc& d = p->d;
+    return d.nb_channels == 1 && d.nb_kernels == 1 && !trajectory && d.gf_id[0] == GF_POLY_QUAD4 && d.state_fn == SF_V1;
+}
+
+const char* lnx_run_scan_variant(const lnx_plan* p, int32_t with_trajectory) {
+    if (!p) return "";
+    return use_fused(p, with_trajectory != 0) ? "fused" : "generic";
+}
+
+int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_run_iter, uint32_t run_flags, const float* cells0,
+                 const void* table, const float* gf_params, const float* weights, const float* dt, float* stats, float* channel_mass,
+                 float* n_alive, float* final_cells, float* cells_out, float* field_out, float* potential_out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    if (!p) return fail(LNX_ERR_INVALID, "lnx_run_scan: null plan");
+    if (n_sols < 1 || n_init < 1) return fail(LNX_ERR_INVALID, "lnx_run_scan: n_sols and n_init must be >= 1");
+    if (max_run_iter < 1) return fail(LNX_ERR_INVALID, "max_run_iter must be positive, value given: %d", max_run_iter);  // runner.py:51
+    if (!cells0 || !table || !gf_params || !weights || !dt || !stats || !channel_mass || !n_alive)
+        return fail(LNX_ERR_INVALID, "lnx_run_scan: null required pointer");
+    const bool trajectory = cells_out || field_out || potential_out;
+    const bool fused = use_fused(p, trajectory);
+    if (!workspace || workspace_bytes < (fused ? (size_t)256 : lnx_workspace_bytes(p)))
+        return fail(LNX_ERR_INVALID, "lnx_run_scan: workspace too small (%zu < %zu)", workspace_bytes, lnx_workspace_bytes(p));
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cells0 = cells0;
+    a.table = static_cast<const float4*>(table);
+    a.gf_params = gf_params;
+    a.weights = weights;
+    a.dt = dt;
+    a.stats = stats;
+    a.channel_mass = channel_mass;
+    a.n_alive = n_alive;
+    a.final_cells = final_cells;
+    a.cells_out = cells_out;
+    a.field_out = field_out;
+    a.potential_out = potential_out;
+    a.scratch = reinterpret_cast<float4*>(static_cast<unsigned char*>(workspace) + 256);
+    a.queue = static_cast<int*>(workspace);
+    a.n_sols = n_sols;
+    a.n_init = n_init;
+    a.max_iter = max_run_iter;
+    a.C = p->d.nb_channels;
+    a.K = p->d.nb_kernels;
+    a.state_fn = p->d.state_fn;
+    a.mean = p->d.weighted_average;
+    a.R = p->d.R;
+    a.stats_dt = p->d.stats_dt;
+    a.flags = run_flags;
+    for (int k = 0; k < a.K; ++k) {
+        a.c_in[k] = p->d.c_in[k];
+        a.gf_id[k] = p->d.gf_id[k];
+    }
+    LNX_CUDA(cudaMemsetAsync(a.queue, 0, sizeof(int), st));
+    const long long n_worlds = (long long)n_sols * n_init;
+    const int grid = (int)(n_worlds < p->sm_count ? n_worlds : p->sm_count);
+    if (fused) {
+        // NaN can only be born from s == 0 or a zero weight (0 * inf); the fast variant assumes neither.  The host
+        // cannot see device-side parameters without a sync, so the NaN-propagating variant is the default and the
+        // caller opts into the fast one with flag bit 8 (set by the Python layer after checking the parameters).
+        if (run_flags & LNX_RUN_ASSUME_FINITE)
+            lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false><<<grid, NTHREADS, FUSED_SMEM, st>>>(a);
+        else
+            lnx_world128_fused<GF_POLY_QUAD4, SF_V1, true><<<grid, NTHREADS, FUSED_SMEM, st>>>(a);
+    } else {
+        lnx_world128_generic<<<grid, NTHREADS, GENERIC_SMEM, st>>>(a);
+    }
+    LNX_CUDA(cudaGetLastError());
+    return LNX_OK;
+}
+
+}  // extern "C"

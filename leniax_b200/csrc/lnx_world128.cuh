@@ -1,0 +1,353 @@
+// Per-thread phases of the resident 128x128 Lenia step (host+device code).
+//
+// One CTA owns one world.  256 compute threads hold the 8192-point half spectrum (32 complex per thread) and walk
+// five phases per convolution, exchanging data only through one 64 KB shared buffer `W`:
+//
+//   P1  rows : radix-32 DIF over j      (n = 4j + l)                      thread (p,l): packed rows p / p+64
+//   P2  rows : twiddle + radix-4 over l, untangle the two packed real rows,
+//       cols : radix-8 DIF over i       (r = r1 + 16 i) + twiddle         thread (r1,a): 8 rows x 4 spectral columns
+//   P3  cols : radix-16 DIF over r1, multiply by the kernel spectrum,
+//              radix-16 inverse DIT                                      thread (col,bidx): 2 x 16 column entries
+//   P4  mirror of P2, P5 mirror of P1 -> potential of rows p (real part) and p+64 (imaginary part)
+//
+// Follows leniax/core.py:52-102 (get_potential_fft: fftn * K, real(ifftn)) restricted to 2-D 128x128 worlds; the
+// real-input symmetry is exploited (two real rows per complex FFT, half spectrum, DC/Nyquist columns packed).
+#pragma once
+#include "lnx_fft.cuh"
+
+namespace lnx {
+
+constexpr int WS = 128;           // world side
+constexpr int NT = 256;           // compute threads per world
+constexpr int REGION = 512;       // complex elements per exchange region (one per r1 / row group)
+constexpr int W_COMPLEX = 16 * REGION;
+
+struct Regs {
+    float2 v[32];      // working set (re-used by every phase)
+    float2 twr[2][3];  // row twiddles   W128^(l * k1_s), l = 1..3   (P2/P4 mapping)
+    float2 twc[7];     // column twiddles W128^(r1 * m2), m2 = 1..7  (P2/P4 mapping)
+};
+
+// ---- thread index decompositions -------------------------------------------------------------------------------
+LNX_HD int t_group(int tid) { return tid >> 4; }        // G = r1 = p0, 0..15 (two groups per warp)
+LNX_HD int t_sub(int tid) { return tid & 15; }          // a (P2/P4) or 4*q + l (P1/P5)
+LNX_HD int t_col(int tid) { return tid >> 2; }          // P3: spectral column 0..63 (0 = packed DC|Nyquist)
+LNX_HD int t_bidx(int tid) { return tid & 3; }          // P3: unit (m2 pair) 0..3
+
+// k1 handled by P2/P4 thread `a` for s = 0/1
+LNX_HD int k1_of(int a, int s) { return s == 0 ? a : (a == 0 ? 16 : 32 - a); }
+// spectral column c (0..3) written by P2/P4 thread `a`
+LNX_HD int col_of(int a, int c) {
+    if (a == 0) return c == 0 ? 0 : (c == 1 ? 32 : (c == 2 ? 16 : 48));
+    return c == 0 ? a : (c == 1 ? a + 32 : (c == 2 ? 32 - a : 64 - a));
+}
+
+// ---- shared-memory layouts (complex indices inside a 512-element region) -----------------------------------------
+// E1 view [q][k1][l] with XOR swizzles: conflict-free for 64-bit accesses of (q,l) lanes at fixed k1 (P1/P5) and
+// 128-bit accesses of lanes a -> k1 in {a, 32-a} at fixed q (P2/P4).
+LNX_HD int e1_addr(int q, int k1, int l) {
+    return q * 128 + (((k1 & 28) | ((k1 ^ q) & 3)) << 2) + ((((l >> 1) ^ (k1 >> 2)) & 1) << 1) + (l & 1);
+}
+// E2 view [col][unit u][2]: unit = the pair of m2 handled together by a P3 thread.
+LNX_HD int e2_addr(int col, int u) { return col * 8 + ((u ^ ((col >> 1) & 3)) << 1); }
+
+// ---- twiddle setup (once per kernel) ------------------------------------------------------------------------------
+LNX_HD void init_twiddles(int tid, Regs& R, const float2* tw128 /* [128] = (cos, sin)(2 pi k / 128) */) {
+    const int a = t_sub(tid), r1 = t_group(tid);
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int l = 1; l < 4; ++l) R.twr[s][l - 1] = tw128[(l * k1_of(a, s)) & 127];
+#pragma unroll
+    for (int m2 = 1; m2 < 8; ++m2) R.twc[m2 - 1] = tw128[(r1 * m2) & 127];
+}
+// multiply by W = (c, -s) (forward) or conj (inverse), tw = (c, s)
+LNX_HD float2 tw_fwd(float2 d, float2 tw) { return make_float2(d.x * tw.x + d.y * tw.y, d.y * tw.x - d.x * tw.y); }
+LNX_HD float2 tw_inv(float2 d, float2 tw) { return make_float2(d.x * tw.x - d.y * tw.y, d.y * tw.x + d.x * tw.y); }
+
+// =================================================================================================================
+// P1: v[j] = (a[p][4j+l], a[p+64][4j+l]) already loaded by the caller.  radix-32 DIF, store E1.
+// =================================================================================================================
+template <int POS>
+LNX_HD void p1_store(const Regs& R, float2* reg, int q, int l) {
+    if constexpr (POS < 32) {
+        reg[e1_addr(q, bitrev(POS, 5), l)] = R.v[POS];
+        p1_store<POS + 1>(R, reg, q, l);
+    }
+}
+LNX_HD void phase1(int tid, Regs& R, float2* W) {
+    const int sub = t_sub(tid), q = sub >> 2, l = sub & 3;
+    fft_dif<32>(R.v);
+    p1_store<0>(R, W + t_group(tid) * REGION, q, l);
+}
+
+// =================================================================================================================
+// P2: load E1 -> (syncwarp by caller) -> row twiddle, radix-4, untangle, column radix-8, column twiddle, store E2
+// =================================================================================================================
+LNX_HD void phase2_load(int tid, Regs& R, const float2* W) {
+    const int a = t_sub(tid);
+    const float4* reg4 = reinterpret_cast<const float4*>(W + t_group(tid) * REGION);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int k1 = k1_of(a, s);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 t = reg4[e1_addr(q, k1, 2 * h) >> 1];
+                R.v[q * 8 + s * 4 + 2 * h] = make_float2(t.x, t.y);
+                R.v[q * 8 + s * 4 + 2 * h + 1] = make_float2(t.z, t.w);
+            }
+        }
+}
+
+// untangle one (Z[k], Z[128-k]) pair of a packed row into the spectra of its two real rows (factor 2 kept)
+LNX_HD void untangle_pair(float2 z, float2 zc, float2& A2, float2& B2) {
+    A2 = make_float2(z.x + zc.x, z.y - zc.y);
+    B2 = make_float2(z.y + zc.y, zc.x - z.x);
+}
+// inverse of the above: from the spectra A', B' of two real rows rebuild Z'[k] and Z'[128-k]
+LNX_HD void retangle_pair(float2 A, float2 B, float2& z, float2& zc) {
+    z = make_float2(A.x - B.y, A.y + B.x);
+    zc = make_float2(A.x + B.y, B.x - A.y);
+}
+
+template <bool A0>
+LNX_HD void p2_untangle(const float2* z /* [q*8 + s*4 + k2] */, float2* h /* [c*8 + i] */) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2* zq = z + q * 8;
+        if constexpr (A0) {
+            // k1 in {0,16}: columns {0|64 packed, 32, 16, 48}
+            h[0 * 8 + q] = make_float2(2.f * zq[0].x, 2.f * zq[2].x);
+            h[0 * 8 + q + 4] = make_float2(2.f * zq[0].y, 2.f * zq[2].y);
+            untangle_pair(zq[1], zq[3], h[1 * 8 + q], h[1 * 8 + q + 4]);          // 32 <-> 96
+            untangle_pair(zq[4 + 0], zq[4 + 3], h[2 * 8 + q], h[2 * 8 + q + 4]);  // 16 <-> 112
+            untangle_pair(zq[4 + 1], zq[4 + 2], h[3 * 8 + q], h[3 * 8 + q + 4]);  // 48 <-> 80
+        } else {
+            untangle_pair(zq[0], zq[4 + 3], h[0 * 8 + q], h[0 * 8 + q + 4]);  // a      <-> (32-a)+96
+            untangle_pair(zq[1], zq[4 + 2], h[1 * 8 + q], h[1 * 8 + q + 4]);  // a+32   <-> (32-a)+64
+            untangle_pair(zq[4 + 0], zq[3], h[2 * 8 + q], h[2 * 8 + q + 4]);  // 32-a   <-> a+96
+            untangle_pair(zq[4 + 1], zq[2], h[3 * 8 + q], h[3 * 8 + q + 4]);  // 64-a   <-> a+64
+        }
+    }
+}
+template <bool A0>
+LNX_HD void p4_retangle(const float2* h /* [c*8 + i] */, float2* z /* [q*8 + s*4 + k2] */) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2* zq = z + q * 8;
+        if constexpr (A0) {
+            zq[0] = make_float2(h[0 * 8 + q].x, h[0 * 8 + q + 4].x);
+            zq[2] = make_float2(h[0 * 8 + q].y, h[0 * 8 + q + 4].y);
+            retangle_pair(h[1 * 8 + q], h[1 * 8 + q + 4], zq[1], zq[3]);
+            retangle_pair(h[2 * 8 + q], h[2 * 8 + q + 4], zq[4 + 0], zq[4 + 3]);
+            retangle_pair(h[3 * 8 + q], h[3 * 8 + q + 4], zq[4 + 1], zq[4 + 2]);
+        } else {
+            retangle_pair(h[0 * 8 + q], h[0 * 8 + q + 4], zq[0], zq[4 + 3]);
+            retangle_pair(h[1 * 8 + q], h[1 * 8 + q + 4], zq[1], zq[4 + 2]);
+            retangle_pair(h[2 * 8 + q], h[2 * 8 + q + 4], zq[4 + 0], zq[3]);
+            retangle_pair(h[3 * 8 + q], h[3 * 8 + q + 4], zq[4 + 1], zq[2]);
+        }
+    }
+}
+
+// position (in the bit-reversed 8-point output) of the two m2 of unit u:  u0=(0,4) u1=(1,7) u2=(2,6) u3=(3,5)
+LNX_HDC int unit_m2(int u, int e) { return u == 0 ? (e == 0 ? 0 : 4) : (e == 0 ? u : 8 - u); }
+LNX_HDC int unit_pos(int u, int e) { return bitrev(unit_m2(u, e), 3); }
+
+LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W) {
+    const int a = t_sub(tid);
+    // row twiddle + radix-4 over l (forward, W4 = -i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            float2* y = R.v + q * 8 + s * 4;
+            const float2 y0 = y[0];
+            const float2 y1 = tw_fwd(y[1], R.twr[s][0]);
+            const float2 y2 = tw_fwd(y[2], R.twr[s][1]);
+            const float2 y3 = tw_fwd(y[3], R.twr[s][2]);
+            const float2 t0 = cadd(y0, y2), t1 = csub(y0, y2), t2 = cadd(y1, y3);
+            const float2 d = csub(y1, y3);
+            const float2 t3 = make_float2(d.y, -d.x);  // * (-i)
+            y[0] = cadd(t0, t2);
+            y[2] = csub(t0, t2);
+            y[1] = cadd(t1, t3);
+            y[3] = csub(t1, t3);
+        }
+    float2 h[32];
+    if (a == 0)
+        p2_untangle<true>(R.v, h);
+    else
+        p2_untangle<false>(R.v, h);
+    float4* reg4 = reinterpret_cast<float4*>(W + t_group(tid) * REGION);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float2* hc = h + c * 8;
+        fft_dif<8>(hc);  // over i; output position pos <-> m2 = bitrev3(pos)
+#pragma unroll
+        for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_fwd(hc[pos], R.twc[bitrev(pos, 3) - 1]);
+        const int col = col_of(a, c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 f = hc[unit_pos(u, 0)], g = hc[unit_pos(u, 1)];
+            reg4[e2_addr(col, u) >> 1] = make_float4(f.x, f.y, g.x, g.y);
+        }
+    }
+}
+
+// =================================================================================================================
+// P3: load E2 (all 16 regions), radix-16 DIF over r1  |  multiply  |  radix-16 inverse DIT, store back in place
+//     v[h*16 + pos], pos <-> m1 = bitrev4(pos), m = m2(bidx,h) + 8*m1
+// =================================================================================================================
+LNX_HD void phase3_load_fft(int tid, Regs& R, const float2* W) {
+    const float4* w4 = reinterpret_cast<const float4*>(W);
+    const int off = e2_addr(t_col(tid), t_bidx(tid)) >> 1;
+#pragma unroll
+    for (int r1 = 0; r1 < 16; ++r1) {
+        const float4 t = w4[r1 * (REGION / 2) + off];
+        R.v[r1] = make_float2(t.x, t.y);
+        R.v[16 + r1] = make_float2(t.z, t.w);
+    }
+    fft_dif<16>(R.v);
+    fft_dif<16>(R.v + 16);
+}
+LNX_HD void phase3_ifft_store(int tid, Regs& R, float2* W) {
+    ifft_dit<16>(R.v);
+    ifft_dit<16>(R.v + 16);
+    float4* w4 = reinterpret_cast<float4*>(W);
+    const int off = e2_addr(t_col(tid), t_bidx(tid)) >> 1;
+#pragma unroll
+    for (int r1 = 0; r1 < 16; ++r1)
+        w4[r1 * (REGION / 2) + off] = make_float4(R.v[r1].x, R.v[r1].y, R.v[16 + r1].x, R.v[16 + r1].y);
+}
+
+// slot of -m for the packed column (col 0): partner of slot (h,pos)
+LNX_HDC int col0_partner(int bidx0, int slot) {
+    const int h = slot >> 4, pos = slot & 15;
+    if (bidx0 && h == 0) return bitrev((16 - bitrev(pos, 4)) & 15, 4);  // m2 = 0: m1 <-> -m1
+    if (bidx0) return 16 + (15 - pos);                                  // m2 = 4: m1 <-> 15 - m1 (same h)
+    return (1 - h) * 16 + (15 - pos);                                   // m2 = b <-> 8-b, m1 <-> 15 - m1
+}
+
+// Kt: float4 [16][256] = complex multipliers for slots (2i, 2i+1) of thread tid (already scaled by 1/(2*128*128)).
+// Kpq: float4 [32][4] = (Kp, Kq) for slot s of threads 0..3 (packed DC|Nyquist column), see DESIGN.md §3.4.
+template <int I>
+LNX_HD void p3_mul_generic(Regs& R, const float4* Kt, int tid) {
+    if constexpr (I < 16) {
+        const float4 k = Kt[I * NT + tid];
+        R.v[2 * I] = cmul(R.v[2 * I], make_float2(k.x, k.y));
+        R.v[2 * I + 1] = cmul(R.v[2 * I + 1], make_float2(k.z, k.w));
+        p3_mul_generic<I + 1>(R, Kt, tid);
+    }
+}
+template <bool B0, int S>
+LNX_HD void p3_mul_col0(const float2* in, float2* out, const float4* Kpq, int tid) {
+    if constexpr (S < 32) {
+        const float4 k = Kpq[S * 4 + tid];
+        const float2 g = in[S], gp = in[col0_partner(B0, S)];
+        const float2 a = cmul(g, make_float2(k.x, k.y));
+        const float2 b = cmul(make_float2(gp.x, -gp.y), make_float2(k.z, k.w));
+        out[S] = cadd(a, b);
+        p3_mul_col0<B0, S + 1>(in, out, Kpq, tid);
+    }
+}
+LNX_HD void phase3_multiply(int tid, Regs& R, const float4* Kt, const float4* Kpq) {
+    if (tid >= 4) {
+        p3_mul_generic<0>(R, Kt, tid);
+    } else {
+        float2 o[32];
+        if (tid == 0)
+            p3_mul_col0<true, 0>(R.v, o, Kpq, tid);
+        else
+            p3_mul_col0<false, 0>(R.v, o, Kpq, tid);
+#pragma unroll
+        for (int s = 0; s < 32; ++s) R.v[s] = o[s];
+    }
+}
+
+// =================================================================================================================
+// P4: load E2 (own region) -> inverse twiddle, inverse radix-8 over m2, retangle, inverse radix-4, twiddle, store E1
+// =================================================================================================================
+LNX_HD void phase4_load(int tid, Regs& R, const float2* W) {
+    const int a = t_sub(tid);
+    const float4* reg4 = reinterpret_cast<const float4*>(W + t_group(tid) * REGION);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int col = col_of(a, c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 t = reg4[e2_addr(col, u) >> 1];
+            R.v[c * 8 + unit_pos(u, 0)] = make_float2(t.x, t.y);
+            R.v[c * 8 + unit_pos(u, 1)] = make_float2(t.z, t.w);
+        }
+    }
+}
+LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W) {
+    const int a = t_sub(tid);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float2* hc = R.v + c * 8;
+#pragma unroll
+        for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_inv(hc[pos], R.twc[bitrev(pos, 3) - 1]);
+        ifft_dit<8>(hc);  // -> natural i
+    }
+    float2 z[32];
+    if (a == 0)
+        p4_retangle<true>(R.v, z);
+    else
+        p4_retangle<false>(R.v, z);
+    float4* reg4 = reinterpret_cast<float4*>(W + t_group(tid) * REGION);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float2* y = z + q * 8 + s * 4;
+            const float2 t0 = cadd(y[0], y[2]), t1 = csub(y[0], y[2]), t2 = cadd(y[1], y[3]);
+            const float2 d = csub(y[1], y[3]);
+            const float2 t3 = make_float2(-d.y, d.x);  // * (+i)
+            const float2 u0 = cadd(t0, t2);
+            const float2 u2 = tw_inv(csub(t0, t2), R.twr[s][1]);
+            const float2 u1 = tw_inv(cadd(t1, t3), R.twr[s][0]);
+            const float2 u3 = tw_inv(csub(t1, t3), R.twr[s][2]);
+            const int k1 = k1_of(a, s);
+            reg4[e1_addr(q, k1, 0) >> 1] = make_float4(u0.x, u0.y, u1.x, u1.y);
+            reg4[e1_addr(q, k1, 2) >> 1] = make_float4(u2.x, u2.y, u3.x, u3.y);
+        }
+}
+
+// =================================================================================================================
+// P5: load E1, radix-32 inverse DIT -> v[j] = (potential[p][4j+l], potential[p+64][4j+l])
+// =================================================================================================================
+template <int POS>
+LNX_HD void p5_load(Regs& R, const float2* reg, int q, int l) {
+    if constexpr (POS < 32) {
+        R.v[POS] = reg[e1_addr(q, bitrev(POS, 5), l)];
+        p5_load<POS + 1>(R, reg, q, l);
+    }
+}
+LNX_HD void phase5_load(int tid, Regs& R, const float2* W) {
+    const int sub = t_sub(tid);
+    p5_load<0>(R, W + t_group(tid) * REGION, sub >> 2, sub & 3);
+}
+LNX_HD void phase5_ifft(Regs& R) { ifft_dit<32>(R.v); }
+
+// =================================================================================================================
+// State layout (thread-private, float4 index i*256 + tid): i = 0..7 row p, i = 8..15 row p+64; element e of float4 i
+// is column 4*(4*(i&7) + e) + l.  Cell coordinates of thread tid:
+// =================================================================================================================
+LNX_HD int cell_row(int tid, int half) { return t_group(tid) + 16 * (t_sub(tid) >> 2) + 64 * half; }
+LNX_HD int cell_col(int tid, int j) { return 4 * j + (t_sub(tid) & 3); }
+
+// Kernel-spectrum table slot -> (m, m2, ...) used by the table builder (device gather kernel and the emulator)
+LNX_HD int p3_slot_m(int tid, int slot) {
+    const int bidx = t_bidx(tid), h = slot >> 4, pos = slot & 15;
+    const int m2 = bidx == 0 ? (h == 0 ? 0 : 4) : (h == 0 ? bidx : 8 - bidx);
+    int m1 = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) m1 |= ((pos >> b) & 1) << (3 - b);
+    return m2 + 8 * m1;
+}
+
+}  // namespace lnx

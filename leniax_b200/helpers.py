@@ -1,0 +1,103 @@
+"""Helper functions gluing the hot path together (reference: leniax/helpers.py:35-128, 130-190, 401-515)."""
+import copy
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import core as leniax_core
+from . import kernels as leniax_kernels
+from . import loader as leniax_loader
+from . import runner as leniax_runner
+from . import statistics as leniax_stat
+from . import utils as leniax_utils
+from .growth_functions import resolve as resolve_gf
+
+
+def create_init_cells(world_size: List[int], nb_channels: int, other_cells: Union[torch.Tensor, List] = [],
+                      offsets: List[List[int]] = []) -> torch.Tensor:
+    """helpers.py:91-128."""
+    if isinstance(other_cells, list):
+        cells = torch.zeros([nb_channels] + list(world_size))
+        use_off = len(offsets) == len(other_cells)
+        for i, c in enumerate(other_cells):
+            if len(c) != 0:
+                cells = leniax_utils.merge_cells(cells, torch.as_tensor(c), offsets[i] if use_off else None)
+        return cells[None]
+    if isinstance(other_cells, (torch.Tensor, np.ndarray)):
+        return torch.as_tensor(other_cells).to(torch.float32)
+    raise ValueError(f'Don\'t know how to handle {type(other_cells)}')
+
+
+def init(config: Dict, use_init_cells: bool = True, fft: bool = True, device=None
+         ) -> Tuple[torch.Tensor, torch.Tensor, leniax_kernels.KernelMapping]:
+    """Initial state, kernels and mapping (helpers.py:35-88)."""
+    wp = config['world_params']
+    nb_dims, nb_channels = wp['nb_dims'], wp['nb_channels']
+    world_size = list(config['render_params']['world_size'])
+    assert len(world_size) == nb_dims
+    assert nb_channels > 0
+    raw_cells = leniax_loader.load_raw_cells(config, use_init_cells)
+    if wp.get('scale', 1.) != 1.:
+        raise NotImplementedError('world_params.scale != 1 (scipy.ndimage.zoom, helpers.py:59-66) is outside the accelerated path')
+    if raw_cells.dim() > 1 + nb_dims:
+        init_cells = create_init_cells(world_size, nb_channels, raw_cells)
+    else:
+        init_cells = create_init_cells(world_size, nb_channels, [raw_cells])
+    K, mapping = leniax_kernels.get_kernels_and_mapping(config['kernels_params'], world_size, nb_channels, wp['R'], fft, device=device)
+    return init_cells.to(K.device), K, mapping
+
+
+def build_get_potential_fn(kernel_shape: Tuple[int, ...], true_channels: Optional[List[bool]] = None, fft: bool = True,
+                           channel_first: bool = True) -> leniax_core.PotentialFn:
+    """helpers.py:430-488.  ``kernel_shape`` is ``K.shape`` = ``[1, C, max_k, H, W]`` for the FFT path."""
+    if not fft:
+        raise NotImplementedError('the direct-convolution potential (fft=False, core.py:105-146) is not built; use fft=True')
+    if not channel_first:
+        raise NotImplementedError('channel_first=False layouts are not built')
+    C, max_k = int(kernel_shape[1]), int(kernel_shape[2])
+    tc = tuple(i for i, t in enumerate(true_channels) if t) if true_channels is not None else None
+    return leniax_core.PotentialFn(tc, C * max_k, max_k, True, True)
+
+
+def build_get_field_fn(cin_gfs: List[List[str]], average: bool = True) -> leniax_core.FieldFn:
+    """helpers.py:491-515."""
+    slugs = tuple(resolve_gf(s).slug for per_channel in cin_gfs for s in per_channel)
+    return leniax_core.FieldFn(slugs, bool(average))
+
+
+def build_update_fn(kernel_shape: Tuple[int, ...], mapping: leniax_kernels.KernelMapping, get_state_fn_slug: str = 'v1',
+                    average_weight: bool = True, fft: bool = True) -> leniax_core.UpdateFn:
+    """helpers.py:401-427."""
+    return leniax_core.UpdateFn(
+        build_get_potential_fn(kernel_shape, mapping.true_channels, fft),
+        build_get_field_fn(mapping.cin_gfs, average_weight),
+        leniax_core._resolve_state_fn(get_state_fn_slug),
+    )
+
+
+def init_and_run(rng_key, config: Dict, use_init_cells: bool = True, with_jit: bool = True, fft: bool = True,
+                 stat_trunc: bool = False, device=None):
+    """Initialise and simulate a Lenia configuration (helpers.py:130-190)."""
+    config = copy.deepcopy(config)
+    cells, K, mapping = init(config, use_init_cells, fft, device=device)
+    dev = K.device
+    gf_params = mapping.get_gf_params(dev)
+    weights = mapping.get_kernels_weight_per_channel(dev)
+    wp = config['world_params']
+    R = wp['R']
+    T = torch.tensor(wp['T'], dtype=torch.float32, device=dev)
+    max_run_iter = config['run_params']['max_run_iter']
+    update_fn = build_update_fn(K.shape, mapping, wp.get('get_state_fn_slug', 'v1'), wp.get('weighted_average', True), fft)
+    stats_fn = leniax_stat.build_compute_stats_fn(wp, config['render_params'])
+    if with_jit:
+        all_cells, all_fields, all_potentials, stats = leniax_runner.run_scan(rng_key, cells, K, gf_params, weights, T, max_run_iter,
+                                                                             R, update_fn, stats_fn)
+    else:
+        all_cells, all_fields, all_potentials, stats = leniax_runner.run(rng_key, cells, K, gf_params, weights, T, max_run_iter, R,
+                                                                        update_fn, stats_fn, stat_trunc)
+    stats = {k: v.squeeze() for k, v in stats.items()}
+    if stat_trunc:
+        n = int(stats['N'])
+        all_cells, all_fields, all_potentials = all_cells[:n], all_fields[:n], all_potentials[:n]
+    return all_cells, all_fields, all_potentials, stats

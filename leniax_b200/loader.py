@@ -1,0 +1,131 @@
+"""Cell codecs needed to start a simulation from a leniax config (reference: leniax/loader.py:16-129, 206-350).
+
+Only decoding (and the quantisation used by the initialisers) is provided: gzip+base64 int32, the 2-character code and
+the legacy run-length format used by the reference's test fixtures.
+"""
+import base64
+import gzip
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from .constant import NB_CHARS
+
+_MAX_VAL = NB_CHARS**2 - 1
+
+
+def make_array_compressible(cells: torch.Tensor) -> torch.Tensor:  # loader.py:16-30
+    return (torch.round(cells * _MAX_VAL).to(torch.int32) / _MAX_VAL).to(torch.float32)
+
+
+def decompress_array_gzip(string_cells: str) -> torch.Tensor:  # loader.py:105-129
+    ints = np.frombuffer(gzip.decompress(base64.b64decode(string_cells)), dtype='<i4')
+    n = int(ints[0])
+    shape = [int(s) for s in ints[1 + n:]]
+    return torch.from_numpy((ints[1:1 + n].reshape(shape) / _MAX_VAL).astype(np.float32))
+
+
+def ch2val(c: str) -> int:  # loader.py:148-175
+    def idx(ch):
+        if ord(ch) >= ord('À'):
+            return ord(ch) - ord('À') + (ord('Z') - ord('A')) + (ord('z') - ord('a'))
+        if ord(ch) >= ord('a'):
+            return ord(ch) - ord('a') + (ord('Z') - ord('A'))
+        return ord(ch) - ord('A')
+
+    assert len(c) == 2
+    return idx(c[0]) * NB_CHARS + idx(c[1])
+
+
+def _legacy_val(ch: str) -> int:  # loader.py:275-283
+    if ch in '.b':
+        return 0
+    if ch == 'o':
+        return 255
+    if len(ch) == 1:
+        return ord(ch) - ord('A') + 1
+    return (ord(ch[0]) - ord('p')) * 24 + (ord(ch[1]) - ord('A') + 25)
+
+
+def deprecated_decompress_array(cells_code: str, nb_dims: int) -> torch.Tensor:
+    """Legacy RLE: ``$`` ends a row, ``%`` a plane, ``#`` a volume; digits repeat; two-letter values start with p..y
+    (loader.py:246-350)."""
+    level = {'$': 1, '%': 2, '#': 3}
+    closing = ['', '$', '%', '#'][nb_dims - 1]
+    stacks: List[List] = [[] for _ in range(nb_dims)]
+    prefix, count = '', ''
+    for ch in cells_code.rstrip('!') + closing:
+        if ch.isdigit():
+            count += ch
+        elif ch in 'pqrstuvwxy@':
+            prefix = ch
+        else:
+            n = int(count) if count else 1
+            tok = prefix + ch
+            if tok in level:
+                for d in range(level[tok]):
+                    stacks[d + 1].append(stacks[d])
+                    stacks[d + 1].extend([] for _ in range(n - 1))
+                    stacks[d] = []
+            else:
+                stacks[0].extend([_legacy_val(tok) / 255] * n)
+            prefix, count = '', ''
+    nested = stacks[nb_dims - 1]
+    lens = [0] * nb_dims
+
+    def measure(d, lst):
+        lens[d] = max(lens[d], len(lst))
+        if d < nb_dims - 1:
+            for sub in lst:
+                measure(d + 1, sub)
+
+    measure(0, nested)
+    out = np.zeros(lens, dtype=np.float32)
+
+    def fill(d, lst, idx):
+        if d == nb_dims - 1:
+            out[idx + (slice(0, len(lst)), )] = lst
+        else:
+            for i, sub in enumerate(lst):
+                fill(d + 1, sub, idx + (i, ))
+
+    fill(0, nested, ())
+    return torch.from_numpy(out)
+
+
+def decompress_array(string_cells: str, nb_dims: int = 0) -> torch.Tensor:  # loader.py:69-102 (best effort chain)
+    try:
+        return decompress_array_gzip(string_cells)
+    except Exception:
+        pass
+    parts = string_cells.split('::')
+    if len(parts) == 2 and len(parts[0]) % 2 == 0:
+        try:
+            shape = [int(c) for c in parts[1].split(';')]
+            vals = [ch2val(parts[0][i:i + 2]) for i in range(0, len(parts[0]), 2)]
+            return (torch.tensor(vals, dtype=torch.int32).reshape(shape) / _MAX_VAL).to(torch.float32)
+        except Exception:
+            pass
+    return deprecated_decompress_array(string_cells, nb_dims)
+
+
+def load_raw_cells(config: Dict, use_init_cells: bool = True) -> torch.Tensor:  # loader.py:206-240
+    nb_dims = config['world_params']['nb_dims']
+    rp = config['run_params']
+    cells = rp['init_cells'] if (use_init_cells and 'init_cells' in rp) else rp['cells']
+    if isinstance(cells, str):
+        if cells == 'MISSING':
+            cells = torch.zeros(0)
+        elif cells == 'last_frame.p':
+            import os
+            import pickle
+            with open(os.path.join(config['main_path'], 'last_frame.p'), 'rb') as f:
+                cells = torch.as_tensor(np.asarray(pickle.load(f), dtype=np.float32))
+        else:
+            cells = decompress_array(cells, nb_dims + 1)
+    elif isinstance(cells, list):
+        cells = torch.tensor(cells, dtype=torch.float32)
+    if cells.dim() == nb_dims and config['world_params']['nb_channels'] == 1:
+        cells = cells[None]
+    return cells.to(torch.float32)

@@ -1,0 +1,148 @@
+"""Time loops (reference: leniax/runner.py:16-334), executed by the persistent CUDA kernels.
+
+Same names and positional signatures as the reference.  ``update_fn`` is a ``core.UpdateFn`` descriptor and
+``compute_stats_fn`` a ``statistics.ComputeStatsFn`` descriptor (both built by ``helpers`` / ``statistics`` exactly like
+the reference builds its callables).  Arrays may be torch tensors (CUDA or CPU) or numpy arrays; results are CUDA
+tensors.  ``rng_key`` is accepted and ignored: no registered state function consumes randomness (core.py:245-319).
+"""
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib, engine
+from .constant import EPSILON, START_CHECK_STOP
+from .core import UpdateFn
+from .statistics import ComputeStatsFn, mass_volume_heuristic, monotonic_heuristic
+
+
+def _check_fns(update_fn, compute_stats_fn):
+    if not isinstance(update_fn, UpdateFn):
+        raise NotImplementedError(
+            'update_fn must be the descriptor returned by leniax_b200.helpers.build_update_fn; arbitrary Python '
+            'callables cannot be fused into the CUDA scan and there is no CPU fallback'
+        )
+    if not isinstance(compute_stats_fn, ComputeStatsFn):
+        raise NotImplementedError('compute_stats_fn must come from leniax_b200.statistics.build_compute_stats_fn')
+    if not update_fn.get_potential_fn.fft:
+        raise NotImplementedError('the direct-convolution potential (fft=False) is not built; use fft=True')
+
+
+def _finite_params(gf_params: torch.Tensor, weights: torch.Tensor, average: bool) -> bool:
+    """True when NaN cannot be born in the step: no growth width s == 0, no all-zero weight row."""
+    ok = bool((gf_params[..., 1] != 0).all().item()) and bool(torch.isfinite(gf_params).all().item())
+    if average:
+        ok = ok and bool((weights.sum(dim=-1) != 0).all().item())
+    return ok and bool(torch.isfinite(weights).all().item())
+
+
+def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, stats_fn: ComputeStatsFn, *, batched: bool,
+          keep_trajectory: bool, early_stop: bool = False):
+    assert max_run_iter > 0, f"max_run_iter must be positive, value given: {max_run_iter}"  # runner.py:51
+    dev = engine.require_cuda_device(cells0.device if isinstance(cells0, torch.Tensor) and cells0.is_cuda else None)
+    f32 = torch.float32
+    cells0 = engine.as_device_tensor(cells0, f32, dev)
+    gf_params = engine.as_device_tensor(gf_params, f32, dev)
+    weights = engine.as_device_tensor(weights, f32, dev)
+    T = engine.as_device_tensor(T, f32, dev)
+    K = engine.as_device_tensor(K, torch.complex64, dev)
+    if not batched:
+        cells0, gf_params, weights, T, K = cells0[None], gf_params[None], weights[None], T.reshape(1), K[None]
+    n_sols, n_init, C = cells0.shape[0], cells0.shape[1], cells0.shape[2]
+    world_size = tuple(cells0.shape[3:])
+    if tuple(stats_fn.world_size) != world_size:
+        raise ValueError(f'compute_stats_fn was built for world_size {stats_fn.world_size}, cells are {world_size}')
+    pf = update_fn.get_potential_fn
+    slots, c_in, gf_ids = update_fn.kernel_layout(C)
+    K = K.reshape((n_sols, pf.nb_slots) + world_size)
+    plan = engine.Plan.get(world_size=world_size, nb_channels=C, slots=slots, c_in=c_in, gf_ids=gf_ids, nb_slots=pf.nb_slots,
+                           state_fn=update_fn.get_state_fn.slug, weighted_average=update_fn.get_field_fn.average, R=stats_fn.R,
+                           stats_dt=stats_fn.dt, device=dev)
+    flags = 0
+    if early_stop:
+        flags |= _lib.LNX_RUN_EARLY_STOP
+    if _finite_params(gf_params, weights, update_fn.get_field_fn.average):
+        flags |= _lib.LNX_RUN_ASSUME_FINITE
+    dt = (1. / T.reshape(n_sols)).contiguous()  # runner.py:307
+    return plan.run_scan(cells0.contiguous(), K, gf_params.reshape(n_sols, len(slots), 2), weights.reshape(n_sols, C, len(slots)),
+                         dt, max_run_iter, keep_trajectory=keep_trajectory, flags=flags)
+
+
+def run_scan(rng_key, cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter: int, R: float, update_fn,
+             compute_stats_fn) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+    """Simulate a single configuration with ``N_init`` initialisations (runner.py:119-164).
+
+    Returns ``(cells [T, N_init, C, H, W], field, potential [T, N_init, K, H, W], stats {k: [T, N_init]})`` with
+    ``stats['channel_mass'] [T, N_init, C]`` and ``stats['N'] [N_init]``.
+    """
+    _check_fns(update_fn, compute_stats_fn)
+    res = _scan(cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter, update_fn, compute_stats_fn, batched=False,
+                keep_trajectory=True)
+    stats = {k: v[0] for k, v in res['stats'].items()}
+    return res['cells'][0], res['field'][0], res['potential'][0], stats
+
+
+def run_scan_mem_optimized(rng_key, cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter: int, R: float,
+                           update_fn, compute_stats_fn, early_stop: bool = False
+                           ) -> Tuple[Dict[str, torch.Tensor], torch.Tensor]:
+    """Simulate ``N_sols`` configurations x ``N_init`` initialisations (runner.py:167-215).
+
+    ``cells0 [N_sols, N_init, C, H, W]``, ``K [N_sols, 1, C, max_k, H, W]``, ``gf_params [N_sols, K, 2]``,
+    ``kernels_weight_per_channel [N_sols, C, K]``, ``T [N_sols]``.  Returns ``(stats {k: [N_sols, T, N_init]}, final_cells)``.
+    ``early_stop=True`` (extension) lets a world stop once its stop criteria fired and 128 rows exist; the rows the QD
+    consumer reads (qd.py:181-185) are unaffected, later rows are zero.
+    """
+    _check_fns(update_fn, compute_stats_fn)
+    res = _scan(cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter, update_fn, compute_stats_fn, batched=True,
+                keep_trajectory=False, early_stop=early_stop)
+    return res['stats'], res['final_cells']
+
+
+def run_scan_mem_optimized_pmap(rng_key, cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter: int, R: float,
+                                update_fn, compute_stats_fn) -> Tuple[Dict[str, torch.Tensor], torch.Tensor]:
+    """Leading ``N_device`` axis (runner.py:218-268).  One process drives one GPU here, so the device axis is folded
+    into the solution axis; multi-GPU sharding lives in ``leniax_b200.distributed``."""
+    nd, ns = cells0.shape[0], cells0.shape[1]
+    fold = lambda x: x.reshape((nd * ns, ) + tuple(x.shape[2:]))  # noqa: E731
+    stats, final = run_scan_mem_optimized(rng_key, fold(cells0), fold(K), fold(gf_params), fold(kernels_weight_per_channel),
+                                          fold(T), max_run_iter, R, update_fn, compute_stats_fn)
+    unfold = lambda x: x.reshape((nd, ns) + tuple(x.shape[1:]))  # noqa: E731
+    return {k: unfold(v) for k, v in stats.items()}, unfold(final)
+
+
+def run(rng_key, cells, K, gf_params, kernels_weight_per_channel, T, max_run_iter: int, R: float, update_fn, compute_stats_fn,
+        stat_trunc: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+    """Simulate a single configuration with the semantics of the reference's python loop (runner.py:16-116).
+
+    The reference dispatches two jitted calls per step and breaks on its on-the-fly heuristics.  The break only
+    truncates, so the same result is obtained by scanning ``max_run_iter`` steps on the GPU and replaying the loop's
+    stop rules (total-mass min/max against the un-normalised initial sum, monotone / volume counters that never see
+    ``previous_mass`` updated, grace period ``START_CHECK_STOP``) on the statistics afterwards.
+    """
+    assert max_run_iter > 0, f"max_run_iter must be positive, value given: {max_run_iter}"
+    assert cells.shape[0] == 1
+    all_cells, all_fields, all_potentials, stats = run_scan(rng_key, cells, K, gf_params, kernels_weight_per_channel, T,
+                                                           max_run_iter, R, update_fn, compute_stats_fn)
+    stats.pop('N')
+    mass = stats['mass'][:, 0].detach().cpu()
+    mass_volume = stats['mass_volume'][:, 0].detach().cpu()
+    init_mass = float(all_cells[0].sum().item())  # runner.py:61 (not divided by R^2)
+    previous_sign = torch.zeros(())
+    mono = torch.zeros((), dtype=torch.int32)
+    vol = torch.zeros((), dtype=torch.int32)
+    should_continue = 1
+    current_iter = max_run_iter - 1
+    for it in range(max_run_iter):
+        cond = bool(mass[it] >= EPSILON) and bool(mass[it] <= 3 * init_mass)
+        sign = torch.sign(mass[it] - init_mass)  # previous_mass is never updated in the reference loop
+        c, mono = monotonic_heuristic(sign, previous_sign, mono)
+        cond = cond and bool(c)
+        c, vol = mass_volume_heuristic(mass_volume[it], vol)
+        cond = cond and bool(c)
+        should_continue *= int(cond)
+        if stat_trunc is True and it >= START_CHECK_STOP and should_continue == 0:
+            current_iter = it
+            break
+    n = current_iter + 1
+    stats = {k: v[:n] for k, v in stats.items()}
+    stats['N'] = torch.tensor(current_iter)
+    return all_cells[:n], all_fields[:n], all_potentials[:n], stats

