@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
         if (tid < C) {
             float sum = 0.f;
             for (int k = 0; k < K; ++k) sum += P.weights[((size_t)sol * C + tid) * K + k];
-            gc->inv_wsum[tid] = P.mean ? 1.0f / sum : 1.0f;
+            gc->inv_wsum[tid] = P.mean ? sum : 1.0f;  // generic kernel: true division by the row sum (core.py:240)
         }
         if (tid == 0) gc->dt = P.dt[sol];
         __syncthreads();
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                             f1 = fa[(8 + i) * NT + tid];
                         }
                         const float a0[4] = {c0.x, c0.y, c0.z, c0.w}, a1[4] = {c1.x, c1.y, c1.z, c1.w};
-                        const float q0[4] = {f0.x * inv, f0.y * inv, f0.z * inv, f0.w * inv}, q1[4] = {f1.x * inv, f1.y * inv, f1.z * inv, f1.w * inv};
+                        const float q0[4] = {f0.x / inv, f0.y / inv, f0.z / inv, f0.w / inv}, q1[4] = {f1.x / inv, f1.y / inv, f1.z / inv, f1.w / inv};
                         float n0[4], n1[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {

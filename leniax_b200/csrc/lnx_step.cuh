@@ -49,11 +49,12 @@ LNX_HD GfConst gf_prepare(int gf, float m, float s) {
 }
 
 // NP = propagate NaN exactly like jnp.maximum / jnp.clip do (needed when s == 0 or a zero weight row can appear)
-template <int GF, bool NP>
+// XD = use true IEEE divisions where the reference divides (generic kernel); the fused kernel multiplies by reciprocals
+template <int GF, bool NP, bool XD = false>
 LNX_HD float growth(float X, const GfConst& g) {
     if constexpr (GF == GF_POLY_QUAD4) {
         const float t = X - g.m;
-        float o = 1.0f - (t * t) * g.k0;
+        float o = XD ? 1.0f - (t * t) / (9.0f * (g.s * g.s)) : 1.0f - (t * t) * g.k0;
         if constexpr (NP)
             o = (o < 0.f) ? 0.f : o;
         else
@@ -61,11 +62,11 @@ LNX_HD float growth(float X, const GfConst& g) {
         const float o2 = o * o;
         return 2.0f * (o2 * o2) - 1.0f;
     } else if constexpr (GF == GF_GAUSSIAN) {
-        const float t = (X - g.m) * g.k0;
-        return 2.0f * expf(-(t * t) * 0.5f) - 1.0f;
+        const float t = XD ? (X - g.m) / g.s : (X - g.m) * g.k0;
+        return 2.0f * expf(-(t * t) / 2.0f) - 1.0f;
     } else if constexpr (GF == GF_GAUSSIAN_TARGET) {
-        const float t = (X - g.m) * g.k0;
-        return expf(-(t * t) * 0.5f);
+        const float t = XD ? (X - g.m) / g.s : (X - g.m) * g.k0;
+        return expf(-(t * t) / 2.0f);
     } else if constexpr (GF == GF_STEP) {
         return (fabsf(X - g.m) <= g.s) ? 1.0f : -1.0f;
     } else if constexpr (GF == GF_STAIRCASE) {
@@ -74,8 +75,8 @@ LNX_HD float growth(float X, const GfConst& g) {
         o += (X > g.k2 && X <= g.k3) ? 0.5f : 0.f;
         return 2.0f * o - 1.0f;
     } else if constexpr (GF == GF_TRIANGLE) {
-        float o = (X >= g.k0 && X < g.m) ? (X - g.k0) * g.k2 : 0.f;
-        o += (X >= g.m && X <= g.k1) ? (X - g.k1) * g.k3 : 0.f;
+        float o = (X >= g.k0 && X < g.m) ? (XD ? (X - g.k0) / (g.m - g.k0) : (X - g.k0) * g.k2) : 0.f;
+        o += (X >= g.m && X <= g.k1) ? (XD ? (X - g.k1) / (g.m - g.k1) : (X - g.k1) * g.k3) : 0.f;
         return 2.0f * o - 1.0f;
     } else {
         return X;
@@ -84,12 +85,12 @@ LNX_HD float growth(float X, const GfConst& g) {
 template <bool NP>
 LNX_HD float growth_dyn(int gf, float X, const GfConst& g) {
     switch (gf) {
-        case GF_POLY_QUAD4: return growth<GF_POLY_QUAD4, NP>(X, g);
-        case GF_GAUSSIAN: return growth<GF_GAUSSIAN, NP>(X, g);
-        case GF_GAUSSIAN_TARGET: return growth<GF_GAUSSIAN_TARGET, NP>(X, g);
-        case GF_STEP: return growth<GF_STEP, NP>(X, g);
-        case GF_STAIRCASE: return growth<GF_STAIRCASE, NP>(X, g);
-        case GF_TRIANGLE: return growth<GF_TRIANGLE, NP>(X, g);
+        case GF_POLY_QUAD4: return growth<GF_POLY_QUAD4, NP, true>(X, g);
+        case GF_GAUSSIAN: return growth<GF_GAUSSIAN, NP, true>(X, g);
+        case GF_GAUSSIAN_TARGET: return growth<GF_GAUSSIAN_TARGET, NP, true>(X, g);
+        case GF_STEP: return growth<GF_STEP, NP, true>(X, g);
+        case GF_STAIRCASE: return growth<GF_STAIRCASE, NP, true>(X, g);
+        case GF_TRIANGLE: return growth<GF_TRIANGLE, NP, true>(X, g);
         default: return X;
     }
 }

@@ -1,0 +1,161 @@
+"""CPU emulation of the CUDA kernels' per-thread code (tests/emul/lnx_emul.cu) against the oracle.
+
+The emulator executes the exact __host__ __device__ phase functions of leniax_b200/csrc/*.cuh thread by thread, with the
+kernels' synchronisation points as loop boundaries: index maps, twiddles, packing tricks and the statistics formulas are
+validated here without a GPU.  (The product never loads this library.)
+"""
+import ctypes
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lenia_oracle as lo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL = os.path.join(ROOT, 'tests', 'emul', 'liblnx_emul.so')
+KEYS = ['mass', 'mass_volume', 'mass_density', 'growth', 'growth_volume', 'growth_density', 'mass_speed', 'mass_angle_speed',
+        'mass_growth_dist', 'inertia', 'potential_volume']
+
+
+@pytest.fixture(scope='module')
+def emul():
+    if not os.path.exists(EMUL):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(EMUL)
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def build_tables(emul, Kfull):
+    Kt, Kpq = np.zeros((16, 256, 4), np.float32), np.zeros((32, 4, 4), np.float32)
+    emul.lnx_emul_build_kt(P(np.ascontiguousarray(Kfull.astype(np.complex64))), P(Kt), P(Kpq))
+    return Kt, Kpq
+
+
+def test_potential_real_symmetric_and_general_kernel(emul, golden_dir):
+    cfg = lo.load_yaml_config(os.path.join(golden_dir, 'orbium-test.yaml'))
+    _, K, _ = lo.init(cfg)
+    rng = np.random.default_rng(0)
+    state = rng.random((128, 128), dtype=np.float32)
+    pot = np.zeros((128, 128), np.float32)
+    Kt, Kpq = build_tables(emul, K[0, 0, 0])
+    emul.lnx_emul_potential(P(state), P(Kt), P(Kpq), P(pot))
+    assert np.abs(pot - lo.get_potential_fft(state[None, None], K)[0, 0]).max() < 1e-6
+    # non-symmetric kernel => complex spectrum; exercises the packed DC|Nyquist column formulas (Kp, Kq)
+    kern = rng.random((128, 128)).astype(np.float32)
+    kern /= kern.sum()
+    ref = np.real(np.fft.ifft2(np.fft.fft2(state.astype(np.float64)) * np.fft.fft2(kern.astype(np.float64))))
+    Kt, Kpq = build_tables(emul, np.fft.fft2(kern))
+    emul.lnx_emul_potential(P(state), P(Kt), P(Kpq), P(pot))
+    assert np.abs(pot - ref).max() < 5e-7
+
+
+def _run_fused(emul, cells0, K, gf, m, s, w, mean, T, sf, R, steps):
+    Kt, Kpq = build_tables(emul, K)
+    stats = np.zeros((11, steps), np.float32)
+    cm, N, fin = np.zeros(steps, np.float32), np.zeros(1, np.float32), np.zeros((128, 128), np.float32)
+    f = ctypes.c_float
+    rc = emul.lnx_emul_run_fused(P(np.ascontiguousarray(cells0)), P(Kt), P(Kpq), gf, f(m), f(s), f(w), mean, f(T), sf, f(R),
+                                 f(1. / T), steps, P(stats), P(cm), P(N), P(fin), None)
+    assert rc == 0
+    return stats, cm, float(N[0]), fin
+
+
+def test_orbium_trajectory_stats_and_golden(emul, golden_dir):
+    cfg = lo.load_yaml_config(os.path.join(golden_dir, 'orbium-test.yaml'))
+    cells, K, _ = lo.init(cfg)
+    oc, _, _, ostats = lo.init_and_run(cfg, with_jit=True)
+    stats, cm, N, fin = _run_fused(emul, cells[0, 0], K[0, 0, 0], 0, .15, .015, 1., 1, 10., 0, 13., 128)
+    tol = dict(zip(KEYS, [2e-6, 1e-7, 2e-6, 5e-6, 1e-7, 1e-5, 5e-5, 0.05, 2e-5, 5e-6, 0.05]))
+    for i, k in enumerate(KEYS):
+        assert np.abs(stats[i] - ostats[k][:, 0]).max() <= tol[k], k
+    assert np.abs(cm - ostats['channel_mass'][:, 0, 0]).max() < 2e-6
+    assert N == float(ostats['N'][0]) == 128.
+    # state after 127 updates vs the reference's golden fixture (tests/test_pipeline.py:18-54, decimal=4)
+    _, _, _, fin127 = _run_fused(emul, cells[0, 0], K[0, 0, 0], 0, .15, .015, 1., 1, 10., 0, 13., 127)
+    gold = np.load(os.path.join(golden_dir, 'orbium-test_last_frame.npy'))
+    np.testing.assert_array_almost_equal(gold[0], fin127, decimal=4)
+    assert np.abs(fin127 - oc[-1, 0, 0]).max() < 5e-5
+
+
+def test_dying_world_stops_like_check_heuristics(emul, golden_dir):
+    cfg = lo.load_yaml_config(os.path.join(golden_dir, 'orbium-test.yaml'))
+    cells, K, mapping = lo.init(cfg)
+    weak = (cells * 0.2).astype(np.float32)  # fades away: channel mass falls under epsilon
+    steps = 40
+    upd = lo.build_update_fn(mapping)
+    sfn = lo.build_compute_stats_fn(cfg['world_params'], cfg['render_params'])
+    ostats, _ = lo.run_scan(weak, K, mapping.get_gf_params(), mapping.get_kernels_weight_per_channel(), np.float32(10.), steps, upd, sfn, False)
+    stats, cm, N, _ = _run_fused(emul, weak[0, 0], K[0, 0, 0], 0, .15, .015, 1., 1, 10., 0, 13., steps)
+    assert N == float(ostats['N'][0]) and N < steps
+    assert np.abs(stats[0] - ostats['mass'][:, 0]).max() < 2e-6
+
+
+@pytest.mark.parametrize('gf,sf,slug,sslug,params', [(1, 0, 'gaussian', 'v1', (.15, .02)), (2, 1, 'gaussian_target', 'v2', (.2, .05)),
+                                                     (5, 0, 'triangle', 'v1', (.15, .05)), (6, 2, 'identity', 'simple', (0., 1.))])
+def test_other_growth_and_state_functions(emul, golden_dir, gf, sf, slug, sslug, params):
+    cfg = lo.load_yaml_config(os.path.join(golden_dir, 'orbium-test.yaml'))
+    cfg['kernels_params'][0]['gf_slug'] = slug
+    cfg['kernels_params'][0]['gf_params'] = list(params)
+    cfg['world_params']['get_state_fn_slug'] = sslug
+    cfg['run_params']['max_run_iter'] = 6
+    cells, K, _ = lo.init(cfg)
+    oc, _, _, ostats = lo.init_and_run(cfg, with_jit=True)
+    stats, cm, N, fin = _run_fused(emul, cells[0, 0], K[0, 0, 0], gf, params[0], params[1], 1., 1, 10., sf, 13., 5)
+    assert np.abs(fin - oc[5, 0, 0]).max() < 2e-5
+    assert np.abs(stats[0] - ostats['mass'][:5, 0]).max() < 1e-4 * max(1., np.abs(ostats['mass']).max())
+
+
+# ---- shared-memory bank conflicts of every access pattern of the exchange buffer (addresses from the real code) ----
+def _conflict_degree(byte_addrs, width):
+    """Max wavefronts needed by one warp-wide access: lanes are served in groups of 128/width... (8 lanes for 128-bit,
+    16 for 64-bit); within a group every 4-byte bank may be touched once."""
+    group = {16: 8, 8: 16, 4: 32}[width]
+    worst = 1
+    for g0 in range(0, 32, group):
+        banks = {}
+        for a in byte_addrs[g0:g0 + group]:
+            for wd in range(width // 4):
+                b = ((a // 4) + wd) % 32
+                banks.setdefault(b, set()).add((a // 4) + wd)
+        worst = max(worst, max(len(v) for v in banks.values()))
+    return worst
+
+
+def test_exchange_layouts_are_bank_conflict_free(emul):
+    e1, e2 = emul.lnx_emul_e1_addr, emul.lnx_emul_e2_addr
+    k1_of, col_of = emul.lnx_emul_k1_of, emul.lnx_emul_col_of
+    for warp in range(8):
+        tids = [warp * 32 + ln for ln in range(32)]
+        G = [t >> 4 for t in tids]
+        sub = [t & 15 for t in tids]
+        # P1 stores / P5 loads: 64-bit, lanes (q,l), fixed k1
+        for k1 in range(32):
+            addrs = [(G[i] * 512 + e1(sub[i] >> 2, k1, sub[i] & 3)) * 8 for i in range(32)]
+            assert _conflict_degree(addrs, 8) == 1, ('E1 64-bit', warp, k1)
+        # P2 loads / P4 stores: 128-bit, lanes a, fixed (q, s, half)
+        for q, s, h in itertools.product(range(4), range(2), range(2)):
+            addrs = [(G[i] * 512 + e1(q, k1_of(sub[i], s), 2 * h)) * 8 for i in range(32)]
+            assert all(a % 16 == 0 for a in addrs)
+            assert _conflict_degree(addrs, 16) == 1, ('E1 128-bit', warp, q, s, h)
+        # P2 stores / P4 loads: 128-bit, lanes a, fixed (c, u)
+        for c, u in itertools.product(range(4), range(4)):
+            addrs = [(G[i] * 512 + e2(col_of(sub[i], c), u)) * 8 for i in range(32)]
+            assert _conflict_degree(addrs, 16) == 1, ('E2 group', warp, c, u)
+        # P3 loads / stores: 128-bit, lanes (col, bidx), fixed r1
+        for r1 in range(16):
+            addrs = [(r1 * 512 + e2(t >> 2, t & 3)) * 8 for t in tids]
+            assert _conflict_degree(addrs, 16) == 1, ('E2 column', warp, r1)
+
+
+def test_exchange_layouts_are_bijections(emul):
+    e1, e2 = emul.lnx_emul_e1_addr, emul.lnx_emul_e2_addr
+    assert sorted(e1(q, k, l) for q in range(4) for k in range(32) for l in range(4)) == list(range(512))
+    assert sorted(e2(c, u) + e for c in range(64) for u in range(4) for e in range(2)) == list(range(512))
+    cols = sorted(emul.lnx_emul_col_of(a, c) for a in range(16) for c in range(4))
+    assert cols == list(range(64))

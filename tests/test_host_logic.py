@@ -1,0 +1,142 @@
+"""Host-side logic of the product package and the C-ABI surface (CPU only: no compute calls)."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import leniax_b200
+from leniax_b200 import _lib, core, growth_functions, helpers, kernels, loader, runner, statistics, utils
+from oracle import lenia_oracle as lo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_loads_and_exports_every_declared_symbol():
+    lib = leniax_b200.load_library()
+    header = open(os.path.join(ROOT, 'include', 'leniax_b200.h')).read()
+    declared = set(re.findall(r'^(?:int|size_t|const char\*)\s+(lnx_[a-z0-9_]+)\(', header, flags=re.M))
+    assert declared >= {'lnx_plan_create', 'lnx_plan_destroy', 'lnx_run_scan', 'lnx_kernels_prepare', 'lnx_rfft2', 'lnx_last_error'}
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/leniax_b200.h but not exported'
+    assert set(_lib.EXPORTS) == declared
+    assert lib.lnx_version() == 100
+    if not torch.cuda.is_available():
+        assert lib.lnx_device_count() == 0
+
+
+def test_no_cpu_fallback_without_gpu(golden_dir):
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    cfg = utils.load_config(os.path.join(golden_dir, 'orbium-test.yaml'))
+    with pytest.raises(_lib.LeniaxB200Error):
+        helpers.init(cfg)  # the kernel spectrum needs lnx_rfft2
+    K, mapping = kernels.get_kernels_and_mapping(cfg['kernels_params'], [128, 128], 1, 13, fft=False)
+    ufn = helpers.build_update_fn((1, 1, 1, 128, 128), mapping)
+    sfn = statistics.build_compute_stats_fn(cfg['world_params'], cfg['render_params'])
+    cells = torch.zeros(1, 1, 128, 128)
+    with pytest.raises(_lib.LeniaxB200Error):
+        runner.run_scan(None, cells, torch.zeros(1, 1, 1, 128, 128, dtype=torch.complex64), mapping.get_gf_params(),
+                        mapping.get_kernels_weight_per_channel(), 10., 4, 13, ufn, sfn)
+    d = _lib.LnxDesc(nb_dims=2, nb_channels=1, nb_kernels=1, nb_slots=1, R=13., stats_dt=.1)
+    d.dims[0] = d.dims[1] = 128
+    handle = ctypes.c_void_p()
+    rc = leniax_b200.load_library().lnx_plan_create(ctypes.byref(d), ctypes.byref(handle))
+    assert rc == _lib.LNX_ERR_NO_DEVICE and b'no CPU fallback' in leniax_b200.load_library().lnx_last_error()
+
+
+def test_plan_validation_errors():
+    lib = leniax_b200.load_library()
+    handle = ctypes.c_void_p()
+    d = _lib.LnxDesc(nb_dims=2, nb_channels=1, nb_kernels=1, nb_slots=1, R=13., stats_dt=.1)
+    d.dims[0], d.dims[1] = 64, 64
+    assert lib.lnx_plan_create(ctypes.byref(d), ctypes.byref(handle)) == _lib.LNX_ERR_UNSUPPORTED
+    d.dims[0] = d.dims[1] = 128
+    d.nb_channels = 99
+    assert lib.lnx_plan_create(ctypes.byref(d), ctypes.byref(handle)) == _lib.LNX_ERR_INVALID
+    d.nb_channels, d.gf_id[0] = 1, 42
+    assert lib.lnx_plan_create(ctypes.byref(d), ctypes.byref(handle)) == _lib.LNX_ERR_INVALID
+    assert b'growth function' in lib.lnx_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(_lib.LNX_ERR_INVALID)
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.LNX_ERR_UNSUPPORTED)
+
+
+@pytest.mark.parametrize('name', ['orbium-test', 'orbium-scutium-test', 'aquarium-test'])
+def test_kernel_rasterisation_and_mapping_match_oracle(golden_dir, name):
+    cfg = utils.load_config(os.path.join(golden_dir, name + '.yaml'))
+    ocfg = lo.load_yaml_config(os.path.join(golden_dir, name + '.yaml'))
+    wp = cfg['world_params']
+    K, m = kernels.get_kernels_and_mapping(cfg['kernels_params'], [128, 128], wp['nb_channels'], wp['R'], fft=False, device='cpu')
+    Ko, mo = lo.get_kernels_and_mapping(ocfg['kernels_params'], [128, 128], wp['nb_channels'], wp['R'], fft=False)
+    assert tuple(K.shape) == Ko.shape
+    np.testing.assert_allclose(K.numpy(), Ko, atol=5e-8)
+    assert m.true_channels == mo.true_channels and m.cin_kernels == mo.cin_kernels and m.cin_gfs == mo.cin_gfs
+    np.testing.assert_array_equal(m.get_gf_params().numpy(), mo.get_gf_params())
+    np.testing.assert_array_equal(m.get_kernels_weight_per_channel().numpy(), mo.get_kernels_weight_per_channel())
+    assert [p['c_in'] for p in cfg['kernels_params']] == sorted(p['c_in'] for p in cfg['kernels_params'])  # sorted in place
+
+
+def test_ellipse_kernels_match_oracle():
+    for fn, ofn in ((kernels.ellipse_2d, lo.ellipse_2d), (kernels.oriented_ellipse_2d, lo.oriented_ellipse_2d)):
+        a = fn(13, [1., [1., .5], 1.2, .8, .25], 'gauss_bump', [4], device='cpu').numpy()
+        b = ofn(13, [1., [1., .5], 1.2, .8, .25], 'gauss_bump', [4])
+        np.testing.assert_allclose(a, b, atol=2e-7)
+    np.testing.assert_array_equal(kernels.circle_2d(5., [1., [1.]], 'poly_quad', [4], device='cpu').shape, [1, 10, 10])  # test_kernels.py:12-20
+
+
+def test_update_fn_descriptor_layout(golden_dir):
+    cfg = utils.load_config(os.path.join(golden_dir, 'aquarium-test.yaml'))
+    K, m = kernels.get_kernels_and_mapping(cfg['kernels_params'], [128, 128], 3, 12, fft=False, device='cpu')
+    ufn = helpers.build_update_fn((1, 3, 5, 128, 128), m, 'v1', False, True)
+    slots, c_in, gf_ids = ufn.kernel_layout(3)
+    assert len(slots) == 15 and c_in == (0, ) * 5 + (1, ) * 5 + (2, ) * 5 and set(gf_ids) == {1}
+    assert ufn.get_field_fn.average is False and ufn.get_state_fn.slug == 'v1'
+    # padded slots (kernels.py:122-143): 2 channels, 2+1 kernels -> tc_indices (0, 1, 2)
+    kp = [dict(k_slug='circle_2d', k_params=[1., [1.]], kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015],
+               h=1., c_in=ci, c_out=co) for ci, co in [(1, 0), (0, 0), (0, 1)]]
+    K, m = kernels.get_kernels_and_mapping(kp, [128, 128], 2, 13, fft=False, device='cpu')
+    ufn = helpers.build_update_fn((1, 2, 2, 128, 128), m)
+    assert ufn.kernel_layout(2) == ((0, 1, 2), (0, 0, 1), (0, 0, 0))
+    with pytest.raises(NotImplementedError):
+        helpers.build_update_fn((1, 2, 2, 128, 128), m, fft=False)
+    with pytest.raises(NotImplementedError):
+        growth_functions.resolve(lambda p, x: x)
+    with pytest.raises(NotImplementedError):
+        core.update(None, torch.zeros(1, 1, 128, 128), None, None, None, .1, lambda *a: a, lambda *a: a, 'v1')
+
+
+def test_loaders_and_config_upgrade_match_oracle(golden_dir):
+    for name in ('orbium-test', 'orbium-scutium-test', 'aquarium-test', 'orbium'):
+        cfg = utils.load_config(os.path.join(golden_dir, name + '.yaml'))
+        ocfg = lo.load_yaml_config(os.path.join(golden_dir, name + '.yaml'))
+        assert cfg['kernels_params'] == ocfg['kernels_params'] and cfg['render_params']['world_size'] == [128, 128]
+        np.testing.assert_array_equal(loader.load_raw_cells(cfg).numpy(), lo.load_raw_cells(ocfg))
+    cells = helpers.create_init_cells([128, 128], 1, [loader.load_raw_cells(cfg, False)])
+    assert cells.shape == (1, 1, 128, 128) and float(cells[0, 0, 54:74, 54:74].sum()) == pytest.approx(float(cells.sum()))
+    assert utils.st2fracs2float('1,2/3,6.7') == pytest.approx([1., 2 / 3, 6.7])  # tests/test_utils.py
+    d = {}
+    utils.set_param(d, 'kernels_params.1.gf_params.0', .3)
+    assert utils.get_param(d, 'kernels_params.1.gf_params.0') == .3
+    q = loader.make_array_compressible(torch.tensor([.12345678]))
+    assert float(q) == pytest.approx(round(.12345678 * 12543) / 12543)
+
+
+def test_host_heuristics_kats():  # tests/test_statistics.py:14-50
+    mv = torch.tensor([800., 1600., 2400., 3200.]) / 13.**2
+    ok, nxt = statistics.mass_volume_heuristic(mv, torch.tensor([10, 70, 127, 128]))
+    assert ok.tolist() == [True, True, True, False] and nxt.tolist() == [1, 1, 128, 129]
+    sign = torch.sign(torch.tensor([1.1, .9, .9, .9]) - 1)
+    ok, nxt = statistics.monotonic_heuristic(sign, torch.tensor([1., 1., -1., -1.]), torch.tensor([40, 128, 30, 128]))
+    assert ok.tolist() == [True, True, True, False] and nxt.tolist() == [41, 1, 31, 129]
+    T, N = 300, 2
+    mass = torch.ones(T, N)
+    mass[:, 0] += torch.arange(T) * 1e-3
+    mass[:, 1] = 1 + .01 * ((torch.arange(T) % 2) * 2 - 1)
+    st = {'mass': mass, 'channel_mass': mass[..., None].clone(), 'mass_volume': torch.ones(T, N)}
+    ref = lo.check_heuristics({k: v.numpy() for k, v in st.items()})
+    np.testing.assert_array_equal(statistics.check_heuristics(st).numpy(), ref)
