@@ -1,0 +1,121 @@
+"""Initial-state generators for the batched search (reference: leniax/initializations.py:10-123, leniax/perlin.py:16-71).
+
+Generated on the device that will run the simulation (no 268 MB host->device copy per generation).  Random numbers come
+from a counter-based key (``RngKey``) feeding ``torch.Generator``; bit-parity with ``jax.random`` (threefry) is NOT
+provided — no reference test pins a perlin output (SURVEY.md §8c "parity unpinned").
+"""
+import math
+from typing import Callable, Dict, List, Tuple
+
+import torch
+
+from .loader import make_array_compressible
+
+
+class RngKey:
+    """Minimal splittable key (stands in for ``jax.random.PRNGKey``): a 64-bit integer, split with SplitMix64."""
+    _MASK = (1 << 64) - 1
+
+    def __init__(self, seed: int):
+        self.seed = int(seed) & self._MASK
+
+    @staticmethod
+    def _mix(z: int) -> int:
+        z = (z + 0x9E3779B97F4A7C15) & RngKey._MASK
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & RngKey._MASK
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & RngKey._MASK
+        return z ^ (z >> 31)
+
+    def split(self, num: int = 2) -> List['RngKey']:
+        return [RngKey(self._mix(self.seed + 0x632BE59BD9B4E019 * (i + 1))) for i in range(num)]
+
+    def generator(self, device) -> torch.Generator:
+        g = torch.Generator(device=device)
+        g.manual_seed(self.seed & ((1 << 63) - 1))
+        return g
+
+    def tolist(self):
+        return [self.seed >> 32, self.seed & 0xFFFFFFFF]
+
+    def __repr__(self):
+        return f'RngKey({self.seed:#x})'
+
+
+def _device(device=None):
+    if device is not None:
+        return torch.device(device)
+    return torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+
+
+def interpolant(t):
+    return t * t * t * (t * (t * 6 - 15) + 10)
+
+
+def generate_perlin_noise_2d(angles: torch.Tensor, shape: Tuple[int, int], res: Tuple[int, int], nb_noise: int = 1) -> torch.Tensor:
+    """leniax/perlin.py:16-71, including its ``diff``-based corner slicing."""
+    gradients = torch.stack([torch.cos(angles), torch.sin(angles)], dim=-1)  # [n, Hr, Wr, 2]
+    gradients = torch.cat([gradients, gradients[:, :1]], dim=1)
+    gradients = torch.cat([gradients, gradients[:, :, :1]], dim=2)  # wrap pad -> [n, Hr+1, Wr+1, 2]
+    d = (shape[0] // res[0], shape[1] // res[1])
+    gradients = gradients.repeat_interleave(d[0], dim=1).repeat_interleave(d[1], dim=2)
+    diff = [gradients.shape[1] - shape[0], gradients.shape[2] - shape[1]]
+    g00 = gradients[:, :-diff[0], :-diff[1]]
+    g10 = gradients[:, diff[0]:, :-diff[1]]
+    g01 = gradients[:, :-diff[0], diff[1]:]
+    g11 = gradients[:, diff[0]:, diff[1]:]
+    dev = angles.device
+    gy = (torch.arange(shape[0], device=dev, dtype=torch.float32) * (res[0] / shape[0])) % 1
+    gx = (torch.arange(shape[1], device=dev, dtype=torch.float32) * (res[1] / shape[1])) % 1
+    g0, g1 = torch.meshgrid(gy, gx, indexing='ij')
+    g0, g1 = g0[None], g1[None]
+    n00 = g0 * g00[..., 0] + g1 * g00[..., 1]
+    n10 = (g0 - 1) * g10[..., 0] + g1 * g10[..., 1]
+    n01 = g0 * g01[..., 0] + (g1 - 1) * g01[..., 1]
+    n11 = (g0 - 1) * g11[..., 0] + (g1 - 1) * g11[..., 1]
+    t0, t1 = interpolant(g0), interpolant(g1)
+    n0 = n00 * (1 - t0) + t0 * n10
+    n1 = n01 * (1 - t0) + t0 * n11
+    return math.sqrt(2) * ((1 - t1) * n0 + t1 * n1)
+
+
+def random_uniform(rng_key: RngKey, nb_init: int, world_size: List[int], R: float, gf_params: List, device=None):
+    """initializations.py:10-32 (maxvals broadcast over the world axes)."""
+    device = _device(device)
+    rng_key, subkey = rng_key.split()
+    maxvals = torch.linspace(0.4, 1., nb_init, device=device).reshape([nb_init] + [1] * len(world_size))
+    cells = torch.rand([nb_init] + list(world_size), generator=subkey.generator(device), device=device) * maxvals
+    return rng_key, make_array_compressible(cells)
+
+
+def perlin(rng_key: RngKey, nb_init: int, world_size: List[int], R: float, gf_params: List, device=None):
+    """initializations.py:35-77."""
+    device = _device(device)
+    kernel_radius = math.ceil(R)
+    res = [world_size[0] // (kernel_radius * 3), world_size[1] // (kernel_radius * 2)]
+    lo = gf_params[0]
+    hi = min(1, 3 * lo)
+    scaling = torch.tensor([lo + i / nb_init * (hi - lo) for i in range(nb_init)], dtype=torch.float32, device=device)[:, None, None]
+    rng_key, subkey = rng_key.split()
+    angles = 2 * math.pi * torch.rand([nb_init] + res, generator=subkey.generator(device), device=device)
+    cells = generate_perlin_noise_2d(angles, tuple(world_size), tuple(res), nb_init)
+    cells = cells - cells.amin(dim=(1, 2), keepdim=True)
+    cells = cells / cells.amax(dim=(1, 2), keepdim=True)
+    cells = cells * scaling
+    return rng_key, make_array_compressible(cells[:, None])
+
+
+def cropped_perlin(rng_key: RngKey, nb_init: int, world_size: List[int], R: float, gf_params: List, device=None):
+    """initializations.py:80-116."""
+    rng_key, init_cells = perlin(rng_key, nb_init, world_size, R, gf_params, device)
+    size = math.ceil(R) * 2
+    pad_left = (128 - size) // 2
+    pad_right = pad_left + 1 if pad_left * 2 + size != 128 else pad_left
+    init_cells = torch.nn.functional.pad(init_cells[:, :, 24:24 + size, 24:24 + size], (pad_left, pad_right, pad_left, pad_right))
+    return rng_key, make_array_compressible(init_cells)
+
+
+register: Dict[str, Callable] = {
+    'random_uniform': random_uniform,
+    'perlin': perlin,
+    'cropped_perlin': cropped_perlin,
+}

@@ -274,3 +274,51 @@ def test_full_size_properties(golden_dir):
     for k in ('mass', 'mass_speed', 'inertia', 'growth'):
         assert torch.equal(s3[k], s1[k][:, :, sl]), k
     assert torch.equal(f3, f1[:, sl])
+
+
+def test_qd_eval_batch_path_matches_oracle(golden_dir):
+    """qd.build_eval_lenia_config_mem_optimized_fn (leniax/qd.py:33-77): per-solution kernels/params, perlin inits generated on
+    the device, fitness = max N, behaviours = last-128-row means.  Integer outputs must be identical to the oracle's."""
+    from leniax_b200 import initializations, lenia, qd
+    cfg, ocfg = _setup(golden_dir, 'orbium-test')
+    cfg['run_params']['max_run_iter'] = 150
+    cfg['run_params']['nb_init_search'] = 6
+    cfg['algo']['init_slug'] = 'perlin'
+    cfg['genotype'] = [{'key': 'kernels_params.0.gf_params.0', 'domain': [0.1, 0.3], 'type': 'float'},
+                       {'key': 'kernels_params.0.gf_params.1', 'domain': [0.01, 0.04], 'type': 'float'}]
+    cfg['phenotype'] = ['behaviours.mass_density', 'behaviours.mass_speed']
+    key = initializations.RngKey(7)
+    inds = [lenia.LeniaIndividual(cfg, k, p) for k, p in zip(key.split(3), ([0.25, 0.17], [0.6, 0.5], [0.9, 0.9]))]
+    eval_fn = qd.build_eval_lenia_config_mem_optimized_fn(cfg, device=DEV)
+    _, dyn = qd.get_dynamic_args(cfg, inds, device=DEV)
+    assert dyn[0].shape == (3, 6, 1, 128, 128) and dyn[1].shape == (3, 1, 1, 1, 128, 128) and dyn[2].shape == (3, 1, 2)  # test_qd.py:80-88
+    out = eval_fn(inds)
+    # oracle on the very same initial states / parameters
+    cells0 = dyn[0].cpu().numpy()
+    ostats = []
+    for i, ind in enumerate(inds):
+        c = ind.get_config()
+        oK, om = lo.get_kernels_and_mapping(copy.deepcopy(c['kernels_params']), [128, 128], 1, 13)
+        st, _ = lo.run_scan(cells0[i], oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), 150,
+                            lo.build_update_fn(om), lo.build_compute_stats_fn(c['world_params'], c['render_params']), False)
+        ostats.append(st)
+    stats = {k: np.stack([s[k] for s in ostats]) for k in ostats[0]}
+    fitness, best, beh = lo.behaviours_of({k: v for k, v in stats.items() if k != 'channel_mass'})
+    for i, ind in enumerate(out):
+        assert ind.fitness == float(fitness[i])
+        assert ind.qd_config['algo']['best_init_idxs'] == np.nonzero(stats['N'][i] == stats['N'][i].max())[0].tolist()
+        np.testing.assert_allclose(ind.features, [beh[i]['mass_density'], beh[i]['mass_speed']], rtol=2e-3, atol=2e-4)
+
+
+def test_sharded_entry_point_single_rank(golden_dir):
+    from leniax_b200 import distributed as lnx_dist, qd
+    steps, n = 140, 6
+    cfg, ocfg, worlds, K, mapping, ufn, sfn = _orbium_batch(golden_dir, n, seed=9)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    cells0 = torch.from_numpy(worlds).to(DEV).reshape(2, 3, 1, 128, 128)
+    args = (cells0, torch.stack([K, K]), torch.stack([gf, gf]), torch.stack([w, w]), torch.tensor([10., 10.], device=DEV))
+    summary, keys, _ = lnx_dist.run_scan_mem_optimized_sharded(None, *args, steps, 13, ufn, sfn)
+    stats, _ = runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn)
+    ref, _ = qd.summarize_stats(stats)
+    assert torch.equal(summary[..., 0], stats['N'])
+    torch.testing.assert_close(summary, ref, rtol=1e-6, atol=1e-7)
