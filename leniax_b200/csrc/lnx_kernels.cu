@@ -23,7 +23,9 @@ constexpr int BAR_COMPUTE = 1;      // named barrier: the 256 compute threads
 constexpr int BAR_PARTIALS = 2;     // compute arrive  -> statistics warp sync   (partials of step t are in smem)
 constexpr int BAR_CARRY = 3;        // statistics warp arrive -> compute sync    (shift / stop flag of step t ready)
 constexpr int KT_F4 = 16 * NT;      // float4 per kernel table (complex multipliers)
-constexpr int KPQ_F4 = 32 * 4;      // float4 per packed-column table
+constexpr int KPQ_F4 = 32 * KPQ_LANES;  // float4 per packed-column table (Kp, Kq)
+constexpr int SCRATCH_BYTES = 2 * 4 * 32 * 8;  // packed-column exchange of warp 0
+constexpr int TW_BYTES = TW_TABLE_F4 * 16;     // run-time twiddle table of P2/P4
 constexpr int KTAB_F4 = KT_F4 + KPQ_F4;
 constexpr int NPART_FUSED = PT_FIXED + 1;
 constexpr int NPART_MAX = PT_FIXED + MAX_C;
@@ -37,7 +39,11 @@ struct Ctrl {
     int world;
     int shift0, shift1;
     int stop;
+    float tot[NPART_MAX];          // CTA-wide sums of the step (statistics warp)
+    float row[ST_COUNT + MAX_C];   // finished statistics row
 };
+constexpr int CTRL_BYTES = 256;
+static_assert(sizeof(Ctrl) <= CTRL_BYTES, "Ctrl does not fit its shared-memory slot");
 
 struct RunArgs {
     const float* cells0;
@@ -86,12 +92,12 @@ __global__ void __launch_bounds__(NT) lnx_prepare_kernel(PrepArgs P) {
         }
         tab[i * NT + tid] = make_float4(v[0].x * scale, v[0].y * scale, v[1].x * scale, v[1].y * scale);
     }
-    if (tid < 4) {
+    if (tid < KPQ_LANES) {
         for (int s = 0; s < 32; ++s) {
             const int m = p3_slot_m(tid, s);
             const float2 k0 = Kf[m * WS], k64 = Kf[m * WS + 64];
             const float h = 0.5f * scale;
-            tab[KT_F4 + s * 4 + tid] = make_float4((k0.x + k64.x) * h, (k0.y + k64.y) * h, (k0.x - k64.x) * h, (k0.y - k64.y) * h);
+            tab[KT_F4 + s * KPQ_LANES + tid] = make_float4((k0.x + k64.x) * h, (k0.y + k64.y) * h, (k0.x - k64.x) * h, (k0.y - k64.y) * h);
         }
     }
 }
@@ -117,15 +123,16 @@ __global__ void __launch_bounds__(NT) lnx_rfft2_kernel(const float* __restrict__
     const int tid = threadIdx.x, l = t_sub(tid) & 3;
     const float* img = images + (size_t)blockIdx.x * (WS * WS);
     float2* out = spectra + (size_t)blockIdx.x * (WS * WS);
+    float4* twtab = reinterpret_cast<float4*>(smem + 65536);
     Regs R;
-    init_twiddles(tid, R, c_tw128);
+    init_twiddle_table(tid, twtab, c_tw128);
 #pragma unroll 8
     for (int j = 0; j < 32; ++j) R.v[j] = make_float2(img[cell_row(tid, 0) * WS + 4 * j + l], img[cell_row(tid, 1) * WS + 4 * j + l]);
     phase1(tid, R, W);
     __syncthreads();
     phase2_load(tid, R, W);
     __syncthreads();
-    phase2_compute_store(tid, R, W);
+    phase2_compute_store(tid, R, W, twtab);
     __syncthreads();
     phase3_load_fft(tid, R, W);
     const int col = t_col(tid);
@@ -196,37 +203,36 @@ __device__ __forceinline__ void scatter_state(float* img, const float4* A4, int 
     }
 }
 
-// statistics warp: reduce the partials of one step and finalise (all lanes redundantly, lane 0 publishes)
+// statistics warp: reduce the partials of one step (rolled loop: this code is fetched every step, keep it small),
+// lane 0 finalises, lanes 0..10+C store the row
 __device__ __forceinline__ float stats_step(const RunArgs& P, const float* part, int npart, int lane, int t, int sol, int init,
-                                            StatsCarry& S) {
-    float totals[NPART_MAX];
-#pragma unroll
-    for (int k = 0; k < NPART_MAX; ++k) {
+                                            StatsCarry& S, Ctrl* ctrl, float invR2, float invR, float inv_dt) {
+#pragma unroll 1
+    for (int k = 0; k < npart; ++k) {
         float a = 0.f;
-        if (k < npart) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a += part[k * NT + lane + 32 * i];
+        for (int i = 0; i < 8; ++i) a += part[k * NT + lane + 32 * i];
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-        }
-        totals[k] = a;
+        for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) ctrl->tot[k] = a;
     }
-    float row[ST_COUNT], cm[MAX_C];
-    const float sc = stats_finalize(totals, P.C, t, P.R, P.stats_dt, S, row, cm);
-    if (lane == 0) {
-        const size_t plane = (size_t)P.n_sols * P.max_iter * P.n_init;
-        const size_t idx = ((size_t)sol * P.max_iter + t) * P.n_init + init;
-#pragma unroll
-        for (int k = 0; k < ST_COUNT; ++k) P.stats[k * plane + idx] = row[k];
-        for (int c = 0; c < P.C; ++c) P.channel_mass[idx * P.C + c] = cm[c];
-    }
+    __syncwarp();
+    float sc = 0.f;
+    if (lane == 0) sc = stats_finalize(ctrl->tot, P.C, t, invR2, invR, inv_dt, S, ctrl->row);
+    sc = __shfl_sync(0xffffffffu, sc, 0);
+    const size_t plane = (size_t)P.n_sols * P.max_iter * P.n_init;
+    const size_t idx = ((size_t)sol * P.max_iter + t) * P.n_init + init;
+    if (lane < ST_COUNT)
+        P.stats[lane * plane + idx] = ctrl->row[lane];
+    else if (lane < ST_COUNT + P.C)
+        P.channel_mass[idx * P.C + (lane - ST_COUNT)] = ctrl->row[lane];
     return sc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // fused kernel: C = K = 1
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int FUSED_SMEM = 65536 * 3 + KPQ_F4 * 16 + NPART_FUSED * NT * 4 + 64;
+constexpr int FUSED_SMEM = 65536 * 3 + KPQ_F4 * 16 + NPART_FUSED * NT * 4 + CTRL_BYTES + SCRATCH_BYTES + TW_BYTES;
 
 template <int GF, int SF, bool NP>
 __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs P) {
@@ -237,12 +243,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
     float4* Kpq = reinterpret_cast<float4*>(smem + 196608);
     float* part = reinterpret_cast<float*>(smem + 196608 + KPQ_F4 * 16);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 196608 + KPQ_F4 * 16 + NPART_FUSED * NT * 4);
+    float2* scratch = reinterpret_cast<float2*>(smem + 196608 + KPQ_F4 * 16 + NPART_FUSED * NT * 4 + CTRL_BYTES);
+    float4* twtab = reinterpret_cast<float4*>(smem + 196608 + KPQ_F4 * 16 + NPART_FUSED * NT * 4 + CTRL_BYTES + SCRATCH_BYTES);
 
     const int tid = threadIdx.x;
     const int n_worlds = P.n_sols * P.n_init;
     const bool early = (P.flags & LNX_RUN_EARLY_STOP) != 0;
     Regs R;
-    if (tid < NT) init_twiddles(tid, R, c_tw128);
+    init_twiddle_table(tid, twtab, c_tw128);  // made visible by the __syncthreads of the first world fetch
     int loaded_sol = -1;
 
     for (;;) {
@@ -269,10 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
             FusedConsts fc;
             {
                 const float m = __ldg(P.gf_params + (size_t)sol * 2), s = __ldg(P.gf_params + (size_t)sol * 2 + 1);
-                fc.gf = gf_prepare(GF, m, s);
-                fc.w = __ldg(P.weights + sol);
-                fc.inv_wsum = P.mean ? 1.0f / fc.w : 1.0f;
-                fc.dt = __ldg(P.dt + sol);
+                fc = fused_consts(GF, m, s, __ldg(P.weights + sol), P.mean, __ldg(P.dt + sol));
             }
             bar_sync(BAR_COMPUTE, NT);  // Kt / Kpq visible to every compute thread
 
@@ -284,15 +289,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
                 __syncwarp();
                 phase2_load(tid, R, W);
                 __syncwarp();
-                phase2_compute_store(tid, R, W);
+                phase2_compute_store(tid, R, W, twtab);
                 bar_sync(BAR_COMPUTE, NT);
                 phase3_load_fft(tid, R, W);
-                phase3_multiply(tid, R, Kt, Kpq);
+                if (tid < 32) {  // warp 0 owns the packed DC|Nyquist column
+                    phase3_col0_stash(tid, R, scratch);
+                    __syncwarp();
+                    phase3_col0_compute(tid, scratch, Kpq);
+                    __syncwarp();
+                }
+                phase3_multiply(tid, R, Kt);
+                if (tid < 32) phase3_col0_fetch(tid, R, scratch);
                 phase3_ifft_store(tid, R, W);
                 bar_sync(BAR_COMPUTE, NT);
                 phase4_load(tid, R, W);
                 __syncwarp();
-                phase4_compute_store(tid, R, W);
+                phase4_compute_store(tid, R, W, twtab);
                 __syncwarp();
                 phase5_load(tid, R, W);
                 phase5_ifft(R);
@@ -312,11 +324,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
         } else {
             // ------------------------------------------------ statistics warp ------------------------------------------
             const int lane = tid - NT;
+            const float invR2 = 1.0f / (P.R * P.R), invR = 1.0f / P.R, inv_dt = 1.0f / P.stats_dt;
             StatsCarry S;
             S.reset();
             for (int t = 0; t < P.max_iter; ++t) {
                 bar_sync(BAR_PARTIALS, NTHREADS);
-                const float sc = stats_step(P, part, NPART_FUSED, lane, t, sol, init, S);
+                const float sc = stats_step(P, part, NPART_FUSED, lane, t, sol, init, S, ctrl, invR2, invR, inv_dt);
                 const int stop = (early && sc == 0.f && t + 1 >= 128) ? 1 : 0;
                 if (lane == 0) {
                     ctrl->shift0 = S.shift[0];
@@ -342,7 +355,7 @@ struct GenericConsts {
     float inv_wsum[MAX_C];
     float dt;
 };
-constexpr int GENERIC_SMEM = 65536 + NPART_MAX * NT * 4 + 64 + (int)sizeof(GenericConsts);
+constexpr int GENERIC_SMEM = 65536 + NPART_MAX * NT * 4 + CTRL_BYTES + SCRATCH_BYTES + TW_BYTES + (int)sizeof(GenericConsts);
 constexpr int PLANE_F4 = 16 * NT;  // float4 per thread-private image
 
 __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArgs P) {
@@ -350,7 +363,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
     float2* W = reinterpret_cast<float2*>(smem);
     float* part = reinterpret_cast<float*>(smem + 65536);
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 65536 + NPART_MAX * NT * 4);
-    GenericConsts* gc = reinterpret_cast<GenericConsts*>(smem + 65536 + NPART_MAX * NT * 4 + 64);
+    float2* scratch = reinterpret_cast<float2*>(smem + 65536 + NPART_MAX * NT * 4 + CTRL_BYTES);
+    float4* twtab = reinterpret_cast<float4*>(smem + 65536 + NPART_MAX * NT * 4 + CTRL_BYTES + SCRATCH_BYTES);
+    GenericConsts* gc = reinterpret_cast<GenericConsts*>(smem + 65536 + NPART_MAX * NT * 4 + CTRL_BYTES + SCRATCH_BYTES + TW_BYTES);
 
     const int tid = threadIdx.x;
     const int C = P.C, K = P.K;
@@ -361,7 +376,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
     float4* Sp = Ast + (size_t)C * PLANE_F4;                            // [C] forward spectra (P3 layout)
     float4* Fa = Sp + (size_t)C * PLANE_F4;                             // [C] field accumulators
     Regs R;
-    if (tid < NT) init_twiddles(tid, R, c_tw128);
+    init_twiddle_table(tid, twtab, c_tw128);
 
     for (;;) {
         if (tid == NT) {
@@ -399,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                     __syncwarp();
                     phase2_load(tid, R, W);
                     __syncwarp();
-                    phase2_compute_store(tid, R, W);
+                    phase2_compute_store(tid, R, W, twtab);
                     bar_sync(BAR_COMPUTE, NT);
                     phase3_load_fft(tid, R, W);
                     float4* sp = Sp + (size_t)c * PLANE_F4;
@@ -418,12 +433,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                         R.v[2 * i] = make_float2(s4.x, s4.y);
                         R.v[2 * i + 1] = make_float2(s4.z, s4.w);
                     }
-                    phase3_multiply(tid, R, tab + (size_t)k * KTAB_F4, tab + (size_t)k * KTAB_F4 + KT_F4);
+                    if (tid < 32) {
+                        phase3_col0_stash(tid, R, scratch);
+                        __syncwarp();
+                        phase3_col0_compute(tid, scratch, tab + (size_t)k * KTAB_F4 + KT_F4);
+                        __syncwarp();
+                    }
+                    phase3_multiply(tid, R, tab + (size_t)k * KTAB_F4);
+                    if (tid < 32) phase3_col0_fetch(tid, R, scratch);
                     phase3_ifft_store(tid, R, W);
                     bar_sync(BAR_COMPUTE, NT);
                     phase4_load(tid, R, W);
                     __syncwarp();
-                    phase4_compute_store(tid, R, W);
+                    phase4_compute_store(tid, R, W, twtab);
                     __syncwarp();
                     phase5_load(tid, R, W);
                     bar_sync(BAR_COMPUTE, NT);  // W is free for the next kernel's spectrum
@@ -475,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                 const int sh0 = ctrl->shift0, sh1 = ctrl->shift1;
                 const float xr0 = rolled_coord(cell_row(tid, 0), sh0), xr1 = rolled_coord(cell_row(tid, 1), sh0);
                 const float cbase = (float)(((l - sh1) & (WS - 1)) - WS / 2);
-                float mx_r = 0.f, mx2_r = 0.f, gx_r = 0.f, mxc = 0.f, mx2c = 0.f, gxc = 0.f, cnt_a = 0.f, cnt_g = 0.f, g00 = 0.f;
+                float mx_r = 0.f, mx2_r = 0.f, gx_r = 0.f, mxc = 0.f, mx2c = 0.f, gxc = 0.f, g00 = 0.f, cnt_a = 0.f, cnt_g = 0.f;
                 for (int c = 0; c < C; ++c) {
                     float4* st = Ast + (size_t)c * PLANE_F4;
                     const float4* fa = Fa + (size_t)c * PLANE_F4;
@@ -543,11 +565,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                 for (int c = 0; c < C; ++c) scatter_state(P.final_cells + ((size_t)world * C + c) * (WS * WS), Ast + (size_t)c * PLANE_F4, tid);
         } else {
             const int lane = tid - NT;
+            const float invR2 = 1.0f / (P.R * P.R), invR = 1.0f / P.R, inv_dt = 1.0f / P.stats_dt;
             StatsCarry S;
             S.reset();
             for (int t = 0; t < P.max_iter; ++t) {
                 bar_sync(BAR_PARTIALS, NTHREADS);
-                const float sc = stats_step(P, part, npart, lane, t, sol, init, S);
+                const float sc = stats_step(P, part, npart, lane, t, sol, init, S, ctrl, invR2, invR, inv_dt);
                 const int stop = (early && sc == 0.f && t + 1 >= 128) ? 1 : 0;
                 if (lane == 0) {
                     ctrl->shift0 = S.shift[0];
@@ -614,7 +637,7 @@ static int ensure_device_init(int* dev_out, int* sms_out) {
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, GENERIC_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        LNX_CUDA(cudaFuncSetAttribute(lnx_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + TW_BYTES));
         sms[dev] = prop.multiProcessorCount;
         done[dev] = true;
     }
@@ -703,7 +726,7 @@ int lnx_rfft2(const lnx_plan* p, int32_t n_images, const float* images, void* sp
     if (!images || !spectra || n_images < 1) return fail(LNX_ERR_INVALID, "lnx_rfft2: bad argument");
     const int rc = ensure_device_init(nullptr, nullptr);
     if (rc != LNX_OK) return rc;
-    lnx_rfft2_kernel<<<n_images, NT, 65536, static_cast<cudaStream_t>(stream)>>>(images, static_cast<float2*>(spectra));
+    lnx_rfft2_kernel<<<n_images, NT, 65536 + TW_BYTES, static_cast<cudaStream_t>(stream)>>>(images, static_cast<float2*>(spectra));
     LNX_CUDA(cudaGetLastError());
     return LNX_OK;
 }

@@ -120,9 +120,9 @@ LNX_HD float rolled_coord(int idx, int shift) { return (float)(((idx - shift) & 
 struct CellAcc {
     float sa0, sa1;   // sum of cells in row p / p+64 (all channels)
     float sg0, sg1;   // sum of positive field
-    float cnt_a, cnt_g, cnt_p;
-    float mxc, mx2c, gxc;  // column-coordinate moments
-    LNX_HD void clear() { sa0 = sa1 = sg0 = sg1 = cnt_a = cnt_g = cnt_p = mxc = mx2c = gxc = 0.f; }
+    float cnt_a, cnt_g, cnt_p;  // counts kept as floats (exact up to 2^24): FSET.BF + FADD per cell
+    float mxc, mx2c, gxc;       // column-coordinate moments
+    LNX_HD void clear() { sa0 = sa1 = sg0 = sg1 = mxc = mx2c = gxc = cnt_a = cnt_g = cnt_p = 0.f; }
 };
 
 // statistics contribution of one column j of the thread's two rows: a0/a1 = cells, f0/f1 = field
@@ -133,12 +133,18 @@ LNX_HD void acc_cells(CellAcc& A, float xc, float a0, float a1, float f0, float 
     const float g0 = fmaxf(f0, 0.f), g1 = fmaxf(f1, 0.f);  // statistics.py:65
     A.sg0 += g0;
     A.sg1 += g1;
-    A.cnt_g += (g0 > EPS ? 1.f : 0.f) + (g1 > EPS ? 1.f : 0.f);
+    A.cnt_g += (f0 > EPS ? 1.f : 0.f) + (f1 > EPS ? 1.f : 0.f);  // max(f, 0) > eps <=> f > eps
     const float as = a0 + a1, gs = g0 + g1;
     const float ax = as * xc;
     A.mxc += ax;
     A.mx2c += ax * xc;
     A.gxc += gs * xc;
+}
+LNX_HD float opaque(float x) {  // hide the integer origin of a value so ptxas keeps the arithmetic on the FP pipe
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+f"(x));
+#endif
+    return x;
 }
 LNX_HD float col_coord(float base /* (l - shift1) & 127 - 64 */, int j) {
     const float t = base + (float)(4 * j);
@@ -148,16 +154,47 @@ LNX_HD float col_coord(float base /* (l - shift1) & 127 - 64 */, int j) {
 // ---- fused single-channel single-kernel cell phase (the north-star fast path) ----
 struct FusedConsts {
     GfConst gf;
-    float w;         // kernels_weight_per_channel[0][0]
-    float inv_wsum;  // 1 / sum_k W[0][k] (weighted_mean) or 1 (weighted_sum)
-    float dt;        // 1 / T of this solution (runner.py:307)
+    float c;   // w * (1 / sum_k W[0][k]) for weighted_mean, w for weighted_sum (core.py:202-242 with one kernel)
+    float c2;  // 2 c
+    float dt;  // 1 / T of this solution (runner.py:307)
 };
+LNX_HD FusedConsts fused_consts(int gf, float m, float s, float w, int mean, float dt) {
+    FusedConsts K;
+    K.gf = gf_prepare(gf, m, s);
+    K.c = mean ? w * (1.0f / w) : w;
+    K.c2 = 2.0f * K.c;
+    K.dt = dt;
+    return K;
+}
+// field = c * growth(X); for poly_quad4 the affine tail 2 o^4 - 1 and the weight fold into one FMA
+template <int GF, bool NP>
+LNX_HD float field_fused(float X, const FusedConsts& K) {
+    if constexpr (GF == GF_POLY_QUAD4) {
+        const float t = X - K.gf.m;
+        float o = 1.0f - (t * t) * K.gf.k0;
+        if constexpr (NP)
+            o = (o < 0.f) ? 0.f : o;
+        else
+            o = fmaxf(o, 0.f);
+        const float o2 = o * o;
+        return K.c2 * (o2 * o2) - K.c;
+    } else {
+        return K.c * growth<GF, NP>(X, K.gf);
+    }
+}
+LNX_HD float saturate01(float x) {
+#ifdef __CUDA_ARCH__
+    return __saturatef(x);
+#else
+    return fminf(fmaxf(x, 0.f), 1.f);
+#endif
+}
 template <int GF, int SF, bool NP>
 LNX_HD void cells_fused(int tid, const float2* pot /* [32] */, float4* A4, const FusedConsts& K, int shift0, int shift1,
                         float* part /* [NPART][256] */) {
     const int l = t_sub(tid) & 3;
     const float xr0 = rolled_coord(cell_row(tid, 0), shift0), xr1 = rolled_coord(cell_row(tid, 1), shift0);
-    const float cbase = (float)(((l - shift1) & (WS - 1)) - WS / 2);
+    const float cbase = opaque((float)(((l - shift1) & (WS - 1)) - WS / 2));
     CellAcc A;
     A.clear();
 #pragma unroll
@@ -170,11 +207,15 @@ LNX_HD void cells_fused(int tid, const float2* pot /* [32] */, float4* A4, const
             const int j = 4 * i + e;
             const float p0 = pot[j].x, p1 = pot[j].y;
             A.cnt_p += (p0 > EPS ? 1.f : 0.f) + (p1 > EPS ? 1.f : 0.f);  // statistics.py:70
-            const float f0 = (K.w * growth<GF, NP>(p0, K.gf)) * K.inv_wsum;
-            const float f1 = (K.w * growth<GF, NP>(p1, K.gf)) * K.inv_wsum;
+            const float f0 = field_fused<GF, NP>(p0, K), f1 = field_fused<GF, NP>(p1, K);
             acc_cells(A, col_coord(cbase, j), a0[e], a1[e], f0, f1);
-            n0[e] = state_update<SF, NP>(a0[e], f0, K.dt);
-            n1[e] = state_update<SF, NP>(a1[e], f1, K.dt);
+            if constexpr (SF == SF_V1 && !NP) {  // clip(a + dt f, 0, 1) as one saturating FMA (no NaN possible here)
+                n0[e] = saturate01(a0[e] + K.dt * f0);
+                n1[e] = saturate01(a1[e] + K.dt * f1);
+            } else {
+                n0[e] = state_update<SF, NP>(a0[e], f0, K.dt);
+                n1[e] = state_update<SF, NP>(a1[e], f1, K.dt);
+            }
         }
         A4[i * NT + tid] = make_float4(n0[0], n0[1], n0[2], n0[3]);
         A4[(8 + i) * NT + tid] = make_float4(n1[0], n1[1], n1[2], n1[3]);
@@ -213,10 +254,21 @@ struct StatsCarry {
     }
 };
 
-LNX_HD float py_fmod(float x, float m) {  // sign of the divisor, like jnp `%`
-    float r = fmodf(x, m);
-    if (r != 0.f && ((r < 0.f) != (m < 0.f))) r += m;
+// x mod 360 with the sign of the divisor (jnp `%`), for |x| of a few thousand at most (angles): one floor + FMA
+LNX_HD float mod360(float x) {
+    float r = x - 360.f * floorf(x * (1.0f / 360.f));
+    if (r < 0.f) r += 360.f;
+    if (r >= 360.f) r -= 360.f;
     return r;
+}
+// division used by the per-step statistics (once per world-step, on the statistics warp): approximate reciprocal based
+// on the device (2 ulp) to keep the warp's code small — the statistics code is fetched every step by every SM
+LNX_HD float sdiv(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
 }
 LNX_HD int py_mod(int x, int m) {
     int r = x % m;
@@ -225,54 +277,60 @@ LNX_HD int py_mod(int x, int m) {
 LNX_HD int trunc_to_int(float x) { return (x == x && fabsf(x) < 2.0e9f) ? (int)x : 0; }
 
 // totals[PT_*] are the CTA-wide sums.  Writes the 11 scalar stats + C channel masses, updates the carry and the
-// stop criteria.  Returns should_continue (0/1) for this step.
-LNX_HD float stats_finalize(const float* totals, int C, int t, float R, float dt, StatsCarry& S, float* out /* [ST_COUNT] */,
-                            float* cm_out /* [C] */) {
-    const float R2 = R * R;
+// stop criteria.  Returns should_continue (0/1) for this step.  invR2 = 1/R^2, invR = 1/R, inv_dt = 1/dt (per plan).
+LNX_HD float stats_finalize(const float* totals, int C, int t, float invR2, float invR, float inv_dt, StatsCarry& S,
+                            float* out /* [ST_COUNT + C]: scalar stats then channel masses */) {
+    float* cm_out = out + ST_COUNT;
     float m00 = 0.f;
-    for (int c = 0; c < C; ++c) m00 += totals[PT_M00_C0 + c];
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        m00 += totals[PT_M00_C0 + c];
+        cm_out[c] = totals[PT_M00_C0 + c] * invR2;
+    }
     const float g00 = totals[PT_G00];
-    const float mass = m00 / R2;
-    const float mass_volume = totals[PT_CNT_A] / R2;
-    const float growth = g00 / R2;
-    const float growth_volume = totals[PT_CNT_G] / R2;
+    const float mass = m00 * invR2;
+    const float mass_volume = totals[PT_CNT_A] * invR2;
+    const float growth = g00 * invR2;
+    const float growth_volume = totals[PT_CNT_G] * invR2;
     out[ST_MASS] = mass;
     out[ST_MASS_VOLUME] = mass_volume;
-    out[ST_MASS_DENSITY] = mass / (mass_volume + EPS);
+    out[ST_MASS_DENSITY] = sdiv(mass, mass_volume + EPS);
     out[ST_GROWTH] = growth;
     out[ST_GROWTH_VOLUME] = growth_volume;
-    out[ST_GROWTH_DENSITY] = growth / (growth_volume + EPS);
-    out[ST_POTENTIAL_VOLUME] = totals[PT_CNT_P] / R2;
-    for (int c = 0; c < C; ++c) cm_out[c] = totals[PT_M00_C0 + c] / R2;
+    out[ST_GROWTH_DENSITY] = sdiv(growth, growth_volume + EPS);
+    out[ST_POTENTIAL_VOLUME] = totals[PT_CNT_P] * invR2;
 
-    const float c0 = totals[PT_MX_R] / (m00 + EPS), c1 = totals[PT_MX_C] / (m00 + EPS);
+    const float im = sdiv(1.0f, m00 + EPS), ig = sdiv(1.0f, g00 + EPS);
+    const float c0 = totals[PT_MX_R] * im, c1 = totals[PT_MX_C] * im;
     const float d0 = c0 - S.centroid[0], d1 = c1 - S.centroid[1];
     const float dist = sqrtf(d0 * d0 + d1 * d1);
-    out[ST_MASS_SPEED] = dist / R / dt;
-    const float angle = (atan2f(d1, d0) * 57.29577951308232f) * ((dist / R > 0.001f) ? 1.f : 0.f);
-    out[ST_MASS_ANGLE_SPEED] = (py_fmod(angle - S.angle + 540.f, 360.f) - 180.f) / dt;
-    const float gc0 = totals[PT_GX_R] / (g00 + EPS), gc1 = totals[PT_GX_C] / (g00 + EPS);
-    const float e0 = gc0 - c0, e1 = gc1 - c1;
-    out[ST_MASS_GROWTH_DIST] = sqrtf(e0 * e0 + e1 * e1) / R;
-    const float den = m00 * m00 + EPS;
-    out[ST_INERTIA] = (totals[PT_MX2_R] - c0 * totals[PT_MX_R]) / den + (totals[PT_MX2_C] - c1 * totals[PT_MX_C]) / den;
+    out[ST_MASS_SPEED] = dist * invR * inv_dt;
+    const float angle = (atan2f(d1, d0) * 57.29577951308232f) * ((dist * invR > 0.001f) ? 1.f : 0.f);
+    out[ST_MASS_ANGLE_SPEED] = (mod360(angle - S.angle + 540.f) - 180.f) * inv_dt;
+    const float e0 = totals[PT_GX_R] * ig - c0, e1 = totals[PT_GX_C] * ig - c1;
+    out[ST_MASS_GROWTH_DIST] = sqrtf(e0 * e0 + e1 * e1) * invR;
+    const float iden = sdiv(1.0f, m00 * m00 + EPS);
+    out[ST_INERTIA] = (totals[PT_MX2_R] - c0 * totals[PT_MX_R]) * iden + (totals[PT_MX2_C] - c1 * totals[PT_MX_C]) * iden;
 
     // carry (statistics.py:117-124)
     const int s0 = trunc_to_int(c0), s1 = trunc_to_int(c1);
-    S.shift[0] = py_mod(S.shift[0] + s0, WS);
-    S.shift[1] = py_mod(S.shift[1] + s1, WS);
+    S.shift[0] = (S.shift[0] + s0) & (WS - 1);  // Python-sign modulo for a power-of-two world size
+    S.shift[1] = (S.shift[1] + s1) & (WS - 1);
     S.centroid[0] = c0 - (float)s0;
     S.centroid[1] = c1 - (float)s1;
     S.angle = angle;
 
     // check_heuristics step t (statistics.py:144-183)
     if (t == 0) {
-        for (int c = 0; c < C; ++c) S.init_cm[c] = cm_out[c];
         S.prev_mass = mass;
         S.prev_sign = 0.f;
     }
     bool cond = true;
-    for (int c = 0; c < C; ++c) cond = cond && (cm_out[c] >= EPS) && (cm_out[c] <= 3.f * S.init_cm[c]);
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        if (t == 0) S.init_cm[c] = cm_out[c];
+        cond = cond && (cm_out[c] >= EPS) && (cm_out[c] <= 3.f * S.init_cm[c]);
+    }
     const float dm = mass - S.prev_mass;
     const float sign = (dm > 0.f) ? 1.f : ((dm < 0.f) ? -1.f : dm);  // jnp.sign: 0 -> 0, NaN -> NaN
     S.mono = S.mono * (sign == S.prev_sign ? 1 : 0) + 1;

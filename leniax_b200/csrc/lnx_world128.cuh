@@ -23,9 +23,18 @@ constexpr int REGION = 512;       // complex elements per exchange region (one p
 constexpr int W_COMPLEX = 16 * REGION;
 
 struct Regs {
-    float2 v[32];      // working set (re-used by every phase)
-    float2 twr[2][3];  // row twiddles   W128^(l * k1_s), l = 1..3   (P2/P4 mapping)
-    float2 twc[7];     // column twiddles W128^(r1 * m2), m2 = 1..7  (P2/P4 mapping)
+    float2 v[32];  // working set (re-used by every phase)
+};
+// Run-time twiddles of P2/P4 (they depend on the thread's a / r1) live in a 1.8 KB shared table and are re-read at the
+// start of both phases: keeping 26 values in registers for the whole kernel made ptxas spill them to local memory.
+//   TW_A: float4 [16 a ][3]  = W128^(l*k1_s) for (s,l) = (0,1),(0,2) | (0,3),(1,1) | (1,2),(1,3)      (cos, sin) pairs
+//   TW_R: float4 [16 r1][4]  = W128^(r1*m2)  for m2 = 1,2 | 3,4 | 5,6 | 7,-
+constexpr int TW_A_F4 = 16 * 3;
+constexpr int TW_R_F4 = 16 * 4;
+constexpr int TW_TABLE_F4 = TW_A_F4 + TW_R_F4;
+struct Twiddles {
+    float2 twr[2][3];  // row twiddles   W128^(l * k1_s), l = 1..3
+    float2 twc[7];     // column twiddles W128^(r1 * m2), m2 = 1..7
 };
 
 // ---- thread index decompositions -------------------------------------------------------------------------------
@@ -51,15 +60,38 @@ LNX_HD int e1_addr(int q, int k1, int l) {
 // E2 view [col][unit u][2]: unit = the pair of m2 handled together by a P3 thread.
 LNX_HD int e2_addr(int col, int u) { return col * 8 + ((u ^ ((col >> 1) & 3)) << 1); }
 
-// ---- twiddle setup (once per kernel) ------------------------------------------------------------------------------
-LNX_HD void init_twiddles(int tid, Regs& R, const float2* tw128 /* [128] = (cos, sin)(2 pi k / 128) */) {
+// ---- twiddle table setup (once per kernel, threads 0..15 fill row `tid` of both tables) ----------------------------
+LNX_HD void init_twiddle_table(int tid, float4* table, const float2* tw128 /* [128] = (cos, sin)(2 pi k / 128) */) {
+    if (tid < 16) {
+        float2 r[6];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int l = 1; l < 4; ++l) r[s * 3 + l - 1] = tw128[(l * k1_of(tid, s)) & 127];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) table[tid * 3 + i] = make_float4(r[2 * i].x, r[2 * i].y, r[2 * i + 1].x, r[2 * i + 1].y);
+        float2 c[8];
+#pragma unroll
+        for (int m2 = 1; m2 < 8; ++m2) c[m2 - 1] = tw128[(tid * m2) & 127];
+        c[7] = make_float2(1.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) table[TW_A_F4 + tid * 4 + i] = make_float4(c[2 * i].x, c[2 * i].y, c[2 * i + 1].x, c[2 * i + 1].y);
+    }
+}
+LNX_HD void load_twiddles(int tid, Twiddles& T, const float4* table) {
     const int a = t_sub(tid), r1 = t_group(tid);
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < 3; ++i) {
+        const float4 t = table[a * 3 + i];
+        (&T.twr[0][0])[2 * i] = make_float2(t.x, t.y);
+        (&T.twr[0][0])[2 * i + 1] = make_float2(t.z, t.w);
+    }
 #pragma unroll
-        for (int l = 1; l < 4; ++l) R.twr[s][l - 1] = tw128[(l * k1_of(a, s)) & 127];
-#pragma unroll
-    for (int m2 = 1; m2 < 8; ++m2) R.twc[m2 - 1] = tw128[(r1 * m2) & 127];
+    for (int i = 0; i < 4; ++i) {
+        const float4 t = table[TW_A_F4 + r1 * 4 + i];
+        T.twc[2 * i] = make_float2(t.x, t.y);
+        if (i < 3) T.twc[2 * i + 1] = make_float2(t.z, t.w);
+    }
 }
 // multiply by W = (c, -s) (forward) or conj (inverse), tw = (c, s)
 LNX_HD float2 tw_fwd(float2 d, float2 tw) { return make_float2(d.x * tw.x + d.y * tw.y, d.y * tw.x - d.x * tw.y); }
@@ -156,8 +188,10 @@ LNX_HD void p4_retangle(const float2* h /* [c*8 + i] */, float2* z /* [q*8 + s*4
 LNX_HDC int unit_m2(int u, int e) { return u == 0 ? (e == 0 ? 0 : 4) : (e == 0 ? u : 8 - u); }
 LNX_HDC int unit_pos(int u, int e) { return bitrev(unit_m2(u, e), 3); }
 
-LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W) {
+LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W, const float4* twtab) {
     const int a = t_sub(tid);
+    Twiddles T;
+    load_twiddles(tid, T, twtab);
     // row twiddle + radix-4 over l (forward, W4 = -i)
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -165,9 +199,9 @@ LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W) {
         for (int s = 0; s < 2; ++s) {
             float2* y = R.v + q * 8 + s * 4;
             const float2 y0 = y[0];
-            const float2 y1 = tw_fwd(y[1], R.twr[s][0]);
-            const float2 y2 = tw_fwd(y[2], R.twr[s][1]);
-            const float2 y3 = tw_fwd(y[3], R.twr[s][2]);
+            const float2 y1 = tw_fwd(y[1], T.twr[s][0]);
+            const float2 y2 = tw_fwd(y[2], T.twr[s][1]);
+            const float2 y3 = tw_fwd(y[3], T.twr[s][2]);
             const float2 t0 = cadd(y0, y2), t1 = csub(y0, y2), t2 = cadd(y1, y3);
             const float2 d = csub(y1, y3);
             const float2 t3 = make_float2(d.y, -d.x);  // * (-i)
@@ -187,7 +221,7 @@ LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W) {
         float2* hc = h + c * 8;
         fft_dif<8>(hc);  // over i; output position pos <-> m2 = bitrev3(pos)
 #pragma unroll
-        for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_fwd(hc[pos], R.twc[bitrev(pos, 3) - 1]);
+        for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_fwd(hc[pos], T.twc[bitrev(pos, 3) - 1]);
         const int col = col_of(a, c);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -232,7 +266,6 @@ LNX_HDC int col0_partner(int bidx0, int slot) {
 }
 
 // Kt: float4 [16][256] = complex multipliers for slots (2i, 2i+1) of thread tid (already scaled by 1/(2*128*128)).
-// Kpq: float4 [32][4] = (Kp, Kq) for slot s of threads 0..3 (packed DC|Nyquist column), see DESIGN.md §3.4.
 template <int I>
 LNX_HD void p3_mul_generic(Regs& R, const float4* Kt, int tid) {
     if constexpr (I < 16) {
@@ -242,30 +275,54 @@ LNX_HD void p3_mul_generic(Regs& R, const float4* Kt, int tid) {
         p3_mul_generic<I + 1>(R, Kt, tid);
     }
 }
-template <bool B0, int S>
-LNX_HD void p3_mul_col0(const float2* in, float2* out, const float4* Kpq, int tid) {
-    if constexpr (S < 32) {
-        const float4 k = Kpq[S * 4 + tid];
-        const float2 g = in[S], gp = in[col0_partner(B0, S)];
-        const float2 a = cmul(g, make_float2(k.x, k.y));
-        const float2 b = cmul(make_float2(gp.x, -gp.y), make_float2(k.z, k.w));
-        out[S] = cadd(a, b);
-        p3_mul_col0<B0, S + 1>(in, out, Kpq, tid);
-    }
+// Packed DC|Nyquist column (threads 0..3): G' = G*Kp + conj(G[-m])*Kq.  Done through a 2 KB shared scratch by all 32
+// lanes of warp 0 in a rolled loop (4 products per lane) so that the special case costs ~60 instructions of code instead
+// of 400+ unrolled ones (the loop body of this kernel is instruction-fetch bound).
+// Kpq: float4 [32 slots][4 threads] = (Kp, Kq).   scratch: float2 [2][4][32].
+constexpr int KPQ_LANES = 4;
+LNX_HD int bitrev4_rt(int x) { return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3); }
+LNX_HD int col0_partner_rt(bool b0, int s) {
+    const int h = s >> 4, pos = s & 15;
+    if (b0) return h == 0 ? bitrev4_rt((16 - bitrev4_rt(pos)) & 15) : 16 + (15 - pos);
+    return (1 - h) * 16 + (15 - pos);
 }
-LNX_HD void phase3_multiply(int tid, Regs& R, const float4* Kt, const float4* Kpq) {
-    if (tid >= 4) {
-        p3_mul_generic<0>(R, Kt, tid);
-    } else {
-        float2 o[32];
-        if (tid == 0)
-            p3_mul_col0<true, 0>(R.v, o, Kpq, tid);
-        else
-            p3_mul_col0<false, 0>(R.v, o, Kpq, tid);
+LNX_HD void phase3_col0_stash(int tid, const Regs& R, float2* scratch) {
+    if (tid < 4) {
+        float4* d = reinterpret_cast<float4*>(scratch + tid * 32);
 #pragma unroll
-        for (int s = 0; s < 32; ++s) R.v[s] = o[s];
+        for (int i = 0; i < 16; ++i) d[i] = make_float4(R.v[2 * i].x, R.v[2 * i].y, R.v[2 * i + 1].x, R.v[2 * i + 1].y);
     }
 }
+LNX_HD void phase3_col0_compute(int tid, float2* scratch, const float4* Kpq) {  // tid < 32
+    const int t = tid & 3;
+    float2 g[4], gp[4];
+    float4 k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // all loads first: the four products of a lane overlap their shared-memory latency
+        const int sl = (tid >> 2) + 8 * i;
+        g[i] = scratch[t * 32 + sl];
+        gp[i] = scratch[t * 32 + col0_partner_rt(t == 0, sl)];
+        k[i] = Kpq[sl * KPQ_LANES + t];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 a = cmul(g[i], make_float2(k[i].x, k[i].y));
+        const float2 b = cmul(make_float2(gp[i].x, -gp[i].y), make_float2(k[i].z, k[i].w));
+        scratch[128 + t * 32 + (tid >> 2) + 8 * i] = cadd(a, b);
+    }
+}
+LNX_HD void phase3_col0_fetch(int tid, Regs& R, const float2* scratch) {
+    if (tid < 4) {
+        const float4* d = reinterpret_cast<const float4*>(scratch + 128 + tid * 32);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 v = d[i];
+            R.v[2 * i] = make_float2(v.x, v.y);
+            R.v[2 * i + 1] = make_float2(v.z, v.w);
+        }
+    }
+}
+LNX_HD void phase3_multiply(int tid, Regs& R, const float4* Kt) { p3_mul_generic<0>(R, Kt, tid); }
 
 // =================================================================================================================
 // P4: load E2 (own region) -> inverse twiddle, inverse radix-8 over m2, retangle, inverse radix-4, twiddle, store E1
@@ -284,13 +341,15 @@ LNX_HD void phase4_load(int tid, Regs& R, const float2* W) {
         }
     }
 }
-LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W) {
+LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W, const float4* twtab) {
     const int a = t_sub(tid);
+    Twiddles T;
+    load_twiddles(tid, T, twtab);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float2* hc = R.v + c * 8;
 #pragma unroll
-        for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_inv(hc[pos], R.twc[bitrev(pos, 3) - 1]);
+        for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_inv(hc[pos], T.twc[bitrev(pos, 3) - 1]);
         ifft_dit<8>(hc);  // -> natural i
     }
     float2 z[32];
@@ -308,9 +367,9 @@ LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W) {
             const float2 d = csub(y[1], y[3]);
             const float2 t3 = make_float2(-d.y, d.x);  // * (+i)
             const float2 u0 = cadd(t0, t2);
-            const float2 u2 = tw_inv(csub(t0, t2), R.twr[s][1]);
-            const float2 u1 = tw_inv(cadd(t1, t3), R.twr[s][0]);
-            const float2 u3 = tw_inv(csub(t1, t3), R.twr[s][2]);
+            const float2 u2 = tw_inv(csub(t0, t2), T.twr[s][1]);
+            const float2 u1 = tw_inv(cadd(t1, t3), T.twr[s][0]);
+            const float2 u3 = tw_inv(csub(t1, t3), T.twr[s][2]);
             const int k1 = k1_of(a, s);
             reg4[e1_addr(q, k1, 0) >> 1] = make_float4(u0.x, u0.y, u1.x, u1.y);
             reg4[e1_addr(q, k1, 2) >> 1] = make_float4(u2.x, u2.y, u3.x, u3.y);

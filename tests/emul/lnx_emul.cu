@@ -12,6 +12,19 @@ static void make_tw(float2* tw) {
     for (int k = 0; k < 128; ++k) tw[k] = make_float2(Tw128::c[k], Tw128::s[k]);
 }
 
+// P3 with the warp-0 packed-column exchange; sub-phases split at the kernel's __syncwarp points
+static void run_phase3(std::vector<Regs>& regs, std::vector<float2>& W, const float* Kt, const float* Kpq) {
+    std::vector<float2> scratch(256);
+    for (int t = 0; t < NT; ++t) phase3_load_fft(t, regs[t], W.data());
+    for (int t = 0; t < 32; ++t) phase3_col0_stash(t, regs[t], scratch.data());
+    for (int t = 0; t < 32; ++t) phase3_col0_compute(t, scratch.data(), reinterpret_cast<const float4*>(Kpq));
+    for (int t = 0; t < NT; ++t) {
+        phase3_multiply(t, regs[t], reinterpret_cast<const float4*>(Kt));
+        if (t < 32) phase3_col0_fetch(t, regs[t], scratch.data());
+        phase3_ifft_store(t, regs[t], W.data());
+    }
+}
+
 extern "C" {
 
 int lnx_emul_e1_addr(int q, int k1, int l) { return e1_addr(q, k1, l); }
@@ -27,10 +40,10 @@ void lnx_emul_build_kt(const float* Kfull, float* Kt /* float4[16][256] */, floa
             const int m = p3_slot_m(tid, slot), col = t_col(tid);
             float* dst = Kt + ((slot >> 1) * NT + tid) * 4 + (slot & 1) * 2;
             if (col == 0) {
+                float* pq = Kpq + (slot * KPQ_LANES + tid) * 4;
                 dst[0] = dst[1] = 0.f;
                 const float* k0 = Kfull + (m * 128 + 0) * 2;
                 const float* k64 = Kfull + (m * 128 + 64) * 2;
-                float* pq = Kpq + (slot * 4 + tid) * 4;
                 pq[0] = (k0[0] + k64[0]) * 0.5f * scale;
                 pq[1] = (k0[1] + k64[1]) * 0.5f * scale;
                 pq[2] = (k0[0] - k64[0]) * 0.5f * scale;
@@ -48,21 +61,18 @@ void lnx_emul_potential(const float* state /* [128][128] */, const float* Kt, co
     std::vector<float2> W(W_COMPLEX);
     float2 tw[128];
     make_tw(tw);
-    for (int t = 0; t < NT; ++t) init_twiddles(t, regs[t], tw);
+    std::vector<float4> twtab(TW_TABLE_F4);
+    for (int t = 0; t < NT; ++t) init_twiddle_table(t, twtab.data(), tw);
     for (int t = 0; t < NT; ++t) {  // P1
         for (int j = 0; j < 32; ++j)
             regs[t].v[j] = make_float2(state[cell_row(t, 0) * 128 + cell_col(t, j)], state[cell_row(t, 1) * 128 + cell_col(t, j)]);
         phase1(t, regs[t], W.data());
     }
     for (int t = 0; t < NT; ++t) phase2_load(t, regs[t], W.data());
-    for (int t = 0; t < NT; ++t) phase2_compute_store(t, regs[t], W.data());
-    for (int t = 0; t < NT; ++t) {
-        phase3_load_fft(t, regs[t], W.data());
-        phase3_multiply(t, regs[t], reinterpret_cast<const float4*>(Kt), reinterpret_cast<const float4*>(Kpq));
-        phase3_ifft_store(t, regs[t], W.data());
-    }
+    for (int t = 0; t < NT; ++t) phase2_compute_store(t, regs[t], W.data(), twtab.data());
+    run_phase3(regs, W, Kt, Kpq);
     for (int t = 0; t < NT; ++t) phase4_load(t, regs[t], W.data());
-    for (int t = 0; t < NT; ++t) phase4_compute_store(t, regs[t], W.data());
+    for (int t = 0; t < NT; ++t) phase4_compute_store(t, regs[t], W.data(), twtab.data());
     for (int t = 0; t < NT; ++t) {
         phase5_load(t, regs[t], W.data());
         phase5_ifft(regs[t]);
@@ -87,18 +97,15 @@ static void run_fused(const float* cells0, const float* Kt, const float* Kpq, fl
     std::vector<float> part((PT_FIXED + 1) * NT);
     float2 tw[128];
     make_tw(tw);
-    for (int t = 0; t < NT; ++t) init_twiddles(t, regs[t], tw);
+    std::vector<float4> twtab(TW_TABLE_F4);
+    for (int t = 0; t < NT; ++t) init_twiddle_table(t, twtab.data(), tw);
     for (int t = 0; t < NT; ++t)
         for (int i = 0; i < 16; ++i) {
             float e[4];
             for (int k = 0; k < 4; ++k) e[k] = cells0[cell_row(t, i >> 3) * 128 + cell_col(t, 4 * (i & 7) + k)];
             A4[i * NT + t] = make_float4(e[0], e[1], e[2], e[3]);
         }
-    FusedConsts K;
-    K.gf = gf_prepare(GF, m, s);
-    K.w = w;
-    K.inv_wsum = mean ? 1.0f / w : 1.0f;
-    K.dt = 1.0f / T;
+    const FusedConsts K = fused_consts(GF, m, s, w, mean, 1.0f / T);
     StatsCarry S;
     S.reset();
     for (int step = 0; step < n_steps; ++step) {
@@ -114,14 +121,10 @@ static void run_fused(const float* cells0, const float* Kt, const float* Kpq, fl
             phase1(t, regs[t], W.data());
         }
         for (int t = 0; t < NT; ++t) phase2_load(t, regs[t], W.data());
-        for (int t = 0; t < NT; ++t) phase2_compute_store(t, regs[t], W.data());
-        for (int t = 0; t < NT; ++t) {
-            phase3_load_fft(t, regs[t], W.data());
-            phase3_multiply(t, regs[t], reinterpret_cast<const float4*>(Kt), reinterpret_cast<const float4*>(Kpq));
-            phase3_ifft_store(t, regs[t], W.data());
-        }
+        for (int t = 0; t < NT; ++t) phase2_compute_store(t, regs[t], W.data(), twtab.data());
+        run_phase3(regs, W, Kt, Kpq);
         for (int t = 0; t < NT; ++t) phase4_load(t, regs[t], W.data());
-        for (int t = 0; t < NT; ++t) phase4_compute_store(t, regs[t], W.data());
+        for (int t = 0; t < NT; ++t) phase4_compute_store(t, regs[t], W.data(), twtab.data());
         for (int t = 0; t < NT; ++t) phase5_load(t, regs[t], W.data());
         for (int t = 0; t < NT; ++t) {
             phase5_ifft(regs[t]);
@@ -145,10 +148,10 @@ static void run_fused(const float* cells0, const float* Kt, const float* Kpq, fl
                     if ((ln & off) == 0) lane[ln] = lane[ln] + lane[ln ^ off];
             totals[k] = lane[0];
         }
-        float row[ST_COUNT], cmrow[MAX_C];
-        stats_finalize(totals, 1, step, R, stats_dt, S, row, cmrow);
+        float row[ST_COUNT + MAX_C];
+        stats_finalize(totals, 1, step, 1.0f / (R * R), 1.0f / R, 1.0f / stats_dt, S, row);
         for (int k = 0; k < ST_COUNT; ++k) stats[k * n_steps + step] = row[k];
-        cm[step] = cmrow[0];
+        cm[step] = row[ST_COUNT];
     }
     *N_out = S.n_alive;
     for (int t = 0; t < NT; ++t)
