@@ -53,6 +53,9 @@ typedef enum {
     LNX_ST_POTENTIAL_VOLUME
 } lnx_stat_key;
 
+/* plan flags (lnx_desc.flags) */
+#define LNX_PLAN_FORCE_TILED 1u /* run 128x128 worlds through the tiled multi-pass engine too (cross-checks, tests) */
+
 /* run flags */
 #define LNX_RUN_EARLY_STOP 1u /* stop a world once its stop criteria fired and >= 128 stat rows exist (rows after
                                  the stop are left untouched); default off = bit-for-bit [max_run_iter] rows like
@@ -65,8 +68,9 @@ typedef enum {
  * helpers.build_update_fn (leniax/helpers.py:401-427: slugs + tc_indices + mean/sum) and
  * statistics.build_compute_stats_fn (leniax/statistics.py:11-33: R, dt = 1/T of the build-time config). */
 typedef struct {
-    int32_t nb_dims;                     /* world dimensions (2) */
-    int32_t dims[3];                     /* world size per dimension (128, 128) */
+    int32_t nb_dims;                     /* world dimensions: 2 or 3 */
+    int32_t dims[3];                     /* world size per dimension, powers of two in [8, 4096]; 128x128 worlds run in the
+                                            shared-memory resident kernels, everything else in the tiled multi-pass engine */
     int32_t nb_channels;                 /* C */
     int32_t nb_kernels;                  /* K = number of true kernels (after tc_indices) */
     int32_t nb_slots;                    /* C * max_k_per_channel = leading size of the reference's K tensor */
@@ -77,7 +81,7 @@ typedef struct {
     int32_t weighted_average;            /* 1: core.weighted_mean, 0: core.weighted_sum (core.py:202-242) */
     float R;                             /* world_params.R used by the statistics (statistics.py:23) */
     float stats_dt;                      /* 1 / world_params.T of the build-time config (statistics.py:24) */
-    uint32_t flags;                      /* reserved, 0 */
+    uint32_t flags;                      /* LNX_PLAN_* */
 } lnx_desc;
 
 typedef struct lnx_plan lnx_plan;
@@ -103,6 +107,9 @@ int lnx_kernels_prepare(const lnx_plan* plan, int32_t n_sols, const void* K_fft,
  * convention as jnp.fft.fftn.  Used by the Python layer to build K = fftn(fftshift(kernels)) (leniax/kernels.py:145-149)
  * with the engine's own butterflies (no cuFFT). */
 int lnx_rfft2(const lnx_plan* plan, int32_t n_images, const float* images, void* spectra, void* stream);
+
+/* Same for any supported world shape (2-D / 3-D, power-of-two dims): images float32 [n][dims...] -> complex64 [n][dims...]. */
+int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const float* images, void* spectra, void* stream);
 
 /* Measure the FP32 FMA throughput of the current device with a register-resident FMA loop (iters x 128 FMA per thread,
  * 4 CTAs of 512 threads per SM).  Synchronous.  This is the denominator of the FP32 roofline bench.py reports. */
@@ -131,6 +138,9 @@ size_t lnx_workspace_bytes(const lnx_plan* plan);
  *                                                                run_scan_mem_optimized does not)
  *   workspace     lnx_workspace_bytes() bytes of device scratch (contents undefined afterwards)
  */
+/* Scratch needed by lnx_run_scan for n_sols x n_init worlds (the tiled engine keeps per-world spectra in the workspace). */
+size_t lnx_workspace_bytes_for(const lnx_plan* plan, int32_t n_sols, int32_t n_init);
+
 int lnx_run_scan(const lnx_plan* plan, int32_t n_sols, int32_t n_init, int32_t max_run_iter, uint32_t run_flags,
                  const float* cells0, const void* table, const float* gf_params, const float* weights, const float* dt,
                  float* stats, float* channel_mass, float* n_alive, float* final_cells, float* cells_out, float* field_out,

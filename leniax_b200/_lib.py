@@ -13,6 +13,7 @@ LNX_NB_STATS = 11
 
 LNX_RUN_EARLY_STOP = 1
 LNX_RUN_ASSUME_FINITE = 0x100
+LNX_PLAN_FORCE_TILED = 1
 
 LNX_OK, LNX_ERR_INVALID, LNX_ERR_UNSUPPORTED, LNX_ERR_CUDA, LNX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
@@ -54,6 +55,8 @@ EXPORTS = {
     'lnx_rfft2': (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     'lnx_measure_fp32_peak': (ctypes.c_int, [c_int32, POINTER(ctypes.c_double), POINTER(ctypes.c_double), c_void_p]),
     'lnx_workspace_bytes': (c_size_t, [c_void_p]),
+    'lnx_workspace_bytes_for': (c_size_t, [c_void_p, c_int32, c_int32]),
+    'lnx_rfftn': (ctypes.c_int, [c_int32, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_void_p]),
     'lnx_run_scan': (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_uint32] + [c_void_p] * 12 + [c_void_p, c_size_t, c_void_p]),
     'lnx_run_scan_variant': (c_char_p, [c_void_p, c_int32]),
 }

@@ -15,6 +15,7 @@
 
 #include "../../include/leniax_b200.h"
 #include "lnx_step.cuh"
+#include "lnx_tiled.cuh"
 
 namespace lnx {
 
@@ -612,7 +613,113 @@ struct lnx_plan {
     lnx_desc d;
     int device;
     int sm_count;
+    bool tiled;            // false: resident 128x128 kernels, true: multi-pass tiled engine
+    lnx::tiled::Geom g;    // tiled engine geometry
 };
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tiled engine: host side
+// ---------------------------------------------------------------------------------------------------------------------
+namespace th {
+using namespace lnx::tiled;
+
+static int ilog2i(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return l;
+}
+static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
+    memset(g, 0, sizeof(*g));
+    if (nd != 2 && nd != 3) {
+        *why = "only 2-D and 3-D worlds are supported";
+        return false;
+    }
+    for (int d = 0; d < nd; ++d) {
+        const int n = dims[d];
+        if (n < 8 || n > NMAX || (n & (n - 1))) {
+            *why = "every world dimension must be a power of two in [8, 4096]";
+            return false;
+        }
+        g->dims[d] = n;
+    }
+    g->nd = nd;
+    g->L = dims[0];
+    g->A1 = nd == 3 ? dims[1] : 1;
+    g->A2 = dims[nd - 1];
+    g->logL = ilog2i(g->L);
+    g->logA1 = ilog2i(g->A1);
+    g->logA2 = ilog2i(g->A2);
+    g->half = g->A2 / 2 + 1;
+    g->rows = g->L * g->A1;
+    g->cells = (long long)g->rows * g->A2;
+    g->spec = (long long)g->rows * g->half;
+    if (nd == 3) {
+        g->slab_rows = g->A1;
+    } else {
+        int r = 4096 / g->A2;
+        if (r < 2) r = 2;
+        if (r > g->rows) r = g->rows;
+        g->slab_rows = r;
+    }
+    g->n_slabs = g->rows / g->slab_rows;
+    int tc = 8192 / g->L;
+    if (tc < 4) tc = 4;
+    if (tc > 64) tc = 64;
+    g->tc = tc;
+    return true;
+}
+static size_t smem_a(const Geom& g) { return ((size_t)(g.slab_rows / 2) * g.A2 + (g.nd == 3 ? (size_t)g.A1 * g.half : 0)) * sizeof(float2); }
+static size_t smem_b(const Geom& g) { return 2 * (size_t)g.L * g.tc * sizeof(float2); }
+static size_t smem_c(const Geom& g, int C) {
+    return ((size_t)g.slab_rows * g.half + (size_t)(g.slab_rows / 2) * g.A2) * sizeof(float2) + (size_t)C * g.slab_rows * g.A2 * sizeof(float);
+}
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+static float2* g_tw[64] = {nullptr};  // library-owned twiddle master table per device: (cos, sin)(2 pi k / NMAX)
+static int ensure_tiled_init(int dev) {
+    if (g_tw[dev]) return LNX_OK;
+    static float2 host[NMAX / 2];
+    for (int k = 0; k < NMAX / 2; ++k) {
+        const double a = 2.0 * 3.14159265358979323846 * k / NMAX;
+        host[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(host));
+    if (e == cudaSuccess) e = cudaMemcpy(d, host, sizeof(host), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    if (e != cudaSuccess) return -1;
+    g_tw[dev] = d;
+    return LNX_OK;
+}
+struct Workspace {   // carve-up of the caller's scratch for one lnx_run_scan call
+    float* state;
+    float2* spec;
+    float2* pot;
+    float* partials;
+    WorldCarry* carry;
+    size_t bytes;
+};
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static Workspace carve(const Geom& g, int C, int K, long long worlds, unsigned char* base) {
+    Workspace w;
+    size_t off = 256;
+    w.state = reinterpret_cast<float*>(base + off);
+    off += align256((size_t)worlds * C * g.cells * sizeof(float));
+    w.spec = reinterpret_cast<float2*>(base + off);
+    off += align256((size_t)worlds * C * g.spec * sizeof(float2));
+    w.pot = reinterpret_cast<float2*>(base + off);
+    off += align256((size_t)worlds * K * g.spec * sizeof(float2));
+    w.partials = reinterpret_cast<float*>(base + off);
+    off += align256((size_t)worlds * g.n_slabs * NP_T * sizeof(float));
+    w.carry = reinterpret_cast<WorldCarry*>(base + off);
+    off += align256((size_t)worlds * sizeof(WorldCarry));
+    w.bytes = off;
+    return w;
+}
+}  // namespace th
 
 // one-time per-device setup: architecture check (no fallback), twiddle constants, dynamic shared memory opt-in
 static int ensure_device_init(int* dev_out, int* sms_out) {
@@ -668,9 +775,18 @@ int lnx_device_count(void) {
 int lnx_plan_create(const lnx_desc* d, lnx_plan** out) {
     if (!d || !out) return fail(LNX_ERR_INVALID, "lnx_plan_create: null argument");
     *out = nullptr;
-    if (d->nb_dims != 2 || d->dims[0] != WS || d->dims[1] != WS)
-        return fail(LNX_ERR_UNSUPPORTED, "only 2-D %dx%d worlds are built in this version (got nb_dims=%d, dims=%d x %d)", WS, WS,
-                    d->nb_dims, d->dims[0], d->dims[1]);
+    const bool resident = d->nb_dims == 2 && d->dims[0] == WS && d->dims[1] == WS && !(d->flags & LNX_PLAN_FORCE_TILED);
+    lnx::tiled::Geom geom;
+    memset(&geom, 0, sizeof(geom));
+    if (!resident) {
+        const char* why = "";
+        if (!th::make_geom(d->nb_dims, d->dims, &geom, &why))
+            return fail(LNX_ERR_UNSUPPORTED, "unsupported world shape (nb_dims=%d, dims=%d x %d x %d): %s", d->nb_dims, d->dims[0], d->dims[1],
+                        d->nb_dims > 2 ? d->dims[2] : 1, why);
+        if (th::smem_a(geom) > th::SMEM_LIMIT || th::smem_b(geom) > th::SMEM_LIMIT || th::smem_c(geom, d->nb_channels) > th::SMEM_LIMIT)
+            return fail(LNX_ERR_UNSUPPORTED, "world too large for the tiled engine's shared-memory slabs (A %zu, B %zu, C %zu bytes)",
+                        th::smem_a(geom), th::smem_b(geom), th::smem_c(geom, d->nb_channels));
+    }
     if (d->nb_channels < 1 || d->nb_channels > MAX_C) return fail(LNX_ERR_INVALID, "nb_channels must be in [1, %d]", MAX_C);
     if (d->nb_kernels < 1 || d->nb_kernels > MAX_K) return fail(LNX_ERR_INVALID, "nb_kernels must be in [1, %d]", MAX_K);
     if (d->nb_slots < d->nb_kernels) return fail(LNX_ERR_INVALID, "nb_slots < nb_kernels");
@@ -690,6 +806,12 @@ int lnx_plan_create(const lnx_desc* d, lnx_plan** out) {
     p->d = *d;
     p->device = dev;
     p->sm_count = sms;
+    p->tiled = !resident;
+    p->g = geom;
+    if (p->tiled && th::ensure_tiled_init(dev) != LNX_OK) {
+        delete p;
+        return fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = p;
     return LNX_OK;
 }
@@ -700,16 +822,41 @@ int lnx_plan_destroy(lnx_plan* p) {
     return LNX_OK;
 }
 
-size_t lnx_kernel_table_bytes(const lnx_plan* p) { return p ? (size_t)p->d.nb_kernels * KTAB_F4 * sizeof(float4) : 0; }
+size_t lnx_workspace_bytes(const lnx_plan* p);
+
+size_t lnx_kernel_table_bytes(const lnx_plan* p) {
+    if (!p) return 0;
+    if (p->tiled) return (size_t)p->d.nb_kernels * p->g.spec * sizeof(float2);
+    return (size_t)p->d.nb_kernels * KTAB_F4 * sizeof(float4);
+}
+
+size_t lnx_workspace_bytes_for(const lnx_plan* p, int32_t n_sols, int32_t n_init) {
+    if (!p) return 0;
+    if (!p->tiled) return lnx_workspace_bytes(p);
+    return th::carve(p->g, p->d.nb_channels, p->d.nb_kernels, (long long)n_sols * n_init, nullptr).bytes;
+}
 
 size_t lnx_workspace_bytes(const lnx_plan* p) {
     if (!p) return 0;
+    if (p->tiled) return th::carve(p->g, p->d.nb_channels, p->d.nb_kernels, 1, nullptr).bytes;
     // 256 B header (world queue counter) + per-CTA scratch of the generic kernel: [3][C] thread-private images
     return 256 + (size_t)p->sm_count * 3 * p->d.nb_channels * PLANE_F4 * sizeof(float4);
 }
 
 int lnx_kernels_prepare(const lnx_plan* p, int32_t n_sols, const void* K_fft, void* table, void* stream) {
     if (!p || !K_fft || !table || n_sols < 1) return fail(LNX_ERR_INVALID, "lnx_kernels_prepare: bad argument");
+    if (p->tiled) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        int* slots_dev = nullptr;
+        LNX_CUDA(cudaMallocAsync(&slots_dev, sizeof(int) * MAX_K, st));
+        LNX_CUDA(cudaMemcpyAsync(slots_dev, p->d.slot, sizeof(int) * p->d.nb_kernels, cudaMemcpyHostToDevice, st));
+        const dim3 grid((unsigned)((p->g.spec + 255) / 256 > 1024 ? 1024 : (p->g.spec + 255) / 256), p->d.nb_kernels, n_sols);
+        lnx::tiled::gather_ktab_kernel<<<grid, 256, 0, st>>>(static_cast<const float2*>(K_fft), static_cast<float2*>(table), p->g,
+                                                            p->d.nb_kernels, p->d.nb_slots, slots_dev, 1.0f / (float)p->g.cells);
+        LNX_CUDA(cudaGetLastError());
+        LNX_CUDA(cudaFreeAsync(slots_dev, st));
+        return LNX_OK;
+    }
     PrepArgs a;
     a.K_fft = static_cast<const float2*>(K_fft);
     a.table = static_cast<float4*>(table);
@@ -728,6 +875,47 @@ int lnx_rfft2(const lnx_plan* p, int32_t n_images, const float* images, void* sp
     if (rc != LNX_OK) return rc;
     lnx_rfft2_kernel<<<n_images, NT, 65536 + TW_BYTES, static_cast<cudaStream_t>(stream)>>>(images, static_cast<float2*>(spectra));
     LNX_CUDA(cudaGetLastError());
+    return LNX_OK;
+}
+
+int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const float* images, void* spectra, void* stream) {
+    if (!dims || !images || !spectra || n_images < 1) return fail(LNX_ERR_INVALID, "lnx_rfftn: bad argument");
+    if (nb_dims == 2 && dims[0] == WS && dims[1] == WS) return lnx_rfft2(nullptr, n_images, images, spectra, stream);
+    int dev = 0;
+    int rc = ensure_device_init(&dev, nullptr);
+    if (rc != LNX_OK) return rc;
+    lnx::tiled::Geom g;
+    const char* why = "";
+    if (!th::make_geom(nb_dims, dims, &g, &why)) return fail(LNX_ERR_UNSUPPORTED, "lnx_rfftn: %s", why);
+    if (th::smem_a(g) > th::SMEM_LIMIT || th::smem_b(g) > th::SMEM_LIMIT) return fail(LNX_ERR_UNSUPPORTED, "lnx_rfftn: world too large");
+    if (th::ensure_tiled_init(dev) != LNX_OK) return fail(LNX_ERR_CUDA, "tiled engine setup failed");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float2 *sa = nullptr, *sb = nullptr;
+    const size_t bytes = (size_t)n_images * g.spec * sizeof(float2);
+    LNX_CUDA(cudaMallocAsync(&sa, bytes, st));
+    LNX_CUDA(cudaMallocAsync(&sb, bytes, st));
+    lnx::tiled::PassAArgs a;
+    a.state = images;
+    a.spec = sa;
+    a.tw = th::g_tw[dev];
+    a.g = g;
+    a.C = 1;
+    lnx::tiled::pass_a_kernel<<<dim3(g.n_slabs, 1, n_images), lnx::tiled::TPB, th::smem_a(g), st>>>(a);
+    lnx::tiled::PassBArgs b;
+    memset(&b, 0, sizeof(b));
+    b.spec = sa;
+    b.fwd_out = sb;
+    b.tw = th::g_tw[dev];
+    b.g = g;
+    b.C = 1;
+    b.K = 0;
+    b.n_init = 1;
+    const long long M = g.spec / g.L;
+    lnx::tiled::pass_b_kernel<<<dim3((unsigned)((M + g.tc - 1) / g.tc), 1, n_images), lnx::tiled::TPB, th::smem_b(g), st>>>(b);
+    lnx::tiled::expand_hermitian_kernel<<<dim3(1024, 1, n_images), 256, 0, st>>>(sb, static_cast<float2*>(spectra), g);
+    LNX_CUDA(cudaGetLastError());
+    LNX_CUDA(cudaFreeAsync(sa, st));
+    LNX_CUDA(cudaFreeAsync(sb, st));
     return LNX_OK;
 }
 
@@ -759,6 +947,92 @@ int lnx_measure_fp32_peak(int32_t iters, double* tflops, double* ms, void* strea
     return LNX_OK;
 }
 
+static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_run_iter, const float* cells0, const void* table,
+                          const float* gf_params, const float* weights, const float* dt, float* stats, float* channel_mass, float* n_alive,
+                          float* final_cells, float* cells_out, float* field_out, float* potential_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    using namespace lnx::tiled;
+    const Geom& g = p->g;
+    const int C = p->d.nb_channels, K = p->d.nb_kernels;
+    const long long worlds = (long long)n_sols * n_init;
+    if (worlds > 65535) return fail(LNX_ERR_INVALID, "tiled engine: at most 65535 worlds per call (got %lld)", worlds);
+    const th::Workspace ws = th::carve(g, C, K, worlds, static_cast<unsigned char*>(workspace));
+    if (!workspace || workspace_bytes < ws.bytes)
+        return fail(LNX_ERR_INVALID, "lnx_run_scan: workspace too small (%zu < %zu); use lnx_workspace_bytes_for()", workspace_bytes, ws.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float2* tw = th::g_tw[p->device];
+    float* state = final_cells ? final_cells : ws.state;  // working state (updated in place every step)
+    LNX_CUDA(cudaMemcpyAsync(state, cells0, (size_t)worlds * C * g.cells * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    LNX_CUDA(cudaMemsetAsync(ws.carry, 0, (size_t)worlds * sizeof(WorldCarry), st));
+    PassAArgs a;
+    a.state = state;
+    a.spec = ws.spec;
+    a.tw = tw;
+    a.g = g;
+    a.C = C;
+    PassBArgs b;
+    memset(&b, 0, sizeof(b));
+    b.spec = ws.spec;
+    b.pot_spec = ws.pot;
+    b.ktab = static_cast<const float2*>(table);
+    b.fwd_out = nullptr;
+    b.tw = tw;
+    b.g = g;
+    b.C = C;
+    b.K = K;
+    b.n_init = n_init;
+    PassCArgs c;
+    memset(&c, 0, sizeof(c));
+    c.state = state;
+    c.pot_spec = ws.pot;
+    c.gf_params = gf_params;
+    c.weights = weights;
+    c.dt = dt;
+    c.carry = ws.carry;
+    c.partials = ws.partials;
+    c.cells_out = cells_out;
+    c.field_out = field_out;
+    c.potential_out = potential_out;
+    c.tw = tw;
+    c.g = g;
+    c.C = C;
+    c.K = K;
+    c.n_init = n_init;
+    c.max_iter = max_run_iter;
+    c.state_fn = p->d.state_fn;
+    c.mean = p->d.weighted_average;
+    PassDArgs d;
+    d.partials = ws.partials;
+    d.carry = ws.carry;
+    d.stats = stats;
+    d.channel_mass = channel_mass;
+    d.n_alive = n_alive;
+    d.g = g;
+    d.C = C;
+    d.n_sols = n_sols;
+    d.n_init = n_init;
+    d.max_iter = max_run_iter;
+    d.R = p->d.R;
+    d.stats_dt = p->d.stats_dt;
+    for (int k = 0; k < K; ++k) {
+        b.c_in[k] = p->d.c_in[k];
+        c.gf_id[k] = p->d.gf_id[k];
+    }
+    const long long M = g.spec / g.L;
+    const dim3 grid_a(g.n_slabs, C, (unsigned)worlds), grid_b((unsigned)((M + g.tc - 1) / g.tc), C, (unsigned)worlds),
+        grid_c(g.n_slabs, 1, (unsigned)worlds);
+    for (int t = 0; t < max_run_iter; ++t) {
+        c.t = t;
+        d.t = t;
+        pass_a_kernel<<<grid_a, TPB, th::smem_a(g), st>>>(a);
+        pass_b_kernel<<<grid_b, TPB, th::smem_b(g), st>>>(b);
+        pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), st>>>(c);
+        pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
+    }
+    LNX_CUDA(cudaGetLastError());
+    return LNX_OK;
+}
+
 static bool use_fused(const lnx_plan* p, bool trajectory) {
     const lnx_desc& d = p->d;
     return d.nb_channels == 1 && d.nb_kernels == 1 && !trajectory && d.gf_id[0] == GF_POLY_QUAD4 && d.state_fn == SF_V1;
@@ -766,6 +1040,7 @@ static bool use_fused(const lnx_plan* p, bool trajectory) {
 
 const char* lnx_run_scan_variant(const lnx_plan* p, int32_t with_trajectory) {
     if (!p) return "";
+    if (p->tiled) return "tiled";
     return use_fused(p, with_trajectory != 0) ? "fused" : "generic";
 }
 
@@ -778,6 +1053,9 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
     if (max_run_iter < 1) return fail(LNX_ERR_INVALID, "max_run_iter must be positive, value given: %d", max_run_iter);  // runner.py:51
     if (!cells0 || !table || !gf_params || !weights || !dt || !stats || !channel_mass || !n_alive)
         return fail(LNX_ERR_INVALID, "lnx_run_scan: null required pointer");
+    if (p->tiled)
+        return run_scan_tiled(p, n_sols, n_init, max_run_iter, cells0, table, gf_params, weights, dt, stats, channel_mass, n_alive, final_cells,
+                              cells_out, field_out, potential_out, workspace, workspace_bytes, stream);
     const bool trajectory = cells_out || field_out || potential_out;
     const bool fused = use_fused(p, trajectory);
     if (!workspace || workspace_bytes < (fused ? (size_t)256 : lnx_workspace_bytes(p)))

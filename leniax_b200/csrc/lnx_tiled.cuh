@@ -1,0 +1,488 @@
+// Tiled multi-pass engine: worlds that do not fit the resident 128x128 kernel (any power-of-two 2-D / 3-D size,
+// e.g. BASELINE config D 2048x2048 and config E 64^3).  State and spectra live in HBM/L2; one Lenia step is
+//
+//   pass A  inner transforms   rows (two real rows per complex FFT) [+ axis-1 for 3-D planes]  -> half spectrum S_c
+//   pass B  leading axis       FFT along axis 0, multiply by K_k, inverse FFT along axis 0     -> P_k
+//   pass C  inner inverse      [axis-1 inverse,] rows inverse, growth, weighted mix, state update, statistics partials
+//   pass D  statistics         reduce partials per world, finalise the 12 statistics, carry + stop criteria
+//
+// Algorithmic HBM traffic for 1 channel / 1 kernel: A 4+4, B 4+4+4, C 4+4+4 = 32 B per cell-update.
+// Same reference functions as the resident kernels: leniax/core.py:52-102, :163-319, leniax/statistics.py:36-205.
+#pragma once
+#include "lnx_step.cuh"
+
+namespace lnx {
+namespace tiled {
+
+constexpr int NMAX = 4096;     // longest supported axis
+constexpr int TPB = 256;       // threads per block of every pass
+constexpr int MAXD = 3;
+constexpr int NP_T = 4 + 3 * MAXD + MAX_C;  // partials: cnt_a, g00, cnt_g, cnt_p, MX[3], MX2[3], GX[3], m00[C]
+
+struct Geom {
+    int nd;          // 2 or 3
+    int dims[3];     // world dims, leading first (2-D: dims[0]=H, dims[1]=W)
+    int L;           // leading axis length (pass B)
+    int A1, A2;      // inner slab: A1 rows of A2 reals (2-D: A1 = 1)
+    int logL, logA1, logA2;
+    int half;        // A2/2 + 1 spectral columns
+    int rows;        // L * A1 rows of length A2 in a world
+    int slab_rows;   // rows handled by one CTA of pass A / C (3-D: A1; 2-D: 2..16)
+    int n_slabs;     // rows / slab_rows
+    long long cells;      // L * A1 * A2
+    long long spec;       // rows * half complex values per (world, channel)
+    int tc;          // pass B tile width (inner spectral columns per CTA)
+};
+
+__device__ __forceinline__ int brev_n(int x, int logn) { return (int)(__brev((unsigned)x) >> (32 - logn)); }
+
+// In-place radix-2 FFT of `nl` lines of length n held in shared memory; element i of line j at s[i * is + j * js].
+// Forward: DIF, natural order in -> bit-reversed order out.  Inverse: DIT, bit-reversed in -> natural out (unnormalised).
+// LF = lines are the fast thread axis (js == 1).  tw[k] = (cos, sin)(2 pi k / NMAX).
+template <bool INV, bool LF>
+__device__ void block_fft(float2* s, int n, int logn, int is, int nl, int js, const float2* __restrict__ tw) {
+    const int half = n >> 1, total = half * nl, tws = NMAX >> logn;
+    for (int st = 0; st < logn; ++st) {
+        const int lsp = INV ? st : logn - 1 - st;  // log2(span)
+        const int span = 1 << lsp;
+        for (int b = threadIdx.x; b < total; b += blockDim.x) {
+            int line, q;
+            if (LF) {
+                line = b % nl;
+                q = b / nl;
+            } else {
+                q = b & (half - 1);
+                line = b >> (logn - 1);
+            }
+            const int p = q & (span - 1), g = q >> lsp;
+            const int i0 = (g << (lsp + 1)) + p;
+            float2* a = s + (size_t)i0 * is + (size_t)line * js;
+            float2* c = a + (size_t)span * is;
+            const float2 w = __ldg(tw + (p << (logn - 1 - lsp)) * tws);  // angle 2 pi p / (2 span)
+            const float2 x = *a, y = *c;
+            if (!INV) {
+                const float2 d = make_float2(x.x - y.x, x.y - y.y);
+                *a = make_float2(x.x + y.x, x.y + y.y);
+                *c = make_float2(d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y);  // d * (cos - i sin)
+            } else {
+                const float2 t = make_float2(y.x * w.x - y.y * w.y, y.y * w.x + y.x * w.y);  // y * (cos + i sin)
+                *a = make_float2(x.x + t.x, x.y + t.y);
+                *c = make_float2(x.x - t.x, x.y - t.y);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass A: real rows -> half spectrum (natural order), optional axis-1 transform for 3-D planes
+//   grid (n_slabs, C, worlds).  smem: zbuf [slab_rows/2][A2] complex, then (3-D) plane [A1][half] complex
+// ---------------------------------------------------------------------------------------------------------------------
+struct PassAArgs {
+    const float* state;   // [worlds][C][rows][A2]
+    float2* spec;         // [worlds][C][rows][half]
+    const float2* tw;
+    Geom g;
+    int C;
+};
+__global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Geom& g = P.g;
+    float2* z = reinterpret_cast<float2*>(smem_raw);                      // [pairs][A2]
+    float2* pl = z + (size_t)(g.slab_rows / 2) * g.A2;                    // [slab_rows][half] (3-D only)
+    const int slab = blockIdx.x, c = blockIdx.y, w = blockIdx.z;
+    const int pairs = g.slab_rows / 2, A2 = g.A2, half = g.half;
+    const size_t row0 = (size_t)slab * g.slab_rows;
+    const float* src = P.state + (((size_t)w * P.C + c) * g.rows + row0) * A2;
+    for (int i = threadIdx.x; i < pairs * A2; i += blockDim.x) {
+        const int pr = i >> g.logA2, n = i & (A2 - 1);
+        z[i] = make_float2(src[(size_t)(2 * pr) * A2 + n], src[(size_t)(2 * pr + 1) * A2 + n]);
+    }
+    __syncthreads();
+    block_fft<false, false>(z, A2, g.logA2, 1, pairs, A2, P.tw);
+    float2* dst = P.spec + (((size_t)w * P.C + c) * g.rows + row0) * half;
+    const bool plane = g.nd == 3;
+    for (int i = threadIdx.x; i < pairs * half; i += blockDim.x) {
+        const int pr = i / half, k = i - pr * half;
+        const float2 zk = z[(size_t)pr * A2 + brev_n(k, g.logA2)];
+        const float2 zc = z[(size_t)pr * A2 + brev_n((A2 - k) & (A2 - 1), g.logA2)];
+        const float2 a = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+        const float2 b = make_float2(0.5f * (zk.y + zc.y), 0.5f * (zc.x - zk.x));
+        if (plane) {
+            pl[(size_t)(2 * pr) * half + k] = a;
+            pl[(size_t)(2 * pr + 1) * half + k] = b;
+        } else {
+            dst[(size_t)(2 * pr) * half + k] = a;
+            dst[(size_t)(2 * pr + 1) * half + k] = b;
+        }
+    }
+    if (plane) {
+        __syncthreads();
+        block_fft<false, true>(pl, g.A1, g.logA1, half, half, 1, P.tw);  // along axis 1, `half` interleaved lines
+        for (int i = threadIdx.x; i < g.A1 * half; i += blockDim.x) {
+            const int m1 = i / half, k = i - m1 * half;
+            dst[i] = pl[(size_t)brev_n(m1, g.logA1) * half + k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass B: FFT along the leading axis, multiply by every kernel fed by this channel, inverse FFT
+//   grid (ceil(M / tc), C, worlds).  smem: F [L][tc] + T [L][tc]
+// ---------------------------------------------------------------------------------------------------------------------
+struct PassBArgs {
+    const float2* spec;    // [worlds][C][L][M]
+    float2* pot_spec;      // [worlds][K][L][M]     (null in forward-only mode)
+    const float2* ktab;    // [n_sols][K][L][M], pre-scaled by 1 / cells
+    float2* fwd_out;       // forward-only mode (kernel-spectrum builder): [images][L][M]
+    const float2* tw;
+    Geom g;
+    int C, K, n_init;
+    int c_in[MAX_K];
+};
+__global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Geom& g = P.g;
+    const int L = g.L, tc = g.tc;
+    const long long M = g.spec / L;
+    float2* F = reinterpret_cast<float2*>(smem_raw);
+    float2* T = F + (size_t)L * tc;
+    const int c = blockIdx.y, w = blockIdx.z;
+    const long long m0 = (long long)blockIdx.x * tc;
+    const int wdt = (int)((M - m0) < tc ? (M - m0) : tc);
+    const float2* src = P.spec + ((size_t)w * P.C + c) * g.spec + m0;
+    for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
+        const int l = i / tc, j = i - l * tc;
+        F[i] = j < wdt ? src[(size_t)l * M + j] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    block_fft<false, true>(F, L, g.logL, tc, tc, 1, P.tw);
+    if (P.fwd_out) {
+        float2* dst = P.fwd_out + ((size_t)w * P.C + c) * g.spec + m0;
+        for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
+            const int m = i / tc, j = i - m * tc;
+            if (j < wdt) dst[(size_t)m * M + j] = F[(size_t)brev_n(m, g.logL) * tc + j];
+        }
+        return;
+    }
+    const int sol = w / P.n_init;
+    for (int k = 0; k < P.K; ++k) {
+        if (P.c_in[k] != c) continue;
+        const float2* kt = P.ktab + ((size_t)sol * P.K + k) * g.spec + m0;
+        for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
+            const int pos = i / tc, j = i - pos * tc;
+            float2 v = make_float2(0.f, 0.f);
+            if (j < wdt) {
+                const float2 f = F[i], q = __ldg(kt + (size_t)brev_n(pos, g.logL) * M + j);
+                v = make_float2(f.x * q.x - f.y * q.y, f.x * q.y + f.y * q.x);
+            }
+            T[i] = v;
+        }
+        __syncthreads();
+        block_fft<true, true>(T, L, g.logL, tc, tc, 1, P.tw);
+        float2* dst = P.pot_spec + ((size_t)w * P.K + k) * g.spec + m0;
+        for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
+            const int l = i / tc, j = i - l * tc;
+            if (j < wdt) dst[(size_t)l * M + j] = T[i];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass C: inverse inner transforms of every kernel's potential spectrum, growth, mix, state update, statistics partials
+//   grid (n_slabs, 1, worlds).  smem: pl [slab_rows][half] complex, z [pairs][A2] complex, field [C][slab_rows][A2]
+// ---------------------------------------------------------------------------------------------------------------------
+struct WorldCarry {   // per world, device memory
+    int shift[3];
+    float centroid[3];
+    float angle;
+    float should_continue, prev_mass, prev_sign, n_alive;
+    int mono, vol;
+    float init_cm[MAX_C];
+};
+struct PassCArgs {
+    float* state;             // [worlds][C][rows][A2]  updated in place
+    const float2* pot_spec;   // [worlds][K][rows][half]
+    const float* gf_params;   // [n_sols][K][2]
+    const float* weights;     // [n_sols][C][K]
+    const float* dt;          // [n_sols]
+    const WorldCarry* carry;  // [worlds]
+    float* partials;          // [worlds][n_slabs][NP_T]
+    float* cells_out;         // [worlds' trajectory slot] may be null: [C][cells]
+    float* field_out;
+    float* potential_out;     // [K][cells]
+    const float2* tw;
+    Geom g;
+    int C, K, n_init, max_iter, t;
+    int state_fn, mean;
+    int gf_id[MAX_K];
+};
+__global__ void __launch_bounds__(TPB) pass_c_kernel(PassCArgs P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[NP_T][TPB / 32];
+    const Geom& g = P.g;
+    const int A2 = g.A2, half = g.half, R = g.slab_rows, pairs = R / 2;
+    float2* pl = reinterpret_cast<float2*>(smem_raw);       // [R][half]
+    float2* z = pl + (size_t)R * half;                       // [pairs][A2]
+    float* field = reinterpret_cast<float*>(z + (size_t)pairs * A2);  // [C][R][A2]
+    const int slab = blockIdx.x, w = blockIdx.z;
+    const int sol = w / P.n_init, init = w - sol * P.n_init;
+    const size_t row0 = (size_t)slab * R;
+    const bool plane = g.nd == 3;
+    const int slab_cells = R * A2;
+    const size_t traj = ((size_t)sol * P.max_iter + P.t) * P.n_init + init;  // world-step slot of the trajectory outputs
+    for (int i = threadIdx.x; i < P.C * slab_cells; i += blockDim.x) field[i] = 0.f;
+    float acc[NP_T];
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) acc[i] = 0.f;
+
+    for (int k = 0; k < P.K; ++k) {
+        const float2* src = P.pot_spec + (((size_t)w * P.K + k) * g.rows + row0) * half;
+        __syncthreads();
+        if (plane) {
+            for (int i = threadIdx.x; i < R * half; i += blockDim.x) {
+                const int m1 = i / half, kk = i - m1 * half;
+                pl[(size_t)brev_n(m1, g.logA1) * half + kk] = src[i];
+            }
+            __syncthreads();
+            block_fft<true, true>(pl, g.A1, g.logA1, half, half, 1, P.tw);
+        } else {
+            for (int i = threadIdx.x; i < R * half; i += blockDim.x) pl[i] = src[i];
+            __syncthreads();
+        }
+        // retangle: Z'[k] = A + iB, Z'[N-k] = conj(A) + i conj(B), stored at bit-reversed positions for the DIT
+        for (int i = threadIdx.x; i < pairs * half; i += blockDim.x) {
+            const int pr = i / half, kk = i - pr * half;
+            const float2 a = pl[(size_t)(2 * pr) * half + kk], b = pl[(size_t)(2 * pr + 1) * half + kk];
+            z[(size_t)pr * A2 + brev_n(kk, g.logA2)] = make_float2(a.x - b.y, a.y + b.x);
+            if (kk != 0 && kk != A2 / 2) z[(size_t)pr * A2 + brev_n(A2 - kk, g.logA2)] = make_float2(a.x + b.y, b.x - a.y);
+        }
+        __syncthreads();
+        block_fft<true, false>(z, A2, g.logA2, 1, pairs, A2, P.tw);
+        const GfConst gc = gf_prepare(P.gf_id[k], P.gf_params[((size_t)sol * P.K + k) * 2], P.gf_params[((size_t)sol * P.K + k) * 2 + 1]);
+        float* pout = P.potential_out ? P.potential_out + (traj * P.K + k) * g.cells + row0 * A2 : nullptr;
+        float wk[MAX_C];
+#pragma unroll
+        for (int c = 0; c < MAX_C; ++c) wk[c] = c < P.C ? P.weights[((size_t)sol * P.C + c) * P.K + k] : 0.f;
+        for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) {
+            const int r = i >> g.logA2, n = i & (A2 - 1);
+            const float2 zz = z[(size_t)(r >> 1) * A2 + n];
+            const float pot = (r & 1) ? zz.y : zz.x;
+            acc[3] += pot > EPS ? 1.f : 0.f;
+            if (pout) pout[i] = pot;
+            const float gv = growth_dyn<true>(P.gf_id[k], pot, gc);
+#pragma unroll
+            for (int c = 0; c < MAX_C; ++c)
+                if (c < P.C && wk[c] != 0.f) field[(size_t)c * slab_cells + i] += wk[c] * gv;
+        }
+    }
+    __syncthreads();
+    // ---- update + statistics ----
+    const WorldCarry cr = P.carry[w];
+    const float dt = P.dt[sol];
+    for (int c = 0; c < P.C; ++c) {
+        float wsum = 0.f;
+        for (int k = 0; k < P.K; ++k) wsum += P.weights[((size_t)sol * P.C + c) * P.K + k];
+        float* st = P.state + (((size_t)w * P.C + c) * g.rows + row0) * A2;
+        float* cout = P.cells_out ? P.cells_out + (traj * P.C + c) * g.cells + row0 * A2 : nullptr;
+        float* fout = P.field_out ? P.field_out + (traj * P.C + c) * g.cells + row0 * A2 : nullptr;
+        float m00 = 0.f;
+        for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) {
+            const int r = i >> g.logA2, n = i & (A2 - 1);
+            const size_t grow = row0 + r;            // global row index = l * A1 + a1
+            float f = field[(size_t)c * slab_cells + i];
+            if (P.mean) f = f / wsum;
+            const float a = st[i];
+            if (cout) cout[i] = a;
+            if (fout) fout[i] = f;
+            st[i] = state_update_dyn<true>(P.state_fn, a, f, dt);
+            // coordinates of this cell in the rolled (centred) world, statistics.py:28-33 + utils.py:269-293
+            int idx[3];
+            if (g.nd == 3) {
+                idx[0] = (int)(grow >> g.logA1);
+                idx[1] = (int)(grow & (g.A1 - 1));
+                idx[2] = n;
+            } else {
+                idx[0] = (int)grow;
+                idx[1] = n;
+                idx[2] = 0;
+            }
+            const float gp = fmaxf(f, 0.f);
+            m00 += a;
+            acc[0] += a > EPS ? 1.f : 0.f;
+            acc[1] += gp;
+            acc[2] += gp > EPS ? 1.f : 0.f;
+            for (int d = 0; d < g.nd; ++d) {
+                const float x = (float)(((idx[d] - cr.shift[d]) & (g.dims[d] - 1)) - g.dims[d] / 2);
+                acc[4 + d] += a * x;
+                acc[4 + MAXD + d] += a * x * x;
+                acc[4 + 2 * MAXD + d] += gp * x;
+            }
+        }
+        acc[4 + 3 * MAXD + c] = m00;
+    }
+    // block reduction of the partials
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NP_T) {
+        float v = 0.f;
+        for (int j = 0; j < TPB / 32; ++j) v += red[threadIdx.x][j];
+        P.partials[((size_t)w * g.n_slabs + slab) * NP_T + threadIdx.x] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass D: per-world statistics (leniax/statistics.py:36-126, 134-205 for nb_dims = 2 or 3)
+// ---------------------------------------------------------------------------------------------------------------------
+struct PassDArgs {
+    const float* partials;
+    WorldCarry* carry;
+    float* stats;          // [ST_COUNT][n_sols][T][n_init]
+    float* channel_mass;   // [n_sols][T][n_init][C]
+    float* n_alive;
+    Geom g;
+    int C, n_sols, n_init, max_iter, t;
+    float R, stats_dt;
+};
+__global__ void __launch_bounds__(128) pass_d_kernel(PassDArgs P) {
+    __shared__ float tot[NP_T];
+    __shared__ float red[NP_T][4];
+    const Geom& g = P.g;
+    const int w = blockIdx.x;
+    const int sol = w / P.n_init, init = w - sol * P.n_init;
+    float acc[NP_T];
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) acc[i] = 0.f;
+    for (int s = threadIdx.x; s < g.n_slabs; s += blockDim.x) {
+        const float* p = P.partials + ((size_t)w * g.n_slabs + s) * NP_T;
+#pragma unroll
+        for (int i = 0; i < NP_T; ++i) acc[i] += p[i];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NP_T) tot[threadIdx.x] = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    WorldCarry S = P.carry[w];
+    const int nd = g.nd, C = P.C, t = P.t;
+    // reference: R**2 is used for every "volume" normalisation whatever the dimension (statistics.py:70-78)
+    const float R2 = P.R * P.R, R = P.R, dt = P.stats_dt;
+    float m00 = 0.f, cm[MAX_C];
+    for (int c = 0; c < C; ++c) {
+        m00 += tot[4 + 3 * MAXD + c];
+        cm[c] = tot[4 + 3 * MAXD + c] / R2;
+    }
+    const float g00 = tot[1];
+    const float mass = m00 / R2, mass_volume = tot[0] / R2, growth = g00 / R2, growth_volume = tot[2] / R2;
+    float out[ST_COUNT];
+    out[ST_MASS] = mass;
+    out[ST_MASS_VOLUME] = mass_volume;
+    out[ST_MASS_DENSITY] = mass / (mass_volume + EPS);
+    out[ST_GROWTH] = growth;
+    out[ST_GROWTH_VOLUME] = growth_volume;
+    out[ST_GROWTH_DENSITY] = growth / (growth_volume + EPS);
+    out[ST_POTENTIAL_VOLUME] = tot[3] / R2;
+    float cen[3] = {0.f, 0.f, 0.f}, dl[3] = {0.f, 0.f, 0.f};
+    float dist2 = 0.f, gd2 = 0.f, inertia = 0.f;
+    const float den = m00 * m00 + EPS;
+    for (int d = 0; d < nd; ++d) {
+        cen[d] = tot[4 + d] / (m00 + EPS);
+        dl[d] = cen[d] - S.centroid[d];
+        dist2 += dl[d] * dl[d];
+        const float gcd = tot[4 + 2 * MAXD + d] / (g00 + EPS) - cen[d];
+        gd2 += gcd * gcd;
+        inertia += (tot[4 + MAXD + d] - cen[d] * tot[4 + d]) / den;
+    }
+    const float dist = sqrtf(dist2);
+    out[ST_MASS_SPEED] = dist / R / dt;
+    const float angle = (atan2f(dl[1], dl[0]) * 57.29577951308232f) * ((dist / R > 0.001f) ? 1.f : 0.f);  // dims 0 and 1 only
+    out[ST_MASS_ANGLE_SPEED] = (mod360(angle - S.angle + 540.f) - 180.f) / dt;
+    out[ST_MASS_GROWTH_DIST] = sqrtf(gd2) / R;
+    out[ST_INERTIA] = inertia;
+    for (int d = 0; d < nd; ++d) {
+        const int s = trunc_to_int(cen[d]);
+        S.shift[d] = (S.shift[d] + s) & (g.dims[d] - 1);
+        S.centroid[d] = cen[d] - (float)s;
+    }
+    S.angle = angle;
+    if (t == 0) {
+        for (int c = 0; c < C; ++c) S.init_cm[c] = cm[c];
+        S.prev_mass = mass;
+        S.prev_sign = 0.f;
+        S.should_continue = 1.f;
+        S.n_alive = 0.f;
+        S.mono = S.vol = 0;
+    }
+    bool cond = true;
+    for (int c = 0; c < C; ++c) cond = cond && (cm[c] >= EPS) && (cm[c] <= 3.f * S.init_cm[c]);
+    const float dm = mass - S.prev_mass;
+    const float sign = (dm > 0.f) ? 1.f : ((dm < 0.f) ? -1.f : dm);
+    S.mono = S.mono * (sign == S.prev_sign ? 1 : 0) + 1;
+    cond = cond && (S.mono <= 128);
+    S.vol = S.vol * (mass_volume > 10.f ? 1 : 0) + 1;
+    cond = cond && (S.vol <= 128);
+    S.should_continue *= cond ? 1.f : 0.f;
+    S.n_alive += S.should_continue;
+    S.prev_mass = mass;
+    S.prev_sign = sign;
+    P.carry[w] = S;
+    const size_t plane = (size_t)P.n_sols * P.max_iter * P.n_init;
+    const size_t idx = ((size_t)sol * P.max_iter + t) * P.n_init + init;
+    for (int k = 0; k < ST_COUNT; ++k) P.stats[k * plane + idx] = out[k];
+    for (int c = 0; c < C; ++c) P.channel_mass[idx * C + c] = cm[c];
+    P.n_alive[w] = S.n_alive;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// helpers: kernel table gather, Hermitian expansion (kernel-spectrum builder)
+// ---------------------------------------------------------------------------------------------------------------------
+// K_fft full complex [n_sols][nb_slots][cells] (reference layout) -> table [n_sols][K][rows][half] scaled by 1/cells
+__global__ void gather_ktab_kernel(const float2* __restrict__ K_fft, float2* __restrict__ tab, Geom g, int K, int nb_slots,
+                                   const int* __restrict__ slots_dev, float scale) {
+    const long long n = (long long)g.spec;
+    const int sol = blockIdx.z, k = blockIdx.y;
+    const float2* src = K_fft + ((size_t)sol * nb_slots + slots_dev[k]) * g.cells;
+    float2* dst = tab + ((size_t)sol * K + k) * g.spec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / g.half;
+        const int kk = (int)(i - row * g.half);
+        const float2 v = src[row * g.A2 + kk];
+        dst[i] = make_float2(v.x * scale, v.y * scale);
+    }
+}
+// half spectrum [images][rows][half] -> full spectrum [images][rows][A2] using X[-m] = conj(X[m]) over all axes
+__global__ void expand_hermitian_kernel(const float2* __restrict__ half_spec, float2* __restrict__ full, Geom g) {
+    const int img = blockIdx.z;
+    const float2* src = half_spec + (size_t)img * g.spec;
+    float2* dst = full + (size_t)img * g.cells;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < g.cells; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i >> g.logA2;
+        const int kk = (int)(i & (g.A2 - 1));
+        if (kk < g.half) {
+            dst[i] = src[row * g.half + kk];
+        } else {
+            const int l = (int)(row >> g.logA1), a1 = (int)(row & (g.A1 - 1));
+            const long long mrow = ((long long)((g.L - l) & (g.L - 1)) << g.logA1) + ((g.A1 - a1) & (g.A1 - 1));
+            const float2 v = src[mrow * g.half + (g.A2 - kk)];
+            dst[i] = make_float2(v.x, -v.y);
+        }
+    }
+}
+
+}  // namespace tiled
+}  // namespace lnx

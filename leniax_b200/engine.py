@@ -62,9 +62,9 @@ class Plan:
     @classmethod
     def get(cls, *, world_size: Sequence[int], nb_channels: int, slots: Sequence[int], c_in: Sequence[int],
             gf_ids: Sequence[int], nb_slots: int, state_fn: str, weighted_average: bool, R: float, stats_dt: float,
-            device: torch.device) -> 'Plan':
+            device: torch.device, force_tiled: bool = False) -> 'Plan':
         key = (tuple(world_size), nb_channels, tuple(slots), tuple(c_in), tuple(gf_ids), nb_slots, state_fn,
-               bool(weighted_average), float(R), float(stats_dt), str(device))
+               bool(weighted_average), float(R), float(stats_dt), str(device), bool(force_tiled))
         plan = cls._cache.get(key)
         if plan is None:
             if state_fn not in STATE_FN_IDS:
@@ -86,7 +86,7 @@ class Plan:
             d.weighted_average = 1 if weighted_average else 0
             d.R = float(R)
             d.stats_dt = float(stats_dt)
-            d.flags = 0
+            d.flags = _lib.LNX_PLAN_FORCE_TILED if force_tiled else 0
             plan = cls(key, d, device)
             cls._cache[key] = plan
         return plan
@@ -104,10 +104,11 @@ class Plan:
     def run_scan(self, cells0: torch.Tensor, K: torch.Tensor, gf_params: torch.Tensor, weights: torch.Tensor,
                  dt: torch.Tensor, max_run_iter: int, *, keep_trajectory: bool, flags: int = 0,
                  want_final_cells: bool = True) -> Dict[str, Optional[torch.Tensor]]:
-        """cells0 ``[n_sols, n_init, C, H, W]``; K ``[n_sols, nb_slots, H, W]``; gf_params ``[n_sols, K, 2]``;
+        """cells0 ``[n_sols, n_init, C, *dims]``; K ``[n_sols, nb_slots, *dims]``; gf_params ``[n_sols, K, 2]``;
         weights ``[n_sols, C, K]``; dt ``[n_sols]``."""
         dev = self.device
-        n_sols, n_init, C, H, W = cells0.shape
+        n_sols, n_init, C = cells0.shape[:3]
+        dims = tuple(cells0.shape[3:])
         nk = self.desc.nb_kernels
         f32 = torch.float32
         table = self.prepare_kernels(K, n_sols)
@@ -120,10 +121,10 @@ class Plan:
         final = torch.empty_like(cells0) if want_final_cells else None
         traj_c = traj_f = traj_p = None
         if keep_trajectory:
-            traj_c = torch.empty((n_sols, max_run_iter, n_init, C, H, W), dtype=f32, device=dev)
+            traj_c = torch.empty((n_sols, max_run_iter, n_init, C) + dims, dtype=f32, device=dev)
             traj_f = torch.empty_like(traj_c)
-            traj_p = torch.empty((n_sols, max_run_iter, n_init, nk, H, W), dtype=f32, device=dev)
-        ws = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=dev)
+            traj_p = torch.empty((n_sols, max_run_iter, n_init, nk) + dims, dtype=f32, device=dev)
+        ws = torch.empty(int(self.lib.lnx_workspace_bytes_for(self.handle, n_sols, n_init)), dtype=torch.uint8, device=dev)
         ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream

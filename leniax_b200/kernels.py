@@ -4,6 +4,7 @@
 ``K`` is ``complex64 [1, C, max_k_per_channel, H, W]`` for ``fft=True``.  The spectrum is computed on the GPU with the
 engine's own butterflies (``lnx_rfft2``), not cuFFT; rasterisation uses torch elementwise ops on the same device.
 """
+import ctypes
 import math
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -55,7 +56,9 @@ def _shell(distances: torch.Tensor, bs: torch.Tensor, kf_slug: str, kf_params) -
     return (distances < 1).to(distances.dtype) * shell * ring  # kernels.py:199-207
 
 
-def raw(R, k_params: List, kf_slug: str, kf_params, device=None) -> torch.Tensor:  # kernels.py:161-173
+def raw(R, k_params, kf_slug: str, kf_params, device=None) -> torch.Tensor:  # kernels.py:161-173
+    if isinstance(k_params, torch.Tensor):
+        return k_params.to(device=_default_device(device), dtype=torch.float32)
     return torch.tensor(k_params, dtype=torch.float32, device=_default_device(device))
 
 
@@ -118,19 +121,39 @@ def crop_zero(kernels: torch.Tensor) -> torch.Tensor:  # leniax/utils.py:296-318
     raise ValueError("Can't handle more than 3 dimensions")
 
 
-def rfft2_full(images: torch.Tensor) -> torch.Tensor:
-    """``fftn`` of real ``[..., 128, 128]`` float32 CUDA images with the engine's own FFT (``lnx_rfft2``)."""
+def rfftn_full(images: torch.Tensor, nb_dims: int) -> torch.Tensor:
+    """``fftn`` over the last ``nb_dims`` axes of real float32 CUDA images with the engine's own FFT (``lnx_rfftn``:
+    resident 128x128 butterflies or the tiled multi-pass engine; never cuFFT)."""
     if not images.is_cuda:
-        raise _lib.LeniaxB200Error('the kernel spectrum is computed on the GPU by lnx_rfft2; no CPU fallback exists')
+        raise _lib.LeniaxB200Error('the kernel spectrum is computed on the GPU by lnx_rfftn; no CPU fallback exists')
     lib = _lib.load_library()
-    flat = images.reshape(-1, images.shape[-2], images.shape[-1]).contiguous().float()
-    if flat.shape[-1] != 128 or flat.shape[-2] != 128:
-        raise NotImplementedError(f'only 128x128 worlds are built in this version, got {tuple(flat.shape[-2:])}')
+    dims = tuple(images.shape[-nb_dims:])
+    flat = images.reshape((-1, ) + dims).contiguous().float()
     out = torch.empty(flat.shape, dtype=torch.complex64, device=flat.device)
+    cdims = (ctypes.c_int32 * 3)(*(list(dims) + [1] * (3 - nb_dims)))
     with torch.cuda.device(flat.device):
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.lnx_rfft2(None, flat.shape[0], flat.data_ptr(), out.data_ptr(), stream))
+        _lib.check(lib.lnx_rfftn(nb_dims, cdims, flat.shape[0], flat.data_ptr(), out.data_ptr(), stream))
     return out.reshape(images.shape)
+
+
+def rfft2_full(images: torch.Tensor) -> torch.Tensor:
+    return rfftn_full(images, 2)
+
+
+def sphere_nd(R, k_params: List, kf_slug: str, kf_params, device=None, nb_dims: int = 3) -> torch.Tensor:
+    """EXTENSION (not in the reference, which only ships ``*_2d`` generators, kernels.py:312-317): the ``circle_2d``
+    formula evaluated with an ``nb_dims``-dimensional distance.  Used to build the ``raw`` 3-D kernels of BASELINE
+    config E; the result is a plain array, i.e. what ``k_slug: raw`` carries."""
+    device = _default_device(device)
+    r = k_params[0]
+    bs = torch.tensor(k_params[1], dtype=torch.float32, device=device)
+    k_radius_px = math.ceil(r * R)
+    ax = (torch.arange(2 * k_radius_px, device=device, dtype=torch.float32) - k_radius_px) / (r * R)
+    grids = torch.meshgrid(*([ax] * nb_dims), indexing='ij')
+    distances = torch.sqrt(sum(g**2 for g in grids))
+    kernel = _shell(distances, bs, kf_slug, kf_params)
+    return (kernel / kernel.sum())[None]
 
 
 def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_channels: int, R: float, fft: bool = True,
@@ -178,7 +201,7 @@ def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_chan
         dims = tuple(range(-nd, 0))
         K = torch.stack(per_channel)[None]  # [1, C, max_k, *dims]
         K = torch.roll(K, shifts=[s // 2 for s in K.shape[-nd:]], dims=dims)  # fftshift (kernels.py:147)
-        K = rfft2_full(K)  # kernels.py:148
+        K = rfftn_full(K, nd)  # kernels.py:148
     else:
         K = torch.cat(per_channel)[:, None]  # [C*max_k, 1, kh, kw]
     return K, mapping

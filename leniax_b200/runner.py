@@ -35,6 +35,9 @@ def _finite_params(gf_params: torch.Tensor, weights: torch.Tensor, average: bool
     return ok and bool(torch.isfinite(weights).all().item())
 
 
+FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the tiled multi-pass engine as a cross-check
+
+
 def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, stats_fn: ComputeStatsFn, *, batched: bool,
           keep_trajectory: bool, early_stop: bool = False):
     assert max_run_iter > 0, f"max_run_iter must be positive, value given: {max_run_iter}"  # runner.py:51
@@ -56,7 +59,7 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     K = K.reshape((n_sols, pf.nb_slots) + world_size)
     plan = engine.Plan.get(world_size=world_size, nb_channels=C, slots=slots, c_in=c_in, gf_ids=gf_ids, nb_slots=pf.nb_slots,
                            state_fn=update_fn.get_state_fn.slug, weighted_average=update_fn.get_field_fn.average, R=stats_fn.R,
-                           stats_dt=stats_fn.dt, device=dev)
+                           stats_dt=stats_fn.dt, device=dev, force_tiled=FORCE_TILED_ENGINE)
     flags = 0
     if early_stop:
         flags |= _lib.LNX_RUN_EARLY_STOP

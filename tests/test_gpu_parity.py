@@ -324,3 +324,99 @@ def test_sharded_entry_point_single_rank(golden_dir):
     ref, _ = qd.summarize_stats(stats)
     assert torch.equal(summary[..., 0], stats['N'])
     torch.testing.assert_close(summary, ref, rtol=1e-6, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tiled multi-pass engine (worlds that are not 128x128): BASELINE configs D (2048x2048, R=52) and E (64^3)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_rfftn_matches_numpy_2d_3d():
+    rng = np.random.default_rng(1)
+    for shape in [(2, 64, 256), (1, 512, 32), (2, 16, 32, 64), (1, 64, 64, 64)]:
+        img = rng.random(shape, dtype=np.float32)
+        nd = len(shape) - 1
+        out = kernels.rfftn_full(torch.from_numpy(img).to(DEV), nd).cpu().numpy()
+        ref = np.fft.fftn(img.astype(np.float64), axes=tuple(range(1, nd + 1)))
+        assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-6, shape
+
+
+def test_tiled_engine_matches_resident_and_oracle_on_128(golden_dir):
+    """Same 128x128 worlds through the tiled multi-pass engine (forced) : independent FFT code, same answers."""
+    for name, steps in (('orbium-test', 48), ('aquarium-test', 16)):
+        cfg, ocfg = _setup(golden_dir, name, steps)
+        runner.FORCE_TILED_ENGINE = True
+        try:
+            tc, tf, tp, tstats = helpers.init_and_run(None, cfg, with_jit=True, device=DEV)
+        finally:
+            runner.FORCE_TILED_ENGINE = False
+        oc, of, op, ostats = lo.init_and_run(ocfg, with_jit=True)
+        assert np.abs(tp.cpu().numpy()[0] - op[0]).max() < 2e-6
+        tol = 1e-5 if name == 'orbium-test' else 3e-4
+        assert np.abs(tc.cpu().numpy() - oc).max() < tol, name
+        for k in ('mass', 'mass_volume', 'growth', 'mass_speed', 'inertia', 'mass_growth_dist'):
+            assert np.abs(tstats[k].cpu().numpy().reshape(steps) - ostats[k].reshape(steps)).max() < 5e-4, (name, k)
+        assert tstats['N'].cpu().numpy().reshape(-1).tolist() == ostats['N'].tolist()
+
+
+def _big_orbium(size, scale, n_copies, seed):
+    """Orbium upscaled x`scale` (nearest, like helpers.py:59-66) tiled at random positions of a size x size world."""
+    cfg = utils.load_config(os.path.join(os.path.dirname(__file__), 'golden', 'orbium.yaml'))
+    from leniax_b200 import loader
+    raw = loader.load_raw_cells(cfg, use_init_cells=False).numpy()[0]
+    big = np.kron(raw, np.ones((scale, scale), np.float32))
+    world = np.zeros((size, size), np.float32)
+    rng = np.random.default_rng(seed)
+    for _ in range(n_copies):
+        y, x = rng.integers(0, size - big.shape[0], 2)
+        world[y:y + big.shape[0], x:x + big.shape[1]] = np.maximum(world[y:y + big.shape[0], x:x + big.shape[1]], big)
+    return world
+
+
+@pytest.mark.parametrize('size,scale,steps', [(512, 2, 6), (2048, 4, 3)])
+def test_large_2d_world_matches_oracle(size, scale, steps):
+    """BASELINE config D shape: one large world, R scaled with the pattern, 1 channel / 1 kernel."""
+    R = 13 * scale
+    kp = [dict(k_slug='circle_2d', k_params=[1., [1.]], kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015],
+               h=1., c_in=0, c_out=0)]
+    world = _big_orbium(size, scale, 6, seed=size)
+    K, mapping = kernels.get_kernels_and_mapping(copy.deepcopy(kp), [size, size], 1, R, device=DEV)
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(kp), [size, size], 1, R)
+    assert np.abs(K.cpu().numpy() - oK).max() < 5e-6
+    ufn = helpers.build_update_fn(K.shape, mapping)
+    wp, rp = {'R': R, 'T': 10}, {'world_size': [size, size]}
+    sfn = statistics.build_compute_stats_fn(wp, rp)
+    cells0 = torch.from_numpy(world).to(DEV)[None, None]
+    c, f, p, stats = runner.run_scan(None, cells0, K, mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV), 10., steps, R, ufn, sfn)
+    oc, of, op, ostats = lo.run_scan(world[None, None], oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), steps,
+                                     lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp))
+    assert np.abs(p.cpu().numpy() - op).max() < 3e-6
+    assert np.abs(c.cpu().numpy() - oc).max() < 1e-5
+    for k in ('mass', 'mass_volume', 'growth', 'mass_density'):
+        np.testing.assert_allclose(stats[k].cpu().numpy(), ostats[k], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(stats['inertia'].cpu().numpy(), ostats['inertia'], rtol=1e-3)
+
+
+def test_3d_worlds_match_oracle():
+    """BASELINE config E shape (64^3, 1 channel / 1 kernel, raw spherical-shell kernel); the reference has no 3-D kernel
+    generator and no 3-D test: parity is oracle-only."""
+    D, R, steps, n = 64, 13, 4, 3
+    kern = kernels.sphere_nd(R, [1., [1.]], 'poly_quad', [4], device=DEV)  # [1, 26, 26, 26]
+    kp = [dict(k_slug='raw', k_params=kern, kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1., c_in=0, c_out=0)]
+    K, mapping = kernels.get_kernels_and_mapping(kp, [D, D, D], 1, R, device=DEV)
+    okp = [dict(kp[0], k_params=kern.cpu().numpy())]
+    oK, om = lo.get_kernels_and_mapping(okp, [D, D, D], 1, R)
+    assert K.shape == (1, 1, 1, D, D, D) and np.abs(K.cpu().numpy() - oK).max() < 5e-6
+    rng = np.random.default_rng(3)
+    maxv = np.linspace(0.4, 1., n, dtype=np.float32)[:, None, None, None, None]
+    worlds = (rng.random((n, 1, D, D, D), dtype=np.float32) * maxv).astype(np.float32)  # initializations.py:26-28
+    ufn = helpers.build_update_fn(K.shape, mapping)
+    wp, rp = {'R': R, 'T': 10}, {'world_size': [D, D, D]}
+    sfn = statistics.build_compute_stats_fn(wp, rp)
+    c, f, p, stats = runner.run_scan(None, torch.from_numpy(worlds).to(DEV), K, mapping.get_gf_params(DEV),
+                                     mapping.get_kernels_weight_per_channel(DEV), 10., steps, R, ufn, sfn)
+    oc, of, op, ostats = lo.run_scan(worlds, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), steps,
+                                     lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp))
+    assert np.abs(p.cpu().numpy() - op).max() < 3e-6
+    assert np.abs(c.cpu().numpy() - oc).max() < 1e-5
+    for k in ('mass', 'mass_volume', 'growth', 'mass_speed', 'mass_growth_dist', 'potential_volume'):
+        np.testing.assert_allclose(stats[k].cpu().numpy(), ostats[k], rtol=5e-4, atol=1e-4, err_msg=k)
+    assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()

@@ -52,7 +52,7 @@ def test_plan_validation_errors():
     lib = leniax_b200.load_library()
     handle = ctypes.c_void_p()
     d = _lib.LnxDesc(nb_dims=2, nb_channels=1, nb_kernels=1, nb_slots=1, R=13., stats_dt=.1)
-    d.dims[0], d.dims[1] = 64, 64
+    d.dims[0], d.dims[1] = 100, 100  # not a power of two: neither the resident nor the tiled engine takes it
     assert lib.lnx_plan_create(ctypes.byref(d), ctypes.byref(handle)) == _lib.LNX_ERR_UNSUPPORTED
     d.dims[0] = d.dims[1] = 128
     d.nb_channels = 99
