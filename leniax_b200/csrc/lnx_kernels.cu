@@ -674,7 +674,7 @@ static size_t smem_b(const Geom& g) { return 2 * (size_t)g.L * g.tc * sizeof(flo
 static size_t smem_c(const Geom& g, int C) {
     return ((size_t)g.slab_rows * g.half + (size_t)(g.slab_rows / 2) * g.A2) * sizeof(float2) + (size_t)C * g.slab_rows * g.A2 * sizeof(float);
 }
-constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr size_t SMEM_LIMIT = 220 * 1024;  // dynamic part; pass C also has ~1 KB of static shared memory
 
 static float2* g_tw[64] = {nullptr};  // library-owned twiddle master table per device: (cos, sin)(2 pi k / NMAX)
 static int ensure_tiled_init(int dev) {
@@ -690,7 +690,10 @@ static int ensure_tiled_init(int dev) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-    if (e != cudaSuccess) return -1;
+    if (e != cudaSuccess) {
+        fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(e));
+        return -1;
+    }
     g_tw[dev] = d;
     return LNX_OK;
 }
@@ -810,7 +813,7 @@ int lnx_plan_create(const lnx_desc* d, lnx_plan** out) {
     p->g = geom;
     if (p->tiled && th::ensure_tiled_init(dev) != LNX_OK) {
         delete p;
-        return fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return LNX_ERR_CUDA;  // message set by ensure_tiled_init
     }
     *out = p;
     return LNX_OK;
@@ -888,7 +891,7 @@ int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const floa
     const char* why = "";
     if (!th::make_geom(nb_dims, dims, &g, &why)) return fail(LNX_ERR_UNSUPPORTED, "lnx_rfftn: %s", why);
     if (th::smem_a(g) > th::SMEM_LIMIT || th::smem_b(g) > th::SMEM_LIMIT) return fail(LNX_ERR_UNSUPPORTED, "lnx_rfftn: world too large");
-    if (th::ensure_tiled_init(dev) != LNX_OK) return fail(LNX_ERR_CUDA, "tiled engine setup failed");
+    if (th::ensure_tiled_init(dev) != LNX_OK) return LNX_ERR_CUDA;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float2 *sa = nullptr, *sb = nullptr;
     const size_t bytes = (size_t)n_images * g.spec * sizeof(float2);
