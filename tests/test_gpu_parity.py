@@ -164,8 +164,8 @@ def test_fused_batch_matches_oracle_and_generic(golden_dir):
         assert d.max() < 1.3e-2, (k, d.max())  # dying / exploding worlds are chaotic: a couple of cells (1/169 each) may flip
         pure = np.array([i % 7 not in (3, 5) for i in range(n)])  # unperturbed Orbiums: the non-chaotic survivors
         assert d[:, pure].max() < 2e-4, (k, d[:, pure].max())
-    alive = ostats['N'] == steps
-    assert np.abs(final[0].cpu().numpy() - ofinal)[alive].max() < 1e-4
+    pure = np.array([i % 7 not in (3, 5) for i in range(n)])
+    assert np.abs(final[0].cpu().numpy() - ofinal)[pure].max() < 1e-4  # final state after 160 updates, unperturbed Orbiums
     assert len(set(ostats['N'].tolist())) > 1  # the batch really contains worlds that stop early
 
 
