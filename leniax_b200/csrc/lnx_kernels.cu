@@ -22,7 +22,6 @@ namespace lnx {
 constexpr int NTHREADS = NT + 32;   // 256 compute threads + 1 statistics warp
 constexpr int BAR_COMPUTE = 1;      // named barrier: the 256 compute threads
 constexpr int BAR_PARTIALS = 2;     // compute arrive  -> statistics warp sync   (partials of step t are in smem)
-constexpr int BAR_CARRY = 3;        // statistics warp arrive -> compute sync    (shift / stop flag of step t ready)
 constexpr int KT_F4 = 16 * NT;      // float4 per kernel table (complex multipliers)
 constexpr int KPQ_F4 = 32 * KPQ_LANES;  // float4 per packed-column table (Kp, Kq)
 constexpr int SCRATCH_BYTES = 2 * 4 * 32 * 8;  // packed-column exchange of warp 0
@@ -34,12 +33,24 @@ constexpr int NPART_MAX = PT_FIXED + MAX_C;
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// release/acquire flag in shared memory: the statistics warp publishes "step t is final" without forcing the compute
+// warps through a CTA-wide barrier (a bar.sync with all 288 threads re-aligned the 8 compute warps once more per step)
+__device__ __forceinline__ int ld_acquire_smem(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_smem(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
 __constant__ float2 c_tw128[128];
 
 struct Ctrl {
     int world;
     int shift0, shift1;
     int stop;
+    int done;                      // number of steps whose statistics (carry + stop flag) are final
     float tot[NPART_MAX];          // CTA-wide sums of the step (statistics warp)
     float row[ST_COUNT + MAX_C];   // finished statistics row
 };
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
             ctrl->world = atomicAdd(P.queue, 1);
             ctrl->shift0 = ctrl->shift1 = 0;
             ctrl->stop = 0;
+            ctrl->done = 0;
         }
         __syncthreads();
         const int world = ctrl->world;
@@ -282,7 +294,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
             }
             bar_sync(BAR_COMPUTE, NT);  // Kt / Kpq visible to every compute thread
 
-            bool stopped = false;
             for (int t = 0; t < P.max_iter; ++t) {
                 load_state_regs(R, A4, tid);
                 __syncwarp();  // previous step's phase5 reads of this group's region are complete
@@ -310,17 +321,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
                 phase5_load(tid, R, W);
                 phase5_ifft(R);
                 if (t > 0) {
-                    bar_sync(BAR_CARRY, NTHREADS);  // statistics of step t-1 are final: shift carry + stop flag
-                    if (ctrl->stop) {
-                        stopped = true;
-                        break;
-                    }
+                    while (ld_acquire_smem(&ctrl->done) < t) {}  // statistics of step t-1 are final: shift carry + stop flag
+                    if (ctrl->stop) break;
                 }
                 cells_fused<GF, SF, NP>(tid, R.v, A4, fc, ctrl->shift0, ctrl->shift1, part);
                 __threadfence_block();
                 bar_arrive(BAR_PARTIALS, NTHREADS);
             }
-            if (!stopped) bar_sync(BAR_CARRY, NTHREADS);
             if (P.final_cells) scatter_state(P.final_cells + (size_t)world * (WS * WS), A4, tid);
         } else {
             // ------------------------------------------------ statistics warp ------------------------------------------
@@ -336,9 +343,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_fused(const RunArgs 
                     ctrl->shift0 = S.shift[0];
                     ctrl->shift1 = S.shift[1];
                     ctrl->stop = stop;
+                    st_release_smem(&ctrl->done, t + 1);
                 }
-                __threadfence_block();
-                bar_arrive(BAR_CARRY, NTHREADS);
                 if (stop) break;
             }
             if (lane == 0) P.n_alive[world] = S.n_alive;
@@ -384,6 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
             ctrl->world = atomicAdd(P.queue, 1);
             ctrl->shift0 = ctrl->shift1 = 0;
             ctrl->stop = 0;
+            ctrl->done = 0;
         }
         __syncthreads();
         const int world = ctrl->world;
@@ -404,7 +411,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
             const int l = t_sub(tid) & 3;
             for (int c = 0; c < C; ++c) gather_state(Ast + (size_t)c * PLANE_F4, P.cells0 + ((size_t)world * C + c) * (WS * WS), tid);
             const float4* tab = P.table + (size_t)sol * K * KTAB_F4;
-            bool stopped = false;
             for (int t = 0; t < P.max_iter; ++t) {
                 const size_t tstep = ((size_t)sol * P.max_iter + t) * P.n_init + init;  // index of this world-step in trajectories
                 // ---- forward transforms of every channel ----
@@ -488,11 +494,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                     }
                 }
                 if (t > 0) {
-                    bar_sync(BAR_CARRY, NTHREADS);
-                    if (ctrl->stop) {
-                        stopped = true;
-                        break;
-                    }
+                    while (ld_acquire_smem(&ctrl->done) < t) {}
+                    if (ctrl->stop) break;
                 }
                 // ---- state update + statistics partials ----
                 const int sh0 = ctrl->shift0, sh1 = ctrl->shift1;
@@ -561,7 +564,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                 __threadfence_block();
                 bar_arrive(BAR_PARTIALS, NTHREADS);
             }
-            if (!stopped) bar_sync(BAR_CARRY, NTHREADS);
             if (P.final_cells)
                 for (int c = 0; c < C; ++c) scatter_state(P.final_cells + ((size_t)world * C + c) * (WS * WS), Ast + (size_t)c * PLANE_F4, tid);
         } else {
@@ -577,9 +579,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                     ctrl->shift0 = S.shift[0];
                     ctrl->shift1 = S.shift[1];
                     ctrl->stop = stop;
+                    st_release_smem(&ctrl->done, t + 1);
                 }
-                __threadfence_block();
-                bar_arrive(BAR_CARRY, NTHREADS);
                 if (stop) break;
             }
             if (lane == 0) P.n_alive[world] = S.n_alive;
