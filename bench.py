@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument('--sim-steps', type=int, default=SIM_STEPS)
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--fused-r16', action='store_true', help='A/B: time the 512-thread (R16) fused kernel instead of the default 256-thread one')
     return ap.parse_args()
 
 
@@ -198,6 +199,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = leniax_b200.load_library()
+    runner.FUSED_R16 = bool(args.fused_r16)
+    variant_flag = _lib.LNX_RUN_FUSED_R16 if args.fused_r16 else 0
 
     n_worlds, sim_steps = args.worlds, args.sim_steps
     cfg, worlds_np = make_worlds_numpy(n_worlds, seed=1 + rank)
@@ -271,7 +274,7 @@ def run_b200(args):
     stream = torch.cuda.current_stream().cuda_stream
 
     def launch_kernel():
-        _lib.check(lib.lnx_run_scan(plan.handle, 1, n_worlds, sim_steps, _lib.LNX_RUN_ASSUME_FINITE, dev_cells.data_ptr(), table.data_ptr(),
+        _lib.check(lib.lnx_run_scan(plan.handle, 1, n_worlds, sim_steps, _lib.LNX_RUN_ASSUME_FINITE | variant_flag, dev_cells.data_ptr(), table.data_ptr(),
                                     gf.data_ptr(), w.data_ptr(), dt.data_ptr(), stats_buf.data_ptr(), cm_buf.data_ptr(), n_buf.data_ptr(),
                                     None, None, None, None, ws_buf.data_ptr(), ws_buf.numel(), stream))
 
@@ -311,11 +314,11 @@ def run_b200(args):
             },
             'e2e': {'value': e2e_value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': int(host_cells.numel() * 4) * world,
                     'd2h_bytes_per_step': int(block_h.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': 2 * args.steps,  # per step: lnx_prepare_kernel + lnx_world128_fused
+            'gpu_launches': 2 * args.steps,  # per step: lnx_prepare_kernel + the fused world kernel
             'clocks': clocks,
             'roofline': {
                 'bound': 'fp32', 'achieved': achieved_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved_tflops / fp32_peak,
-                'traffic': None, 'kernel': 'lnx_world128_fused', 'kernel_ms': kernel_ms,
+                'traffic': None, 'kernel': 'lnx_world128_r16' if args.fused_r16 else 'lnx_world128_fused', 'kernel_ms': kernel_ms,
                 'flop_per_cell_update': FLOP_PER_CELL_UPDATE, 'peak_source': 'measured live: lnx_measure_fp32_peak FMA loop (MEASURED_PEAKS.json has no FP32 entry)',
                 'peak_analytic_tflops': FP32_PEAK_ANALYTIC_TFLOPS, 'frac_of_analytic': achieved_tflops / FP32_PEAK_ANALYTIC_TFLOPS,
                 'hbm_achieved_gbs': stats_bytes / (kernel_ms * 1e-3) / 1e9, 'hbm_peak_gbs': peaks.get('hbm_gbs'),

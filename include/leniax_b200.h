@@ -61,6 +61,8 @@ typedef enum {
                                  the stop are left untouched); default off = bit-for-bit [max_run_iter] rows like
                                  runner.py:207-213 */
 #define LNX_RUN_NO_STATS 2u   /* reserved */
+#define LNX_RUN_FUSED_R16 0x200u     /* fused single-channel path: use the 512-thread kernel (one real row quarter per thread,
+                                        4 warps per scheduler) instead of the default 256-thread one (A/B runs, tests) */
 #define LNX_RUN_ASSUME_FINITE 0x100u /* caller checked that no growth s == 0 and no weight row sums to 0: NaN cannot
                                         appear, the fused kernel may use min/max clamps that do not propagate NaN */
 

@@ -35,6 +35,7 @@ def _finite_params(gf_params: torch.Tensor, weights: torch.Tensor, average: bool
     return ok and bool(torch.isfinite(weights).all().item())
 
 
+FUSED_R16 = False  # tests / A-B runs: use the 512-thread (R16) fused kernel instead of the default 256-thread one
 FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the tiled multi-pass engine as a cross-check
 
 
@@ -63,6 +64,8 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     flags = 0
     if early_stop:
         flags |= _lib.LNX_RUN_EARLY_STOP
+    if FUSED_R16:
+        flags |= _lib.LNX_RUN_FUSED_R16
     if _finite_params(gf_params, weights, update_fn.get_field_fn.average):
         flags |= _lib.LNX_RUN_ASSUME_FINITE
     dt = (1. / T.reshape(n_sols)).contiguous()  # runner.py:307
