@@ -148,6 +148,13 @@ int lnx_run_scan(const lnx_plan* plan, int32_t n_sols, int32_t n_init, int32_t m
                  float* stats, float* channel_mass, float* n_alive, float* final_cells, float* cells_out, float* field_out,
                  float* potential_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Stand-alone statistics of given arrays: replaces a direct call of the closure returned by
+ * statistics.build_compute_stats_fn (leniax/statistics.py:36-126).  cells/field [n_worlds][C][dims...], potential
+ * [n_worlds][K][dims...]; carry arrays are updated in place: total_shift_idx int32 [n_worlds][nb_dims], mass_centroid
+ * float [nb_dims][n_worlds], mass_angle float [n_worlds].  Out: stats [LNX_NB_STATS][n_worlds], channel_mass [n_worlds][C]. */
+int lnx_compute_stats(const lnx_plan* plan, int32_t n_worlds, const float* cells, const float* field, const float* potential,
+                      int32_t* total_shift_idx, float* mass_centroid, float* mass_angle, float* stats, float* channel_mass, void* stream);
+
 /* Name of the CUDA kernel lnx_run_scan would launch for this plan/arguments ("fused" or "generic"), for tests. */
 const char* lnx_run_scan_variant(const lnx_plan* plan, int32_t with_trajectory);
 

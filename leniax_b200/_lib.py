@@ -59,6 +59,7 @@ EXPORTS = {
     'lnx_workspace_bytes_for': (c_size_t, [c_void_p, c_int32, c_int32]),
     'lnx_rfftn': (ctypes.c_int, [c_int32, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_void_p]),
     'lnx_run_scan': (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_uint32] + [c_void_p] * 12 + [c_void_p, c_size_t, c_void_p]),
+    'lnx_compute_stats': (ctypes.c_int, [c_void_p, c_int32] + [c_void_p] * 8 + [c_void_p]),
     'lnx_run_scan_variant': (c_char_p, [c_void_p, c_int32]),
 }
 

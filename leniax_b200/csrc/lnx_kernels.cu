@@ -1127,6 +1127,57 @@ int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const floa
     return LNX_OK;
 }
 
+int lnx_compute_stats(const lnx_plan* p, int32_t n_worlds, const float* cells, const float* field, const float* potential,
+                      int32_t* total_shift_idx, float* mass_centroid, float* mass_angle, float* stats, float* channel_mass, void* stream) {
+    using namespace lnx::tiled;
+    if (!p || n_worlds < 1 || !cells || !field || !potential || !total_shift_idx || !mass_centroid || !mass_angle || !stats || !channel_mass)
+        return fail(LNX_ERR_INVALID, "lnx_compute_stats: bad argument");
+    if (n_worlds > 65535) return fail(LNX_ERR_INVALID, "lnx_compute_stats: at most 65535 worlds per call");
+    Geom g;
+    const char* why = "";
+    if (!th::make_geom(p->d.nb_dims, p->d.dims, &g, &why)) return fail(LNX_ERR_UNSUPPORTED, "lnx_compute_stats: %s", why);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* partials = nullptr;
+    WorldCarry* carry = nullptr;
+    float* n_alive = nullptr;
+    LNX_CUDA(cudaMallocAsync(&partials, (size_t)n_worlds * g.n_slabs * NP_T * sizeof(float), st));
+    LNX_CUDA(cudaMallocAsync(&carry, (size_t)n_worlds * sizeof(WorldCarry), st));
+    LNX_CUDA(cudaMallocAsync(&n_alive, (size_t)n_worlds * sizeof(float), st));
+    const int nd = g.nd, tb = 128, nb = (n_worlds + tb - 1) / tb;
+    carry_pack_kernel<<<nb, tb, 0, st>>>(carry, total_shift_idx, mass_centroid, mass_angle, n_worlds, nd, false, nullptr, nullptr, nullptr);
+    StatsPartialArgs a;
+    a.cells = cells;
+    a.field = field;
+    a.potential = potential;
+    a.carry = carry;
+    a.partials = partials;
+    a.g = g;
+    a.C = p->d.nb_channels;
+    a.K = p->d.nb_kernels;
+    stats_partials_kernel<<<dim3(g.n_slabs, 1, n_worlds), TPB, 0, st>>>(a);
+    PassDArgs d;
+    d.partials = partials;
+    d.carry = carry;
+    d.stats = stats;
+    d.channel_mass = channel_mass;
+    d.n_alive = n_alive;
+    d.g = g;
+    d.C = p->d.nb_channels;
+    d.n_sols = 1;
+    d.n_init = n_worlds;
+    d.max_iter = 1;
+    d.t = 0;
+    d.R = p->d.R;
+    d.stats_dt = p->d.stats_dt;
+    pass_d_kernel<<<n_worlds, 128, 0, st>>>(d);
+    carry_pack_kernel<<<nb, tb, 0, st>>>(carry, nullptr, nullptr, nullptr, n_worlds, nd, true, total_shift_idx, mass_centroid, mass_angle);
+    LNX_CUDA(cudaGetLastError());
+    LNX_CUDA(cudaFreeAsync(partials, st));
+    LNX_CUDA(cudaFreeAsync(carry, st));
+    LNX_CUDA(cudaFreeAsync(n_alive, st));
+    return LNX_OK;
+}
+
 int lnx_measure_fp32_peak(int32_t iters, double* tflops, double* ms, void* stream) {
     if (iters < 1 || !tflops) return fail(LNX_ERR_INVALID, "lnx_measure_fp32_peak: bad argument");
     int dev = 0, sms = 0;

@@ -449,6 +449,103 @@ __global__ void __launch_bounds__(128) pass_d_kernel(PassDArgs P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// stand-alone compute_stats (leniax/statistics.py:36-126 called outside a scan, e.g. by user code): partial sums of given
+// cells / field / potential arrays, finalised by pass_d_kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct StatsPartialArgs {
+    const float* cells;      // [worlds][C][cells]
+    const float* field;      // [worlds][C][cells]
+    const float* potential;  // [worlds][K][cells]
+    const WorldCarry* carry;
+    float* partials;         // [worlds][n_slabs][NP_T]
+    Geom g;
+    int C, K;
+};
+__global__ void __launch_bounds__(TPB) stats_partials_kernel(StatsPartialArgs P) {
+    __shared__ float red[NP_T][TPB / 32];
+    const Geom& g = P.g;
+    const int slab = blockIdx.x, w = blockIdx.z;
+    const int slab_cells = g.slab_rows * g.A2;
+    const size_t off = (size_t)slab * slab_cells;
+    const WorldCarry cr = P.carry[w];
+    float acc[NP_T];
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) acc[i] = 0.f;
+    for (int k = 0; k < P.K; ++k) {
+        const float* pt = P.potential + ((size_t)w * P.K + k) * g.cells + off;
+        for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) acc[3] += pt[i] > EPS ? 1.f : 0.f;
+    }
+    for (int c = 0; c < P.C; ++c) {
+        const float* ce = P.cells + ((size_t)w * P.C + c) * g.cells + off;
+        const float* fi = P.field + ((size_t)w * P.C + c) * g.cells + off;
+        float m00 = 0.f;
+        for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) {
+            const size_t grow = (size_t)slab * g.slab_rows + (i >> g.logA2);
+            const int n = i & (g.A2 - 1);
+            int idx[3];
+            if (g.nd == 3) {
+                idx[0] = (int)(grow >> g.logA1);
+                idx[1] = (int)(grow & (g.A1 - 1));
+                idx[2] = n;
+            } else {
+                idx[0] = (int)grow;
+                idx[1] = n;
+                idx[2] = 0;
+            }
+            const float a = ce[i], gp = fmaxf(fi[i], 0.f);
+            m00 += a;
+            acc[0] += a > EPS ? 1.f : 0.f;
+            acc[1] += gp;
+            acc[2] += gp > EPS ? 1.f : 0.f;
+            for (int d = 0; d < g.nd; ++d) {
+                const float x = (float)(((idx[d] - cr.shift[d]) & (g.dims[d] - 1)) - g.dims[d] / 2);
+                acc[4 + d] += a * x;
+                acc[4 + MAXD + d] += a * x * x;
+                acc[4 + 2 * MAXD + d] += gp * x;
+            }
+        }
+        acc[4 + 3 * MAXD + c] = m00;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NP_T) {
+        float v = 0.f;
+        for (int j = 0; j < TPB / 32; ++j) v += red[threadIdx.x][j];
+        P.partials[((size_t)w * g.n_slabs + slab) * NP_T + threadIdx.x] = v;
+    }
+}
+// user-facing carry arrays <-> WorldCarry (total_shift_idx [N][nd] int32, mass_centroid [nd][N], mass_angle [N])
+__global__ void carry_pack_kernel(WorldCarry* carry, const int* shift, const float* centroid, const float* angle, int n, int nd, bool unpack,
+                                  int* shift_out, float* centroid_out, float* angle_out) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    if (!unpack) {
+        WorldCarry c;
+        memset(&c, 0, sizeof(c));
+        for (int d = 0; d < nd; ++d) {
+            c.shift[d] = shift[w * nd + d];
+            c.centroid[d] = centroid[d * n + w];
+        }
+        c.angle = angle[w];
+        carry[w] = c;
+    } else {
+        const WorldCarry c = carry[w];
+        for (int d = 0; d < nd; ++d) {
+            shift_out[w * nd + d] = c.shift[d];
+            centroid_out[d * n + w] = c.centroid[d];
+        }
+        angle_out[w] = c.angle;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // helpers: kernel table gather, Hermitian expansion (kernel-spectrum builder)
 // ---------------------------------------------------------------------------------------------------------------------
 // K_fft full complex [n_sols][nb_slots][cells] (reference layout) -> table [n_sols][K][rows][half] scaled by 1/cells

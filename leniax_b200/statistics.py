@@ -24,10 +24,34 @@ class ComputeStatsFn:
     dt: float
 
     def __call__(self, cells, field, potential, total_shift_idx, mass_centroid, mass_angle):
-        raise NotImplementedError(
-            'per-step statistics are fused into the scan kernel; call leniax_b200.runner.run / run_scan / '
-            'run_scan_mem_optimized, which return the same stats dictionary'
-        )
+        """Stand-alone ``compute_stats`` (statistics.py:36-126): ``cells/field [N, C, *dims]``, ``potential [N, K, *dims]``,
+        ``total_shift_idx [N, D]`` int32, ``mass_centroid [D, N]``, ``mass_angle [N]`` ->
+        ``(stats dict, total_shift_idx, mass_centroid, mass_angle)``.  Inside the scans the same statistics are fused
+        into the persistent kernels; this entry point runs ``lnx_compute_stats``."""
+        from . import _lib, engine
+        dev = engine.require_cuda_device(cells.device if isinstance(cells, torch.Tensor) and cells.is_cuda else None)
+        f32 = torch.float32
+        cells = engine.as_device_tensor(cells, f32, dev)
+        field = engine.as_device_tensor(field, f32, dev)
+        potential = engine.as_device_tensor(potential, f32, dev)
+        N, C, K = cells.shape[0], cells.shape[1], potential.shape[1]
+        nd = len(self.world_size)
+        if tuple(cells.shape[2:]) != tuple(self.world_size):
+            raise ValueError(f'compute_stats_fn was built for world_size {self.world_size}, cells are {tuple(cells.shape[2:])}')
+        shift = engine.as_device_tensor(total_shift_idx, torch.int32, dev).reshape(N, nd).clone()
+        centroid = engine.as_device_tensor(mass_centroid, f32, dev).reshape(nd, N).clone()
+        angle = engine.as_device_tensor(mass_angle, f32, dev).reshape(N).clone()
+        plan = engine.Plan.get(world_size=self.world_size, nb_channels=C, slots=tuple(range(K)), c_in=(0, ) * K, gf_ids=(0, ) * K,
+                               nb_slots=K, state_fn='v1', weighted_average=True, R=self.R, stats_dt=self.dt, device=dev)
+        stats = torch.empty((_lib.LNX_NB_STATS, N), dtype=f32, device=dev)
+        cm = torch.empty((N, C), dtype=f32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(plan.lib.lnx_compute_stats(plan.handle, N, cells.data_ptr(), field.data_ptr(), potential.data_ptr(), shift.data_ptr(),
+                                                  centroid.data_ptr(), angle.data_ptr(), stats.data_ptr(), cm.data_ptr(), stream))
+        out = {k: stats[i] for i, k in enumerate(_lib.STAT_KEYS)}
+        out['channel_mass'] = cm
+        return out, shift, centroid, angle
 
 
 def build_compute_stats_fn(world_params: Dict, render_params: Dict) -> ComputeStatsFn:

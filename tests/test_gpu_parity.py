@@ -428,3 +428,89 @@ def test_3d_worlds_match_oracle():
     for k in ('mass', 'mass_volume', 'growth', 'mass_speed', 'mass_growth_dist', 'potential_volume'):
         np.testing.assert_allclose(stats[k].cpu().numpy(), ostats[k], rtol=5e-4, atol=1e-4, err_msg=k)
     assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()
+
+
+def test_standalone_compute_stats_matches_oracle(golden_dir):
+    """The closure returned by statistics.build_compute_stats_fn called on its own (statistics.py:36-126), 2-D and 3-D."""
+    rng = np.random.default_rng(8)
+    for dims, C, K in (((128, 128), 2, 3), ((32, 64, 16), 1, 1)):
+        N, nd = 3, len(dims)
+        wp, rp = {'R': 13, 'T': 10}, {'world_size': list(dims)}
+        cells = rng.random((N, C) + dims, dtype=np.float32) * (rng.random((N, C) + dims) > 0.7)
+        field = (rng.random((N, C) + dims, dtype=np.float32) * 2 - 1).astype(np.float32)
+        pot = (rng.random((N, K) + dims, dtype=np.float32) * 1e-6).astype(np.float32)
+        shift = rng.integers(0, min(dims), size=(N, nd)).astype(np.int32)
+        centroid = (rng.random((nd, N), dtype=np.float32) - 0.5).astype(np.float32)
+        angle = (rng.random(N, dtype=np.float32) * 90).astype(np.float32)
+        ost, oshift, ocen, oang = lo.build_compute_stats_fn(wp, rp)(cells.astype(np.float32), field, pot, shift, centroid, angle)
+        st, sh, cen, ang = statistics.build_compute_stats_fn(wp, rp)(torch.from_numpy(cells.astype(np.float32)).to(DEV), torch.from_numpy(field).to(DEV),
+                                                                    torch.from_numpy(pot).to(DEV), shift, centroid, angle)
+        for k in ost:
+            np.testing.assert_allclose(st[k].cpu().numpy(), ost[k], rtol=2e-4, atol=2e-4, err_msg=f'{dims} {k}')
+        np.testing.assert_array_equal(sh.cpu().numpy(), oshift)
+        np.testing.assert_allclose(cen.cpu().numpy(), ocen, atol=1e-4)
+        np.testing.assert_allclose(ang.cpu().numpy(), oang, atol=1e-2)
+
+
+def test_edge_cases_empty_and_nan_worlds(golden_dir):
+    """Reference edge semantics: an empty world stops at once (channel mass < eps -> N = 0); a zero weight row makes the
+    weighted mean 0/0 = NaN (core.py:240), NaN propagates through clip (core.py:265) and every comparison fails -> N = 0."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test', 6)
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    T = torch.tensor([10.], device=DEV)
+    worlds = torch.stack([torch.zeros_like(cells[0]), cells[0]])[None]  # [1, 2, 1, 128, 128]: empty world + Orbium
+    stats, final = runner.run_scan_mem_optimized(None, worlds, K[None], gf[None], w[None], T, 6, 13, ufn, sfn)
+    assert stats['N'][0].tolist() == [0., 6.]
+    assert float(final[0, 0].abs().max()) == 0. and float(stats['mass'][0, :, 0].abs().max()) == 0.
+    # h = 0: zero weight row
+    w0 = torch.zeros_like(w)
+    ostats, _ = lo.run_scan(cells.cpu().numpy(), lo.init(ocfg)[1], gf.cpu().numpy(), w0.cpu().numpy(), np.float32(10.), 6,
+                            lo.build_update_fn(lo.init(ocfg)[2]), lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), False)
+    for fn in (runner.run_scan_mem_optimized, ):
+        st, fin = fn(None, cells[None], K[None], gf[None], w0[None], T, 6, 13, ufn, sfn)
+        assert torch.isnan(fin).all()
+        assert st['N'][0].tolist() == ostats['N'].tolist()  # first row is finite (pre-update cells), then NaN: N = 1
+        assert bool(torch.isnan(st['mass'][0, 1:, 0]).all()) and np.isnan(ostats['mass'][1:, 0]).all()
+
+
+def test_runner_run_python_loop_semantics(golden_dir):
+    """runner.run (reference runner.py:16-116): on-the-fly heuristics with the grace period and the break."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test', 60)
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    ocells, oK, om = lo.init(ocfg)
+    for scale in (1.0, 0.2):  # a survivor and a world that fades away (mass below epsilon -> break after START_CHECK_STOP)
+        c, f, p, st = runner.run(None, cells * scale, K, gf, w, 10., 60, 13, ufn, sfn, stat_trunc=True)
+        oc, of, op, ost = lo.run((ocells * scale).astype(np.float32), oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), 60,
+                                 lo.build_update_fn(om), lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), True)
+        assert int(st['N']) == int(ost['N'])
+        assert c.shape == oc.shape and st['mass'].shape == ost['mass'].shape
+        np.testing.assert_allclose(c.cpu().numpy(), oc, atol=1e-5)
+
+
+def test_per_solution_parameters_weighted_sum_and_odd_batch(golden_dir):
+    """N_sols with different m, s, h, T (runner.py:167-215 vmaps all of them), weighted_sum mode, batch sizes that are not a
+    multiple of the SM count."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test', 24)
+    cells, K, mapping, _, sfn = _engine_parts(cfg)
+    ufn = helpers.build_update_fn(K.shape, mapping, 'v1', False, True)  # weighted_average = False -> core.weighted_sum
+    n_sols, n_init = 3, 5
+    rng = np.random.default_rng(21)
+    gfp = np.stack([[[0.15, 0.015]], [[0.14, 0.02]], [[0.16, 0.017]]]).astype(np.float32)
+    wts = np.array([[[1.0]], [[0.8]], [[1.2]]], np.float32)
+    Ts = np.array([10., 8., 12.], np.float32)
+    base = cells[0].cpu().numpy()
+    worlds = np.stack([np.stack([np.roll(base, (int(rng.integers(128)), int(rng.integers(128))), axis=(1, 2)) for _ in range(n_init)]) for _ in range(n_sols)])
+    Ks = torch.stack([K] * n_sols)
+    stats, final = runner.run_scan_mem_optimized(None, torch.from_numpy(worlds).to(DEV), Ks, torch.from_numpy(gfp).to(DEV), torch.from_numpy(wts).to(DEV),
+                                                 torch.from_numpy(Ts).to(DEV), 24, 13, ufn, sfn)
+    _, oK, om = lo.init(ocfg)
+    oupd = lo.build_update_fn(om, 'v1', False)
+    osf = lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params'])
+    ostats, ofinal = lo.run_scan_mem_optimized(worlds, np.stack([oK] * n_sols), gfp, wts, Ts, 24, oupd, osf)
+    assert stats['mass'].shape == (n_sols, 24, n_init)
+    np.testing.assert_array_equal(stats['N'].cpu().numpy(), ostats['N'])
+    np.testing.assert_allclose(final.cpu().numpy(), ofinal, atol=2e-5)
+    np.testing.assert_allclose(stats['mass'].cpu().numpy(), ostats['mass'], atol=1e-5)
+    np.testing.assert_allclose(stats['mass_speed'].cpu().numpy(), ostats['mass_speed'], atol=5e-4)
