@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
         if (tid < C) {
             float sum = 0.f;
             for (int k = 0; k < K; ++k) sum += P.weights[((size_t)sol * C + tid) * K + k];
-            gc->inv_wsum[tid] = P.mean ? sum : 1.0f;  // generic kernel: true division by the row sum (core.py:240)
+            gc->inv_wsum[tid] = P.mean ? 1.0f / sum : 1.0f;
         }
         if (tid == 0) gc->dt = P.dt[sol];
         __syncthreads();
@@ -661,20 +661,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                     phase5_ifft(R);
                     if (P.potential_out) {
                         float* img = P.potential_out + (tstep * K + k) * (WS * WS);
-#pragma unroll 8
-                        for (int j = 0; j < 32; ++j) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {  // fully unrolled: R.v must keep compile-time indices (registers)
                             img[cell_row(tid, 0) * WS + 4 * j + l] = R.v[j].x;
                             img[cell_row(tid, 1) * WS + 4 * j + l] = R.v[j].y;
                         }
                     }
-                    const GfConst g = gc->gf[k];
-                    const int gf = P.gf_id[k];
-#pragma unroll 8
-                    for (int j = 0; j < 32; ++j) {
-                        cnt_p += (R.v[j].x > EPS ? 1.f : 0.f) + (R.v[j].y > EPS ? 1.f : 0.f);
-                        R.v[j].x = growth_dyn<true>(gf, R.v[j].x, g);
-                        R.v[j].y = growth_dyn<true>(gf, R.v[j].y, g);
-                    }
+                    growth_vec_dyn<true, 32>(P.gf_id[k], R.v, gc->gf[k], cnt_p);
                     for (int c = 0; c < C; ++c) {
                         const float w = gc->w[c * K + k];
                         if (w == 0.f) continue;
@@ -722,7 +715,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArg
                             f1 = fa[(8 + i) * NT + tid];
                         }
                         const float a0[4] = {c0.x, c0.y, c0.z, c0.w}, a1[4] = {c1.x, c1.y, c1.z, c1.w};
-                        const float q0[4] = {f0.x / inv, f0.y / inv, f0.z / inv, f0.w / inv}, q1[4] = {f1.x / inv, f1.y / inv, f1.z / inv, f1.w / inv};
+                        const float q0[4] = {f0.x * inv, f0.y * inv, f0.z * inv, f0.w * inv}, q1[4] = {f1.x * inv, f1.y * inv, f1.z * inv, f1.w * inv};
                         float n0[4], n1[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {

@@ -82,6 +82,30 @@ LNX_HD float growth(float X, const GfConst& g) {
         return X;
     }
 }
+// growth of a whole per-thread vector with the function selected OUTSIDE the (fully unrolled) loop: v stays in registers.
+// poly_quad4 multiplies by the reciprocal of 9 s^2 (as the fused kernel does); the exponential / piecewise-linear
+// functions keep the true divisions of the reference (they are the ones whose rounding showed in the aquarium fixture).
+template <int GF, bool NP, int N>
+LNX_HD void growth_vec(float2* v, const GfConst& g, float& cnt_p) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        cnt_p += (v[j].x > EPS ? 1.f : 0.f) + (v[j].y > EPS ? 1.f : 0.f);  // statistics.py:70
+        v[j].x = growth<GF, NP, GF != GF_POLY_QUAD4>(v[j].x, g);
+        v[j].y = growth<GF, NP, GF != GF_POLY_QUAD4>(v[j].y, g);
+    }
+}
+template <bool NP, int N>
+LNX_HD void growth_vec_dyn(int gf, float2* v, const GfConst& g, float& cnt_p) {
+    switch (gf) {
+        case GF_POLY_QUAD4: growth_vec<GF_POLY_QUAD4, NP, N>(v, g, cnt_p); break;
+        case GF_GAUSSIAN: growth_vec<GF_GAUSSIAN, NP, N>(v, g, cnt_p); break;
+        case GF_GAUSSIAN_TARGET: growth_vec<GF_GAUSSIAN_TARGET, NP, N>(v, g, cnt_p); break;
+        case GF_STEP: growth_vec<GF_STEP, NP, N>(v, g, cnt_p); break;
+        case GF_STAIRCASE: growth_vec<GF_STAIRCASE, NP, N>(v, g, cnt_p); break;
+        case GF_TRIANGLE: growth_vec<GF_TRIANGLE, NP, N>(v, g, cnt_p); break;
+        default: growth_vec<GF_IDENTITY, NP, N>(v, g, cnt_p); break;
+    }
+}
 template <bool NP>
 LNX_HD float growth_dyn(int gf, float X, const GfConst& g) {
     switch (gf) {
