@@ -38,7 +38,8 @@ def parse_args():
     ap.add_argument('--sim-steps', type=int, default=SIM_STEPS)
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--fused-r16', action='store_true', help='A/B: time the 512-thread (R16) fused kernel instead of the default 256-thread one')
+    ap.add_argument('--fused-r16', action='store_true', help='A/B: time the 512-thread (R16) fused kernel instead of the default TMEM kernel')
+    ap.add_argument('--fused-smem', action='store_true', help='A/B: time the shared-memory-state fused kernel (one world per SM) instead of the default TMEM kernel')
     return ap.parse_args()
 
 
@@ -199,8 +200,9 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = leniax_b200.load_library()
-    runner.FUSED_R16 = bool(args.fused_r16)
-    variant_flag = _lib.LNX_RUN_FUSED_R16 if args.fused_r16 else 0
+    runner.FUSED_VARIANT = 'r16' if args.fused_r16 else ('smem' if args.fused_smem else 'tmem')
+    variant_flag = _lib.LNX_RUN_FUSED_R16 if args.fused_r16 else (_lib.LNX_RUN_FUSED_SMEM if args.fused_smem else 0)
+    kernel_name = {'r16': 'lnx_world128_r16', 'smem': 'lnx_world128_fused', 'tmem': 'lnx_world128_tm'}[runner.FUSED_VARIANT]
 
     n_worlds, sim_steps = args.worlds, args.sim_steps
     cfg, worlds_np = make_worlds_numpy(n_worlds, seed=1 + rank)
@@ -310,7 +312,7 @@ def run_b200(args):
                 'workload': f'configs[1]: {n_worlds} Orbium worlds per GPU, 1c1k 128x128 R=13 T=10, {sim_steps} sim steps per bench step, '
                             '12 statistics + stop criteria every step, early stop OFF (Orbium at random toroidal shifts: all worlds survive)',
                 'parallelism': f'worlds sharded over {world} GPU(s), one NCCL all-gather of [worlds,12] per step',
-                'cache': 'state/spectra are shared-memory resident by design; inputs 268 MB per GPU (> 126 MB L2), read once per step',
+                'cache': 'state/spectra are on-chip resident (tensor memory + shared memory) by design; inputs 268 MB per GPU (> 126 MB L2), read once per step',
             },
             'e2e': {'value': e2e_value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': int(host_cells.numel() * 4) * world,
                     'd2h_bytes_per_step': int(block_h.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
@@ -318,7 +320,7 @@ def run_b200(args):
             'clocks': clocks,
             'roofline': {
                 'bound': 'fp32', 'achieved': achieved_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved_tflops / fp32_peak,
-                'traffic': None, 'kernel': 'lnx_world128_r16' if args.fused_r16 else 'lnx_world128_fused', 'kernel_ms': kernel_ms,
+                'traffic': None, 'kernel': kernel_name, 'kernel_ms': kernel_ms,
                 'flop_per_cell_update': FLOP_PER_CELL_UPDATE, 'peak_source': 'measured live: lnx_measure_fp32_peak FMA loop (MEASURED_PEAKS.json has no FP32 entry)',
                 'peak_analytic_tflops': FP32_PEAK_ANALYTIC_TFLOPS, 'frac_of_analytic': achieved_tflops / FP32_PEAK_ANALYTIC_TFLOPS,
                 'hbm_achieved_gbs': stats_bytes / (kernel_ms * 1e-3) / 1e9, 'hbm_peak_gbs': peaks.get('hbm_gbs'),

@@ -257,6 +257,68 @@ LNX_HD void cells_fused(int tid, const float2* pot /* [32] */, float4* A4, const
     part[PT_M00_C0 * NT + tid] = A.sa0 + A.sa1;
 }
 
+// ---- same cell phase for the register-carried state of the TMEM kernel (lnx_world128_tm) -----------------------------
+// The state of the thread lives in a thread-private store of 8 chunks x 8 floats (chunk i = row p, columns 4(4i+e)+l,
+// e = 0..3, then row p+64, same columns); `Store` provides load(i, dst8) / wait_load(dst8) / store(i, src8) (TMEM on the
+// device, a plain array in the emulator).  v[] holds the potential on entry and the NEW state on exit, i.e. exactly what
+// phase 1 of the next step consumes: the state is read once and written once per step and never re-loaded.
+struct ArrayStore {  // host emulator / tests
+    float* base;     // [64] of this thread
+    LNX_HD void load(int i, float* d) const {
+        for (int e = 0; e < 8; ++e) d[e] = base[8 * i + e];
+    }
+    LNX_HD void wait_load(float*) const {}
+    LNX_HD void store(int i, const float* s) const {
+        for (int e = 0; e < 8; ++e) base[8 * i + e] = s[e];
+    }
+};
+template <int GF, int SF, bool NP, class Store>
+LNX_HD void cells_fused_rs(int tid, float2* v /* [32] */, const Store& st, const FusedConsts& K, int shift0, int shift1,
+                           float* part /* [NPART][256] */) {
+    const int l = t_sub(tid) & 3;
+    const float xr0 = rolled_coord(cell_row(tid, 0), shift0), xr1 = rolled_coord(cell_row(tid, 1), shift0);
+    const float cbase = opaque((float)(((l - shift1) & (WS - 1)) - WS / 2));
+    CellAcc A;
+    A.clear();
+    float buf[2][8];
+    st.load(0, buf[0]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float* a = buf[i & 1];
+        st.wait_load(a);
+        if (i + 1 < 8) st.load(i + 1, buf[(i + 1) & 1]);  // in flight while chunk i is processed
+        float n[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * i + e;
+            const float p0 = v[j].x, p1 = v[j].y;
+            A.cnt_p += (p0 > EPS ? 1.f : 0.f) + (p1 > EPS ? 1.f : 0.f);  // statistics.py:70
+            const float f0 = field_fused<GF, NP>(p0, K), f1 = field_fused<GF, NP>(p1, K);
+            acc_cells(A, col_coord(cbase, j), a[e], a[4 + e], f0, f1);
+            if constexpr (SF == SF_V1 && !NP) {
+                n[e] = saturate01(a[e] + K.dt * f0);
+                n[4 + e] = saturate01(a[4 + e] + K.dt * f1);
+            } else {
+                n[e] = state_update<SF, NP>(a[e], f0, K.dt);
+                n[4 + e] = state_update<SF, NP>(a[4 + e], f1, K.dt);
+            }
+            v[j] = make_float2(n[e], n[4 + e]);
+        }
+        st.store(i, n);
+    }
+    part[PT_CNT_A * NT + tid] = A.cnt_a;
+    part[PT_G00 * NT + tid] = A.sg0 + A.sg1;
+    part[PT_CNT_G * NT + tid] = A.cnt_g;
+    part[PT_CNT_P * NT + tid] = A.cnt_p;
+    part[PT_MX_R * NT + tid] = xr0 * A.sa0 + xr1 * A.sa1;
+    part[PT_MX_C * NT + tid] = A.mxc;
+    part[PT_MX2_R * NT + tid] = (xr0 * xr0) * A.sa0 + (xr1 * xr1) * A.sa1;
+    part[PT_MX2_C * NT + tid] = A.mx2c;
+    part[PT_GX_R * NT + tid] = xr0 * A.sg0 + xr1 * A.sg1;
+    part[PT_GX_C * NT + tid] = A.gxc;
+    part[PT_M00_C0 * NT + tid] = A.sa0 + A.sa1;
+}
+
 // ---- per-world statistics carry + stop criteria (owned by lane 0 of the statistics warp) ----
 struct StatsCarry {
     int shift[2];       // total_shift_idx          (runner.py:285-289)

@@ -162,6 +162,79 @@ static void run_fused(const float* cells0, const float* Kt, const float* Kpq, fl
         }
 }
 
+// Same run through the TMEM kernel's data flow (lnx_world128_tm): the state of a thread lives in a private 64-float store
+// (tensor memory on the device), the new state stays in the registers between the cell phase and phase 1.
+template <int GF, int SF, bool NP>
+static void run_fused_rs(const float* cells0, const float* Kt, const float* Kpq, float m, float s, float w, int mean, float T, float R,
+                         float stats_dt, int n_steps, float* stats, float* cm, float* N_out, float* final_cells) {
+    std::vector<Regs> regs(NT);
+    std::vector<float2> W(W_COMPLEX);
+    std::vector<float> store(64 * NT);
+    std::vector<float> part((PT_FIXED + 1) * NT);
+    float2 tw[128];
+    make_tw(tw);
+    std::vector<float4> twtab(TW_TABLE_F4);
+    for (int t = 0; t < NT; ++t) init_twiddle_table(t, twtab.data(), tw);
+    for (int t = 0; t < NT; ++t)
+        for (int i = 0; i < 8; ++i)
+            for (int e = 0; e < 4; ++e) {
+                const float a0 = cells0[cell_row(t, 0) * 128 + cell_col(t, 4 * i + e)], a1 = cells0[cell_row(t, 1) * 128 + cell_col(t, 4 * i + e)];
+                store[64 * t + 8 * i + e] = a0;
+                store[64 * t + 8 * i + 4 + e] = a1;
+                regs[t].v[4 * i + e] = make_float2(a0, a1);
+            }
+    const FusedConsts K = fused_consts(GF, m, s, w, mean, 1.0f / T);
+    StatsCarry S;
+    S.reset();
+    for (int step = 0; step < n_steps; ++step) {
+        const int sh0 = S.shift[0], sh1 = S.shift[1];
+        for (int t = 0; t < NT; ++t) phase1(t, regs[t], W.data());
+        for (int t = 0; t < NT; ++t) phase2_load(t, regs[t], W.data());
+        for (int t = 0; t < NT; ++t) phase2_compute_store(t, regs[t], W.data(), twtab.data());
+        run_phase3(regs, W, Kt, Kpq);
+        for (int t = 0; t < NT; ++t) phase4_load(t, regs[t], W.data());
+        for (int t = 0; t < NT; ++t) phase4_compute_store(t, regs[t], W.data(), twtab.data());
+        for (int t = 0; t < NT; ++t) phase5_load(t, regs[t], W.data());
+        for (int t = 0; t < NT; ++t) {
+            phase5_ifft(regs[t]);
+            const ArrayStore st{store.data() + 64 * t};
+            cells_fused_rs<GF, SF, NP>(t, regs[t].v, st, K, sh0, sh1, part.data());
+        }
+        float totals[PT_FIXED + 1];
+        for (int k = 0; k <= PT_FIXED; ++k) {
+            float lane[32];
+            for (int ln = 0; ln < 32; ++ln) {
+                float a = 0.f;
+                for (int i = 0; i < 8; ++i) a += part[k * NT + ln + 32 * i];
+                lane[ln] = a;
+            }
+            for (int off = 16; off >= 1; off >>= 1)
+                for (int ln = 0; ln < 32; ++ln)
+                    if ((ln & off) == 0) lane[ln] = lane[ln] + lane[ln ^ off];
+            totals[k] = lane[0];
+        }
+        float row[ST_COUNT + MAX_C];
+        stats_finalize(totals, 1, step, 1.0f / (R * R), 1.0f / R, 1.0f / stats_dt, S, row);
+        for (int k = 0; k < ST_COUNT; ++k) stats[k * n_steps + step] = row[k];
+        cm[step] = row[ST_COUNT];
+    }
+    *N_out = S.n_alive;
+    for (int t = 0; t < NT; ++t)
+        for (int i = 0; i < 8; ++i)
+            for (int e = 0; e < 4; ++e) {
+                final_cells[cell_row(t, 0) * 128 + cell_col(t, 4 * i + e)] = store[64 * t + 8 * i + e];
+                final_cells[cell_row(t, 1) * 128 + cell_col(t, 4 * i + e)] = store[64 * t + 8 * i + 4 + e];
+            }
+}
+
+extern "C" {
+int lnx_emul_run_fused_rs(const float* cells0, const float* Kt, const float* Kpq, float m, float s, float w, int mean, float T, float R,
+                          float stats_dt, int n_steps, float* stats, float* cm, float* N_out, float* final_cells) {
+    run_fused_rs<GF_POLY_QUAD4, SF_V1, true>(cells0, Kt, Kpq, m, s, w, mean, T, R, stats_dt, n_steps, stats, cm, N_out, final_cells);
+    return 0;
+}
+}
+
 extern "C" {
 int lnx_emul_run_fused(const float* cells0, const float* Kt, const float* Kpq, int gf, float m, float s, float w, int mean,
                        float T, int sf, float R, float stats_dt, int n_steps, float* stats, float* cm, float* N_out,

@@ -143,12 +143,12 @@ def _orbium_batch(golden_dir, n, seed=0):
     return cfg, ocfg, np.stack(worlds), K, mapping, ufn, sfn
 
 
-@pytest.mark.parametrize('r16', [False, True])
-def test_fused_batch_matches_oracle_and_generic(golden_dir, r16):
-    """run_scan_mem_optimized (fused persistent kernels: the default 256-thread kernel and the 512-thread R16 variant) vs the
-    oracle and vs the generic kernel on the same worlds."""
+@pytest.mark.parametrize('variant', ['tmem', 'smem', 'r16'])
+def test_fused_batch_matches_oracle_and_generic(golden_dir, variant):
+    """run_scan_mem_optimized (fused persistent kernels: the default TMEM kernel, the shared-memory kernel and the 512-thread
+    R16 variant) vs the oracle and vs the generic kernel on the same worlds."""
     steps, n = 160, 12
-    runner.FUSED_R16 = r16
+    runner.FUSED_VARIANT = variant
     cfg, ocfg, worlds, K, mapping, ufn, sfn = _orbium_batch(golden_dir, n)
     gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
     T = torch.tensor([10.], device=DEV)
@@ -156,7 +156,7 @@ def test_fused_batch_matches_oracle_and_generic(golden_dir, r16):
     try:
         mstats, final = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
     finally:
-        runner.FUSED_R16 = False
+        runner.FUSED_VARIANT = 'tmem'
     assert mstats['mass'].shape == (1, steps, n) and mstats['channel_mass'].shape == (1, steps, n, 1)
     assert mstats['N'].shape == (1, n) and final.shape == cells0.shape
     # generic kernel (trajectory requested)
