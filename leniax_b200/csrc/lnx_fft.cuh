@@ -29,12 +29,49 @@ LNX_HDC int bitrev(int x, int bits) {
 }
 LNX_HDC int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
-LNX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-LNX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// a * b
-LNX_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// Complex arithmetic on (re, im) register pairs.  On the device every operation is one of sm_100's packed FP32 instructions
+// (FADD2 / FMUL2 / FFMA2: two lane-operations per issue slot; operand swap, broadcast and per-half negation are free
+// operand modifiers), which halves the instruction count of the butterflies — the kernels are issue- and instruction-fetch
+// bound, not FP32-pipe bound (tools/f32x2_probe.cu).  The host versions (emulator) are the same formulas.
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+#define LNX_PACKED_F32 1
+#else
+#define LNX_PACKED_F32 0  // host pass of the emulator
+#endif
+LNX_HD float2 pk_add(float2 a, float2 b) {
+#if LNX_PACKED_F32
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+LNX_HD float2 pk_mul(float2 a, float2 b) {
+#if LNX_PACKED_F32
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+LNX_HD float2 pk_fma(float2 a, float2 b, float2 c) {
+#if LNX_PACKED_F32
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+LNX_HD float2 pk_bc(float x) { return make_float2(x, x); }            // broadcast (a free operand modifier in SASS)
+LNX_HD float2 pk_swap(float2 a) { return make_float2(a.y, a.x); }     // free modifier
+LNX_HD float2 pk_neg(float2 a) { return make_float2(-a.x, -a.y); }    // free modifier
+
+LNX_HD float2 cadd(float2 a, float2 b) { return pk_add(a, b); }
+LNX_HD float2 csub(float2 a, float2 b) { return pk_add(a, pk_neg(b)); }
+// a * b = a * b.x + (a.y, a.x) * (-b.y, b.y)
+LNX_HD float2 cmul(float2 a, float2 b) { return pk_fma(pk_swap(a), make_float2(-b.y, b.y), pk_mul(a, pk_bc(b.x))); }
 // a * conj(b)
-LNX_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+LNX_HD float2 cmulc(float2 a, float2 b) { return pk_fma(pk_swap(a), make_float2(b.y, -b.y), pk_mul(a, pk_bc(b.x))); }
+// d * (c - i s): (d.x c + d.y s, d.y c - d.x s);  d * (c + i s): (d.x c - d.y s, d.y c + d.x s)
+LNX_HD float2 rot_fwd(float2 d, float c, float s) { return pk_fma(pk_swap(d), make_float2(s, -s), pk_mul(d, pk_bc(c))); }
+LNX_HD float2 rot_inv(float2 d, float c, float s) { return pk_fma(pk_swap(d), make_float2(-s, s), pk_mul(d, pk_bc(c))); }
 
 // d * W_N^E with W_N = exp(-2*pi*i/N) (INV=false) or its conjugate (INV=true); E, N compile-time.
 template <int E, int N, bool INV>
@@ -42,31 +79,27 @@ LNX_HD float2 mul_tw(float2 d) {
     constexpr int e = ((E % N) + N) % N;
     constexpr int idx = e * (128 / N);
     static_assert(128 % N == 0, "N must divide 128");
+    constexpr float h = Tw128::c[16];  // sqrt(1/2)
     if constexpr (e == 0) {
         return d;
     } else if constexpr (4 * e == N) {  // -i (fwd) / +i (inv)
         return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
     } else if constexpr (2 * e == N) {
-        return make_float2(-d.x, -d.y);
+        return pk_neg(d);
     } else if constexpr (4 * e == 3 * N) {  // +i (fwd) / -i (inv)
         return INV ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x);
-    } else if constexpr (8 * e == N) {  // (1 - i)/sqrt2 fwd, (1 + i)/sqrt2 inv
-        constexpr float h = Tw128::c[16];
-        return INV ? make_float2((d.x - d.y) * h, (d.x + d.y) * h) : make_float2((d.x + d.y) * h, (d.y - d.x) * h);
-    } else if constexpr (8 * e == 3 * N) {  // (-1 - i)/sqrt2 fwd, (-1 + i)/sqrt2 inv
-        constexpr float h = Tw128::c[16];
-        return INV ? make_float2(-(d.x + d.y) * h, (d.x - d.y) * h) : make_float2((d.y - d.x) * h, -(d.x + d.y) * h);
-    } else if constexpr (8 * e == 5 * N) {  // (-1 + i)/sqrt2 fwd
-        constexpr float h = Tw128::c[16];
-        return INV ? make_float2((d.y - d.x) * h, -(d.x + d.y) * h) : make_float2(-(d.x + d.y) * h, (d.x - d.y) * h);
-    } else if constexpr (8 * e == 7 * N) {  // (1 + i)/sqrt2 fwd
-        constexpr float h = Tw128::c[16];
-        return INV ? make_float2((d.x + d.y) * h, (d.y - d.x) * h) : make_float2((d.x - d.y) * h, (d.x + d.y) * h);
+    } else if constexpr (8 * e == N) {  // (1 - i)/sqrt2 fwd: (x + y, y - x) h;  (1 + i)/sqrt2 inv: (x - y, x + y) h
+        return pk_mul(pk_add(d, INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x)), pk_bc(h));
+    } else if constexpr (8 * e == 3 * N) {  // (-1 - i)/sqrt2 fwd: (y - x, -(x + y)) h;  (-1 + i)/sqrt2 inv: (-(x + y), x - y) h
+        return pk_mul(pk_add(pk_neg(d), INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x)), pk_bc(h));
+    } else if constexpr (8 * e == 5 * N) {  // (-1 + i)/sqrt2 fwd: (-(x + y), x - y) h;  inv: (y - x, -(x + y)) h
+        return pk_mul(pk_add(pk_neg(d), INV ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x)), pk_bc(h));
+    } else if constexpr (8 * e == 7 * N) {  // (1 + i)/sqrt2 fwd: (x - y, x + y) h;  inv: (x + y, y - x) h
+        return pk_mul(pk_add(d, INV ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x)), pk_bc(h));
     } else {
         constexpr float c = Tw128::c[idx];
         constexpr float s = Tw128::s[idx];
-        // fwd: d * (c - i s); inv: d * (c + i s)
-        return INV ? make_float2(d.x * c - d.y * s, d.y * c + d.x * s) : make_float2(d.x * c + d.y * s, d.y * c - d.x * s);
+        return INV ? rot_inv(d, c, s) : rot_fwd(d, c, s);
     }
 }
 

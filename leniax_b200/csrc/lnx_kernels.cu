@@ -396,7 +396,8 @@ constexpr int TM_OFF_RING = TM_OFF_PART + NPART_FUSED * NT * 4;
 constexpr int TM_OFF_KPQ = TM_OFF_RING + RING_ROWS * RING_STRIDE * 4;
 constexpr int TM_OFF_SCRATCH = TM_OFF_KPQ + KPQ_F4 * 16;
 constexpr int TM_OFF_TW = TM_OFF_SCRATCH + SCRATCH_BYTES;
-constexpr int TM_OFF_CTRL = TM_OFF_TW + TW_BYTES;
+constexpr int TM_OFF_XT = TM_OFF_TW + TW_BYTES;
+constexpr int TM_OFF_CTRL = TM_OFF_XT + XT_F4 * 16;
 struct TmCtrl {
     int world;
     int shift0, shift1;  // total_shift_idx used by the next cell phase (advanced by warp 1)
@@ -423,21 +424,24 @@ __device__ __forceinline__ float tm_reduce_one(const float* part, int k, int lan
     return a;
 }
 // CTA-wide totals of one step -> ring row; warp 1 also advances the shift carry (statistics.py:117-119)
-__device__ __forceinline__ void tm_reduce_partials(const float* part, float* row, TmCtrl* ctrl, int warp, int lane) {
+__device__ __forceinline__ void tm_reduce_partials(const float* part, float* row, TmCtrl* ctrl, float4* xt, int warp, int lane) {
     if (warp == 1) {
         const float m = tm_reduce_one(part, PT_M00_C0, lane), r = tm_reduce_one(part, PT_MX_R, lane), c = tm_reduce_one(part, PT_MX_C, lane);
+        const float m00 = 0.f + m;
+        const float im = sdiv(1.0f, m00 + EPS);
+        const float c0 = r * im, c1 = c * im;
+        const int shift1 = (ctrl->shift1 + trunc_to_int(c1)) & (WS - 1);  // every lane computes the same value
+        __syncwarp();
         if (lane == 0) {
-            const float m00 = 0.f + m;
-            const float im = sdiv(1.0f, m00 + EPS);
-            const float c0 = r * im, c1 = c * im;
             row[PT_M00_C0] = m;
             row[PT_MX_R] = r;
             row[PT_MX_C] = c;
             row[RING_C0] = c0;
             row[RING_C1] = c1;
             ctrl->shift0 = (ctrl->shift0 + trunc_to_int(c0)) & (WS - 1);
-            ctrl->shift1 = (ctrl->shift1 + trunc_to_int(c1)) & (WS - 1);
+            ctrl->shift1 = shift1;
         }
+        xt_build(lane, shift1, xt);  // column coordinates of the next cell phase
     } else if (warp >= 2) {
         // CNT_A, G00, CNT_G, CNT_P, GX_R, GX_C on warps 2..7; MX2_R, MX2_C as second item of warps 2, 3
         const int ka = warp < 6 ? warp - 2 : warp + 2;
@@ -472,6 +476,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
     float4* Kpq = reinterpret_cast<float4*>(smem + TM_OFF_KPQ);
     float2* scratch = reinterpret_cast<float2*>(smem + TM_OFF_SCRATCH);
     float4* twtab = reinterpret_cast<float4*>(smem + TM_OFF_TW);
+    float4* xt = reinterpret_cast<float4*>(smem + TM_OFF_XT);
     TmCtrl* ctrl = reinterpret_cast<TmCtrl*>(smem + TM_OFF_CTRL);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -511,9 +516,9 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
                 float n[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    n[e] = __ldg(r0 + 16 * i + 4 * e);
-                    n[4 + e] = __ldg(r1 + 16 * i + 4 * e);
-                    R.v[4 * i + e] = make_float2(n[e], n[4 + e]);
+                    n[2 * e] = __ldg(r0 + 16 * i + 4 * e);
+                    n[2 * e + 1] = __ldg(r1 + 16 * i + 4 * e);
+                    R.v[4 * i + e] = make_float2(n[2 * e], n[2 * e + 1]);
                 }
                 st.store(i, n);
             }
@@ -526,6 +531,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
             loaded_sol = sol;
         }
         tm::wait_st();
+        if (warp == 1) xt_build(lane, 0, xt);  // coordinates for step 0 (made visible by the barriers of step 0)
         const FusedConsts fc = fused_consts(GF, __ldg(P.gf_params + (size_t)sol * 2), __ldg(P.gf_params + (size_t)sol * 2 + 1),
                                             __ldg(P.weights + sol), P.mean, __ldg(P.dt + sol));
         const size_t idx_world = (size_t)sol * P.max_iter * P.n_init + init;  // statistics index of step 0
@@ -541,7 +547,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
             __syncthreads();
             if (t > 0) {
                 if (ctrl->stop) break;  // written by warp 7 before this barrier, next written after the following one
-                tm_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * RING_STRIDE, ctrl, warp, lane);
+                tm_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * RING_STRIDE, ctrl, xt, warp, lane);
             }
             float kbuf[2][8];
             tm::ld8(kt_addr, kbuf[0]);  // first multiplier chunk: lands during the column transforms
@@ -573,12 +579,12 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
             phase5_load(tid, R, W);
             phase5_ifft(R);
             tm::wait_st();  // the previous step's state stores (long complete by now)
-            cells_fused_rs<GF, SF, NP>(tid, R.v, st, fc, ctrl->shift0, ctrl->shift1, part);
+            cells_fused_rs<GF, SF, NP>(tid, R.v, st, fc, ctrl->shift0, xt, part);
         }
         // the partial sums of the last completed cell phase (step t-1) are not reduced yet; t >= 1 here
         tm::wait_st();
         __syncthreads();
-        tm_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * RING_STRIDE, ctrl, warp, lane);
+        tm_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * RING_STRIDE, ctrl, xt, warp, lane);
         __syncthreads();
         if (warp == 7) {  // flush the pending rows S.rows .. t-1 (1..32 of them)
             BatchCarry S = ctrl->carry;
@@ -597,8 +603,8 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
                 st.wait_load(n);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    r0[16 * i + 4 * e] = n[e];
-                    r1[16 * i + 4 * e] = n[4 + e];
+                    r0[16 * i + 4 * e] = n[2 * e];
+                    r1[16 * i + 4 * e] = n[2 * e + 1];
                 }
             }
         }

@@ -257,11 +257,14 @@ LNX_HD void cells_fused(int tid, const float2* pot /* [32] */, float4* A4, const
     part[PT_M00_C0 * NT + tid] = A.sa0 + A.sa1;
 }
 
-// ---- same cell phase for the register-carried state of the TMEM kernel (lnx_world128_tm) -----------------------------
-// The state of the thread lives in a thread-private store of 8 chunks x 8 floats (chunk i = row p, columns 4(4i+e)+l,
-// e = 0..3, then row p+64, same columns); `Store` provides load(i, dst8) / wait_load(dst8) / store(i, src8) (TMEM on the
-// device, a plain array in the emulator).  v[] holds the potential on entry and the NEW state on exit, i.e. exactly what
-// phase 1 of the next step consumes: the state is read once and written once per step and never re-loaded.
+// ---- cell phase of the TMEM kernel (lnx_world128_tm): packed over the thread's two rows ---------------------------------
+// The state of the thread lives in a thread-private store of 8 chunks x 8 floats; chunk i holds columns 4(4i+e)+l, e = 0..3,
+// as (row p, row p+64) pairs, i.e. exactly the (re, im) register pairs phase 1 consumes.  `Store` provides load(i, dst8) /
+// wait_load(dst8) / store(i, src8) (TMEM on the device, a plain array in the emulator).  v[] holds the potential on entry
+// and the NEW state on exit: the state is read once and written once per step and never re-loaded.
+// All per-cell arithmetic runs on the (row p, row p+64) pairs with the packed FP32 instructions; the column coordinate of
+// the rolled frame (utils.py:269-293 folded into statistics.py:28-33) and its square come from a 1 KB table rebuilt once
+// per step by the warp that advances the shift carry, instead of three instructions per column in every thread.
 struct ArrayStore {  // host emulator / tests
     float* base;     // [64] of this thread
     LNX_HD void load(int i, float* d) const {
@@ -272,14 +275,44 @@ struct ArrayStore {  // host emulator / tests
         for (int e = 0; e < 8; ++e) base[8 * i + e] = s[e];
     }
 };
+// coordinate table: float4 xt[2][4][XT_STRIDE]: xt[0][l][i] = xc of columns 4(4i+e)+l, e = 0..3; xt[1] = their squares.
+// XT_STRIDE = 9 float4 keeps the four l rows of a warp-wide 128-bit read in different banks.
+constexpr int XT_STRIDE = 9;
+constexpr int XT_F4 = 2 * 4 * XT_STRIDE;
+LNX_HD float xt_coord(int l, int j, int shift1) { return (float)(((4 * j + l - shift1) & (WS - 1)) - WS / 2); }
+// entries 4*idx .. 4*idx+3 of the table (idx = 0..31 <-> l = idx >> 3, i = idx & 7): one lane of the building warp
+LNX_HD void xt_build(int idx, int shift1, float4* xt) {
+    const int l = idx >> 3, i = idx & 7;
+    const float x0 = xt_coord(l, 4 * i, shift1), x1 = xt_coord(l, 4 * i + 1, shift1), x2 = xt_coord(l, 4 * i + 2, shift1),
+                x3 = xt_coord(l, 4 * i + 3, shift1);
+    xt[l * XT_STRIDE + i] = make_float4(x0, x1, x2, x3);
+    xt[(4 + l) * XT_STRIDE + i] = make_float4(x0 * x0, x1 * x1, x2 * x2, x3 * x3);
+}
+// (x > thr, y > thr) as a pair of 1.0f / 0.0f: two FSET.BF, accumulated by one FADD2 (float counts are exact up to 2^24)
+LNX_HD float2 gt_flags(float2 p, float thr) { return make_float2(p.x > thr ? 1.f : 0.f, p.y > thr ? 1.f : 0.f); }
+// c * growth(X) on a pair; poly_quad4 folds the affine tail and the weight into one FMA (as field_fused)
+template <int GF, bool NP>
+LNX_HD float2 field_fused_pk(float2 X, const FusedConsts& K) {
+    if constexpr (GF == GF_POLY_QUAD4) {
+        const float2 t = pk_add(X, pk_bc(-K.gf.m));
+        float2 o = pk_fma(pk_mul(t, t), pk_bc(-K.gf.k0), pk_bc(1.0f));
+        if constexpr (NP)
+            o = make_float2((o.x < 0.f) ? 0.f : o.x, (o.y < 0.f) ? 0.f : o.y);
+        else
+            o = make_float2(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f));
+        const float2 o2 = pk_mul(o, o);
+        return pk_fma(pk_mul(o2, o2), pk_bc(K.c2), pk_bc(-K.c));
+    } else {
+        return make_float2(K.c * growth<GF, NP>(X.x, K.gf), K.c * growth<GF, NP>(X.y, K.gf));
+    }
+}
 template <int GF, int SF, bool NP, class Store>
-LNX_HD void cells_fused_rs(int tid, float2* v /* [32] */, const Store& st, const FusedConsts& K, int shift0, int shift1,
+LNX_HD void cells_fused_rs(int tid, float2* v /* [32] */, const Store& st, const FusedConsts& K, int shift0, const float4* xt,
                            float* part /* [NPART][256] */) {
     const int l = t_sub(tid) & 3;
     const float xr0 = rolled_coord(cell_row(tid, 0), shift0), xr1 = rolled_coord(cell_row(tid, 1), shift0);
-    const float cbase = opaque((float)(((l - shift1) & (WS - 1)) - WS / 2));
-    CellAcc A;
-    A.clear();
+    float2 sa = make_float2(0.f, 0.f), sg = sa, mx = sa, mx2 = sa, gx = sa;  // per-row sums: cells, positive field, moments
+    float2 cnt_a = sa, cnt_g = sa, cnt_p = sa;
     float buf[2][8];
     st.load(0, buf[0]);
 #pragma unroll
@@ -287,36 +320,46 @@ LNX_HD void cells_fused_rs(int tid, float2* v /* [32] */, const Store& st, const
         float* a = buf[i & 1];
         st.wait_load(a);
         if (i + 1 < 8) st.load(i + 1, buf[(i + 1) & 1]);  // in flight while chunk i is processed
+        const float4 x4 = xt[l * XT_STRIDE + i], q4 = xt[(4 + l) * XT_STRIDE + i];
+        const float xc[4] = {x4.x, x4.y, x4.z, x4.w}, xc2[4] = {q4.x, q4.y, q4.z, q4.w};
         float n[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int j = 4 * i + e;
-            const float p0 = v[j].x, p1 = v[j].y;
-            A.cnt_p += (p0 > EPS ? 1.f : 0.f) + (p1 > EPS ? 1.f : 0.f);  // statistics.py:70
-            const float f0 = field_fused<GF, NP>(p0, K), f1 = field_fused<GF, NP>(p1, K);
-            acc_cells(A, col_coord(cbase, j), a[e], a[4 + e], f0, f1);
-            if constexpr (SF == SF_V1 && !NP) {
-                n[e] = saturate01(a[e] + K.dt * f0);
-                n[4 + e] = saturate01(a[4 + e] + K.dt * f1);
+            const float2 A = make_float2(a[2 * e], a[2 * e + 1]), P = v[j];
+            cnt_p = pk_add(cnt_p, gt_flags(P, EPS));  // statistics.py:70
+            const float2 F = field_fused_pk<GF, NP>(P, K);
+            sa = pk_add(sa, A);
+            mx = pk_fma(A, pk_bc(xc[e]), mx);
+            mx2 = pk_fma(A, pk_bc(xc2[e]), mx2);
+            cnt_a = pk_add(cnt_a, gt_flags(A, EPS));
+            const float2 G = make_float2(fmaxf(F.x, 0.f), fmaxf(F.y, 0.f));  // statistics.py:65
+            sg = pk_add(sg, G);
+            gx = pk_fma(G, pk_bc(xc[e]), gx);
+            cnt_g = pk_add(cnt_g, gt_flags(F, EPS));  // max(f, 0) > eps <=> f > eps
+            float2 N;
+            if constexpr (SF == SF_V1 && !NP) {  // clip(a + dt f, 0, 1) as one saturating FMA (no NaN possible here)
+                N = make_float2(saturate01(A.x + K.dt * F.x), saturate01(A.y + K.dt * F.y));
             } else {
-                n[e] = state_update<SF, NP>(a[e], f0, K.dt);
-                n[4 + e] = state_update<SF, NP>(a[4 + e], f1, K.dt);
+                N = make_float2(state_update<SF, NP>(A.x, F.x, K.dt), state_update<SF, NP>(A.y, F.y, K.dt));
             }
-            v[j] = make_float2(n[e], n[4 + e]);
+            v[j] = N;
+            n[2 * e] = N.x;
+            n[2 * e + 1] = N.y;
         }
         st.store(i, n);
     }
-    part[PT_CNT_A * NT + tid] = A.cnt_a;
-    part[PT_G00 * NT + tid] = A.sg0 + A.sg1;
-    part[PT_CNT_G * NT + tid] = A.cnt_g;
-    part[PT_CNT_P * NT + tid] = A.cnt_p;
-    part[PT_MX_R * NT + tid] = xr0 * A.sa0 + xr1 * A.sa1;
-    part[PT_MX_C * NT + tid] = A.mxc;
-    part[PT_MX2_R * NT + tid] = (xr0 * xr0) * A.sa0 + (xr1 * xr1) * A.sa1;
-    part[PT_MX2_C * NT + tid] = A.mx2c;
-    part[PT_GX_R * NT + tid] = xr0 * A.sg0 + xr1 * A.sg1;
-    part[PT_GX_C * NT + tid] = A.gxc;
-    part[PT_M00_C0 * NT + tid] = A.sa0 + A.sa1;
+    part[PT_CNT_A * NT + tid] = cnt_a.x + cnt_a.y;
+    part[PT_G00 * NT + tid] = sg.x + sg.y;
+    part[PT_CNT_G * NT + tid] = cnt_g.x + cnt_g.y;
+    part[PT_CNT_P * NT + tid] = cnt_p.x + cnt_p.y;
+    part[PT_MX_R * NT + tid] = xr0 * sa.x + xr1 * sa.y;
+    part[PT_MX_C * NT + tid] = mx.x + mx.y;
+    part[PT_MX2_R * NT + tid] = (xr0 * xr0) * sa.x + (xr1 * xr1) * sa.y;
+    part[PT_MX2_C * NT + tid] = mx2.x + mx2.y;
+    part[PT_GX_R * NT + tid] = xr0 * sg.x + xr1 * sg.y;
+    part[PT_GX_C * NT + tid] = gx.x + gx.y;
+    part[PT_M00_C0 * NT + tid] = sa.x + sa.y;
 }
 
 // ---- per-world statistics carry + stop criteria (owned by lane 0 of the statistics warp) ----

@@ -145,8 +145,8 @@ LNX_HD void load_twiddles(int u, Twiddles& T, const float4* table) {
         if (i < 3) T.col[2 * i + 1] = make_float2(t.z, t.w);
     }
 }
-LNX_HD float2 tw_fwd(float2 d, float2 tw) { return make_float2(d.x * tw.x + d.y * tw.y, d.y * tw.x - d.x * tw.y); }
-LNX_HD float2 tw_inv(float2 d, float2 tw) { return make_float2(d.x * tw.x - d.y * tw.y, d.y * tw.x + d.x * tw.y); }
+LNX_HD float2 tw_fwd(float2 d, float2 tw) { return rot_fwd(d, tw.x, tw.y); }
+LNX_HD float2 tw_inv(float2 d, float2 tw) { return rot_inv(d, tw.x, tw.y); }
 
 // =====================================================================================================================
 // P1': x[32] (real, natural j) -> Y_l[k1] stored in E1'

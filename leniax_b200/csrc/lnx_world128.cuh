@@ -94,8 +94,8 @@ LNX_HD void load_twiddles(int tid, Twiddles& T, const float4* table) {
     }
 }
 // multiply by W = (c, -s) (forward) or conj (inverse), tw = (c, s)
-LNX_HD float2 tw_fwd(float2 d, float2 tw) { return make_float2(d.x * tw.x + d.y * tw.y, d.y * tw.x - d.x * tw.y); }
-LNX_HD float2 tw_inv(float2 d, float2 tw) { return make_float2(d.x * tw.x - d.y * tw.y, d.y * tw.x + d.x * tw.y); }
+LNX_HD float2 tw_fwd(float2 d, float2 tw) { return rot_fwd(d, tw.x, tw.y); }
+LNX_HD float2 tw_inv(float2 d, float2 tw) { return rot_inv(d, tw.x, tw.y); }
 
 // =================================================================================================================
 // P1: v[j] = (a[p][4j+l], a[p+64][4j+l]) already loaded by the caller.  radix-32 DIF, store E1.
@@ -135,13 +135,13 @@ LNX_HD void phase2_load(int tid, Regs& R, const float2* W) {
 
 // untangle one (Z[k], Z[128-k]) pair of a packed row into the spectra of its two real rows (factor 2 kept)
 LNX_HD void untangle_pair(float2 z, float2 zc, float2& A2, float2& B2) {
-    A2 = make_float2(z.x + zc.x, z.y - zc.y);
-    B2 = make_float2(z.y + zc.y, zc.x - z.x);
+    A2 = pk_add(z, make_float2(zc.x, -zc.y));
+    B2 = pk_add(make_float2(z.y, -z.x), pk_swap(zc));
 }
 // inverse of the above: from the spectra A', B' of two real rows rebuild Z'[k] and Z'[128-k]
 LNX_HD void retangle_pair(float2 A, float2 B, float2& z, float2& zc) {
-    z = make_float2(A.x - B.y, A.y + B.x);
-    zc = make_float2(A.x + B.y, B.x - A.y);
+    z = pk_add(A, make_float2(-B.y, B.x));
+    zc = pk_add(make_float2(A.x, -A.y), pk_swap(B));
 }
 
 template <bool A0>

@@ -179,8 +179,8 @@ static void run_fused_rs(const float* cells0, const float* Kt, const float* Kpq,
         for (int i = 0; i < 8; ++i)
             for (int e = 0; e < 4; ++e) {
                 const float a0 = cells0[cell_row(t, 0) * 128 + cell_col(t, 4 * i + e)], a1 = cells0[cell_row(t, 1) * 128 + cell_col(t, 4 * i + e)];
-                store[64 * t + 8 * i + e] = a0;
-                store[64 * t + 8 * i + 4 + e] = a1;
+                store[64 * t + 8 * i + 2 * e] = a0;
+                store[64 * t + 8 * i + 2 * e + 1] = a1;
                 regs[t].v[4 * i + e] = make_float2(a0, a1);
             }
     const FusedConsts K = fused_consts(GF, m, s, w, mean, 1.0f / T);
@@ -188,6 +188,8 @@ static void run_fused_rs(const float* cells0, const float* Kt, const float* Kpq,
     S.reset();
     for (int step = 0; step < n_steps; ++step) {
         const int sh0 = S.shift[0], sh1 = S.shift[1];
+        std::vector<float4> xt(XT_F4);
+        for (int idx = 0; idx < 32; ++idx) xt_build(idx, sh1, xt.data());
         for (int t = 0; t < NT; ++t) phase1(t, regs[t], W.data());
         for (int t = 0; t < NT; ++t) phase2_load(t, regs[t], W.data());
         for (int t = 0; t < NT; ++t) phase2_compute_store(t, regs[t], W.data(), twtab.data());
@@ -198,7 +200,7 @@ static void run_fused_rs(const float* cells0, const float* Kt, const float* Kpq,
         for (int t = 0; t < NT; ++t) {
             phase5_ifft(regs[t]);
             const ArrayStore st{store.data() + 64 * t};
-            cells_fused_rs<GF, SF, NP>(t, regs[t].v, st, K, sh0, sh1, part.data());
+            cells_fused_rs<GF, SF, NP>(t, regs[t].v, st, K, sh0, xt.data(), part.data());
         }
         float totals[PT_FIXED + 1];
         for (int k = 0; k <= PT_FIXED; ++k) {
@@ -222,8 +224,8 @@ static void run_fused_rs(const float* cells0, const float* Kt, const float* Kpq,
     for (int t = 0; t < NT; ++t)
         for (int i = 0; i < 8; ++i)
             for (int e = 0; e < 4; ++e) {
-                final_cells[cell_row(t, 0) * 128 + cell_col(t, 4 * i + e)] = store[64 * t + 8 * i + e];
-                final_cells[cell_row(t, 1) * 128 + cell_col(t, 4 * i + e)] = store[64 * t + 8 * i + 4 + e];
+                final_cells[cell_row(t, 0) * 128 + cell_col(t, 4 * i + e)] = store[64 * t + 8 * i + 2 * e];
+                final_cells[cell_row(t, 1) * 128 + cell_col(t, 4 * i + e)] = store[64 * t + 8 * i + 2 * e + 1];
             }
 }
 

@@ -83,21 +83,27 @@ def test_orbium_trajectory_stats_and_golden(emul, golden_dir):
     assert np.abs(fin127 - oc[-1, 0, 0]).max() < 5e-5
 
 
-def test_register_carried_state_flow_is_bit_identical(emul, golden_dir):
+def test_register_carried_state_flow_matches_smem_flow_and_oracle(emul, golden_dir):
     """The TMEM kernel's cell phase (state chunks in a thread-private store, new state carried in registers into the next
-    phase 1) must reproduce the shared-memory kernel's data flow bit for bit."""
+    phase 1, arithmetic packed over the thread's two rows, coordinate table) against the shared-memory kernel's cell phase
+    and the oracle."""
     cfg = lo.load_yaml_config(os.path.join(golden_dir, 'orbium-test.yaml'))
     cells, K, _ = lo.init(cfg)
-    n = 40
+    n = 64
     stats, cm, N, fin = _run_fused(emul, cells[0, 0], K[0, 0, 0], 0, .15, .015, 1., 1, 10., 0, 13., n)
     Kt, Kpq = build_tables(emul, K[0, 0, 0])
     stats2, cm2, N2, fin2 = np.zeros((11, n), np.float32), np.zeros(n, np.float32), np.zeros(1, np.float32), np.zeros((128, 128), np.float32)
     f = ctypes.c_float
     emul.lnx_emul_run_fused_rs(P(np.ascontiguousarray(cells[0, 0])), P(Kt), P(Kpq), f(.15), f(.015), f(1.), 1, f(10.), f(13.), f(.1), n,
                                P(stats2), P(cm2), P(N2), P(fin2))
-    np.testing.assert_array_equal(fin, fin2)
-    np.testing.assert_array_equal(stats, stats2)
-    assert N == float(N2[0])
+    assert np.abs(fin - fin2).max() < 2e-5  # same physics; rounding differs (fused multiply-adds), amplified over 64 steps
+    cfg['run_params']['max_run_iter'] = n
+    ostats = lo.init_and_run(cfg, with_jit=True)[3]
+    tol = dict(zip(KEYS, [2e-6, 3e-7, 2e-6, 5e-6, 3e-7, 1e-5, 5e-5, 0.05, 2e-5, 5e-6, 0.05]))
+    for i, k in enumerate(KEYS):
+        assert np.abs(stats2[i] - ostats[k][:, 0]).max() <= tol[k], k
+    np.testing.assert_array_equal(stats[1], stats2[1])  # counts (mass_volume) are exact in both
+    assert N == float(N2[0]) == float(n)
 
 
 def test_dying_world_stops_like_check_heuristics(emul, golden_dir):
