@@ -4,6 +4,7 @@
 // Reference: leniax/growth_functions.py:6-253, leniax/core.py:202-319 (weighted mean/sum, get_state*),
 // leniax/statistics.py:36-126 (compute_stats), :134-205 + :287-333 (check_heuristics), leniax/utils.py:269-293.
 #pragma once
+#include <cstring>
 #include "lnx_world128.cuh"
 
 namespace lnx {
@@ -265,6 +266,15 @@ LNX_HD void cells_fused(int tid, const float2* pot /* [32] */, float4* A4, const
 // All per-cell arithmetic runs on the (row p, row p+64) pairs with the packed FP32 instructions; the column coordinate of
 // the rolled frame (utils.py:269-293 folded into statistics.py:28-33) and its square come from a 1 KB table rebuilt once
 // per step by the warp that advances the shift carry, instead of three instructions per column in every thread.
+LNX_HD int __float_as_int_hd(float x) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(x);
+#else
+    int r;
+    memcpy(&r, &x, 4);
+    return r;
+#endif
+}
 struct ArrayStore {  // host emulator / tests
     float* base;     // [64] of this thread
     LNX_HD void load(int i, float* d) const {
@@ -288,8 +298,11 @@ LNX_HD void xt_build(int idx, int shift1, float4* xt) {
     xt[l * XT_STRIDE + i] = make_float4(x0, x1, x2, x3);
     xt[(4 + l) * XT_STRIDE + i] = make_float4(x0 * x0, x1 * x1, x2 * x2, x3 * x3);
 }
-// (x > thr, y > thr) as a pair of 1.0f / 0.0f: two FSET.BF, accumulated by one FADD2 (float counts are exact up to 2^24)
-LNX_HD float2 gt_flags(float2 p, float thr) { return make_float2(p.x > thr ? 1.f : 0.f, p.y > thr ? 1.f : 0.f); }
+// Threshold counts on the integer/ALU pipe (the FP32 pipe is the busy one): x > thr gives the bit pattern of 1.0f
+// (FSET.BF), and bit patterns are summed three at a time by IADD3.  1.0f = 127 * 2^23, so after n <= 511 hits the sum is
+// ((127 n) mod 512) * 2^23 (mod 2^32) and n = (383 * (sum >> 23)) mod 512 because 127 * 383 = 1 (mod 512).
+LNX_HD int gt_bits(float x, float thr) { return __float_as_int_hd(x > thr ? 1.0f : 0.0f); }
+LNX_HD float count_from_bits(int sum) { return (float)((383 * (int)((unsigned)sum >> 23)) & 511); }
 // c * growth(X) on a pair; poly_quad4 folds the affine tail and the weight into one FMA (as field_fused)
 template <int GF, bool NP>
 LNX_HD float2 field_fused_pk(float2 X, const FusedConsts& K) {
@@ -312,7 +325,7 @@ LNX_HD void cells_fused_rs(int tid, float2* v /* [32] */, const Store& st, const
     const int l = t_sub(tid) & 3;
     const float xr0 = rolled_coord(cell_row(tid, 0), shift0), xr1 = rolled_coord(cell_row(tid, 1), shift0);
     float2 sa = make_float2(0.f, 0.f), sg = sa, mx = sa, mx2 = sa, gx = sa;  // per-row sums: cells, positive field, moments
-    float2 cnt_a = sa, cnt_g = sa, cnt_p = sa;
+    int cnt_a = 0, cnt_g = 0, cnt_p = 0;  // at most 64 hits each per step
     float buf[2][8];
     st.load(0, buf[0]);
 #pragma unroll
@@ -327,16 +340,16 @@ LNX_HD void cells_fused_rs(int tid, float2* v /* [32] */, const Store& st, const
         for (int e = 0; e < 4; ++e) {
             const int j = 4 * i + e;
             const float2 A = make_float2(a[2 * e], a[2 * e + 1]), P = v[j];
-            cnt_p = pk_add(cnt_p, gt_flags(P, EPS));  // statistics.py:70
+            cnt_p += gt_bits(P.x, EPS) + gt_bits(P.y, EPS);  // statistics.py:70
             const float2 F = field_fused_pk<GF, NP>(P, K);
             sa = pk_add(sa, A);
             mx = pk_fma(A, pk_bc(xc[e]), mx);
             mx2 = pk_fma(A, pk_bc(xc2[e]), mx2);
-            cnt_a = pk_add(cnt_a, gt_flags(A, EPS));
+            cnt_a += gt_bits(A.x, EPS) + gt_bits(A.y, EPS);
             const float2 G = make_float2(fmaxf(F.x, 0.f), fmaxf(F.y, 0.f));  // statistics.py:65
             sg = pk_add(sg, G);
             gx = pk_fma(G, pk_bc(xc[e]), gx);
-            cnt_g = pk_add(cnt_g, gt_flags(F, EPS));  // max(f, 0) > eps <=> f > eps
+            cnt_g += gt_bits(F.x, EPS) + gt_bits(F.y, EPS);  // max(f, 0) > eps <=> f > eps
             float2 N;
             if constexpr (SF == SF_V1 && !NP) {  // clip(a + dt f, 0, 1) as one saturating FMA (no NaN possible here)
                 N = make_float2(saturate01(A.x + K.dt * F.x), saturate01(A.y + K.dt * F.y));
@@ -349,10 +362,10 @@ LNX_HD void cells_fused_rs(int tid, float2* v /* [32] */, const Store& st, const
         }
         st.store(i, n);
     }
-    part[PT_CNT_A * NT + tid] = cnt_a.x + cnt_a.y;
+    part[PT_CNT_A * NT + tid] = count_from_bits(cnt_a);
     part[PT_G00 * NT + tid] = sg.x + sg.y;
-    part[PT_CNT_G * NT + tid] = cnt_g.x + cnt_g.y;
-    part[PT_CNT_P * NT + tid] = cnt_p.x + cnt_p.y;
+    part[PT_CNT_G * NT + tid] = count_from_bits(cnt_g);
+    part[PT_CNT_P * NT + tid] = count_from_bits(cnt_p);
     part[PT_MX_R * NT + tid] = xr0 * sa.x + xr1 * sa.y;
     part[PT_MX_C * NT + tid] = mx.x + mx.y;
     part[PT_MX2_R * NT + tid] = (xr0 * xr0) * sa.x + (xr1 * xr1) * sa.y;
