@@ -14,17 +14,22 @@
 namespace lnx {
 
 constexpr int RING_ROWS = 32;
-constexpr int RING_STRIDE = 16;  // floats per row: totals[PT_*] (11), c0, c1, pad
-constexpr int RING_C0 = 11, RING_C1 = 12;
+// ring row: the ten channel-independent totals (PT_CNT_A .. PT_GX_C), c0, c1 (mass centroid), then one mass sum per channel
+constexpr int RING_C0 = PT_FIXED, RING_C1 = PT_FIXED + 1, RING_M00 = PT_FIXED + 2;
+constexpr int RING_STRIDE_1 = 16;   // floats per row, single-channel kernel
+constexpr int RING_STRIDE_C = 24;   // floats per row, up to MAX_C channels (12 + 8 = 20, padded to a multiple of 4)
 
 struct BatchCarry {  // warp-uniform: every lane of the finalising warp holds the same copy
     float cc0, cc1;  // mass_centroid carry = c - trunc(c) of the last finalised step (statistics.py:124)
     float angle;     // mass_angle carry
-    float prev_mass, prev_sign, init_cm, should_continue, n_alive;
+    float prev_mass, prev_sign, should_continue, n_alive;
+    float init_cm[MAX_C];
     int mono, vol;
     int rows;        // rows finalised so far (== index of the next step to finalise)
     __device__ __forceinline__ void reset() {
-        cc0 = cc1 = angle = prev_mass = prev_sign = init_cm = n_alive = 0.f;
+        cc0 = cc1 = angle = prev_mass = prev_sign = n_alive = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAX_C; ++c) init_cm[c] = 0.f;
         should_continue = 1.f;
         mono = vol = rows = 0;
     }
@@ -36,20 +41,21 @@ __device__ __forceinline__ int scan_counter(unsigned reset_mask, int lane, int c
     return upto ? lane - (31 - __clz(upto)) + 1 : carry + lane + 1;
 }
 
-// ring: float [32][16] in shared memory, rows tb .. tb + n - 1 (tb is a multiple of 32, so ring row == lane).
-// Writes the statistics rows to HBM and advances the carry.  Single channel (the fused path).
-__device__ __forceinline__ void stats_finalize_batch(const float* ring, int n, int lane, float* __restrict__ stats, float* __restrict__ channel_mass,
-                                                     size_t plane, size_t idx0 /* index of step tb */, size_t t_stride, float invR2,
-                                                     float invR, float inv_dt, BatchCarry& S) {
+// ring: float [32][STRIDE] in shared memory, rows tb .. tb + n - 1 (tb is a multiple of 32, so ring row == lane).
+// Writes the statistics rows to HBM and advances the carry.  C = number of channels (compile-time bound CMAX).
+template <int CMAX, int STRIDE>
+__device__ __forceinline__ void stats_finalize_batch(const float* ring, int n, int lane, int C, float* __restrict__ stats,
+                                                     float* __restrict__ channel_mass, size_t plane, size_t idx0 /* index of step tb */,
+                                                     size_t t_stride, float invR2, float invR, float inv_dt, BatchCarry& S) {
     const unsigned FULL = 0xffffffffu;
     const bool valid = lane < n;
     const unsigned vmask = n >= 32 ? FULL : ((1u << n) - 1u);
     const int tb = S.rows;
-    float tot[RING_STRIDE];
+    float tot[STRIDE];
     {
-        const float4* rp = reinterpret_cast<const float4*>(ring + lane * RING_STRIDE);
+        const float4* rp = reinterpret_cast<const float4*>(ring + lane * STRIDE);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < STRIDE / 4; ++q) {
             const float4 r = rp[q];
             tot[4 * q] = r.x;
             tot[4 * q + 1] = r.y;
@@ -57,8 +63,15 @@ __device__ __forceinline__ void stats_finalize_batch(const float* ring, int n, i
             tot[4 * q + 3] = r.w;
         }
     }
-    const float m00 = 0.f + tot[PT_M00_C0];
-    const float cm = tot[PT_M00_C0] * invR2;
+    float m00 = 0.f, cm[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        cm[c] = 0.f;
+        if (c < C) {
+            m00 += tot[RING_M00 + c];
+            cm[c] = tot[RING_M00 + c] * invR2;
+        }
+    }
     const float g00 = tot[PT_G00];
     const float mass = m00 * invR2;
     const float mass_volume = tot[PT_CNT_A] * invR2;
@@ -90,10 +103,17 @@ __device__ __forceinline__ void stats_finalize_batch(const float* ring, int n, i
     const float sign = (dm > 0.f) ? 1.f : ((dm < 0.f) ? -1.f : dm);  // jnp.sign: 0 -> 0, NaN -> NaN
     float psign = __shfl_up_sync(FULL, sign, 1);
     if (lane == 0) psign = (tb == 0) ? 0.f : S.prev_sign;
-    const float init_cm = (tb == 0) ? __shfl_sync(FULL, cm, 0) : S.init_cm;
     const int mono = scan_counter(__ballot_sync(FULL, !(sign == psign)) & vmask, lane, S.mono);
     const int vol = scan_counter(__ballot_sync(FULL, !(mass_volume > 10.f)) & vmask, lane, S.vol);
-    const bool cond = (cm >= EPS) && (cm <= 3.f * init_cm) && (mono <= 128) && (vol <= 128);
+    bool cond = (mono <= 128) && (vol <= 128);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+            const float first = __shfl_sync(FULL, cm[c], 0);
+            if (tb == 0) S.init_cm[c] = first;
+            cond = cond && (cm[c] >= EPS) && (cm[c] <= 3.f * S.init_cm[c]);
+        }
+    }
     const unsigned failed = __ballot_sync(FULL, !cond) & vmask;
     const int first_fail = failed ? __ffs(failed) - 1 : 32;
     const int alive_rows = S.should_continue != 0.f ? (first_fail < n ? first_fail : n) : 0;
@@ -111,7 +131,9 @@ __device__ __forceinline__ void stats_finalize_batch(const float* ring, int n, i
         stats[ST_MASS_GROWTH_DIST * plane + idx] = sqrtf(e0 * e0 + e1 * e1) * invR;
         stats[ST_INERTIA * plane + idx] = (tot[PT_MX2_R] - c0 * tot[PT_MX_R]) * iden + (tot[PT_MX2_C] - c1 * tot[PT_MX_C]) * iden;
         stats[ST_POTENTIAL_VOLUME * plane + idx] = tot[PT_CNT_P] * invR2;
-        channel_mass[idx] = cm;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) channel_mass[idx * C + c] = cm[c];
     }
 
     // carry out: values of the last valid lane
@@ -122,7 +144,6 @@ __device__ __forceinline__ void stats_finalize_batch(const float* ring, int n, i
     S.angle = __shfl_sync(FULL, angle, last);
     S.prev_mass = __shfl_sync(FULL, mass, last);
     S.prev_sign = __shfl_sync(FULL, sign, last);
-    S.init_cm = init_cm;
     S.mono = __shfl_sync(FULL, mono, last);
     S.vol = __shfl_sync(FULL, vol, last);
     S.n_alive += (float)alive_rows;
