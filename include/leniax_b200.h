@@ -157,6 +157,16 @@ int lnx_run_scan(const lnx_plan* plan, int32_t n_sols, int32_t n_init, int32_t m
 int lnx_compute_stats(const lnx_plan* plan, int32_t n_worlds, const float* cells, const float* field, const float* potential,
                       int32_t* total_shift_idx, float* mass_centroid, float* mass_angle, float* stats, float* channel_mass, void* stream);
 
+/* One step of core.update with the DIRECT-CONVOLUTION potential (leniax/core.py:105-146 get_potential, selected by
+ * fft=False in helpers.build_get_potential_fn, helpers.py:464-488) followed by get_field / weighted mean-sum / get_state.
+ * 2-D worlds of any size (desc->dims, no power-of-two restriction); desc also gives C, K, slot[], c_in[], gf_id[],
+ * state_fn, weighted_average.  state [n][C][H][W], kernels = the reference's cropped K [nb_slots][1][kh][kw]
+ * (kernels.py:116-117, 153-156), gf_params [K][2], weights [C][K]; out: state_out, field_out [n][C][H][W],
+ * potential_out [n][K][H][W].  This is the reference's cross-check path, not the throughput path. */
+int lnx_update_conv(const lnx_desc* desc, int32_t n_worlds, int32_t kh, int32_t kw, const float* state, const float* kernels,
+                    const float* gf_params, const float* weights, float dt, float* state_out, float* field_out, float* potential_out,
+                    void* stream);
+
 /* Name of the CUDA kernel lnx_run_scan would launch for this plan/arguments ("fused" or "generic"), for tests. */
 const char* lnx_run_scan_variant(const lnx_plan* plan, int32_t with_trajectory);
 

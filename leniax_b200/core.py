@@ -24,6 +24,14 @@ class PotentialFn:
     fft: bool = True
     channel_first: bool = True
 
+    def __call__(self, state, K):
+        """The potential alone, ``[N, K, *dims]`` (what the reference's ``get_potential_fn(state, K)`` returns): one
+        ``update`` with identity growth and zero weights, of which only the potential is kept."""
+        C = int(state.shape[1])
+        nk = len(self.tc_indices) if self.tc_indices is not None else self.nb_slots
+        return update(None, state, K, torch.zeros((nk, 2)), torch.zeros((C, nk)), 0., self, FieldFn(('identity', ) * nk, False),
+                      get_state_simple)[2]
+
 
 @dataclass(frozen=True)
 class FieldFn:
@@ -71,7 +79,8 @@ class UpdateFn:
     def kernel_layout(self, nb_channels: int):
         pf = self.get_potential_fn
         slots = tuple(pf.tc_indices) if pf.tc_indices is not None else tuple(range(pf.nb_slots))
-        c_in = tuple(s // pf.max_k_per_channel for s in slots)
+        max_k = pf.max_k_per_channel or pf.nb_slots // nb_channels  # the conv path learns C from the state
+        c_in = tuple(s // max_k for s in slots)
         gf_ids = tuple(gfs.resolve(s).gf_id for s in self.get_field_fn.gf_slugs)
         if len(gf_ids) != len(slots):
             raise ValueError(f'{len(gf_ids)} growth functions for {len(slots)} kernels')
@@ -92,8 +101,6 @@ def update(rng_key, state, K, gf_params, kernels_weight_per_channel, dt, get_pot
             'core.update needs the PotentialFn / FieldFn descriptors built by leniax_b200.helpers '
             '(arbitrary Python callables cannot be fused into the CUDA step; there is no CPU fallback)'
         )
-    if not get_potential_fn.fft:
-        raise NotImplementedError('the direct-convolution potential (fft=False, core.py:105-146) is not built; use fft=True')
     sfn = _resolve_state_fn(get_state_fn)
     dev = engine.require_cuda_device(state.device if isinstance(state, torch.Tensor) and state.is_cuda else None)
     state_t = engine.as_device_tensor(state, torch.float32, dev)
@@ -101,6 +108,8 @@ def update(rng_key, state, K, gf_params, kernels_weight_per_channel, dt, get_pot
     world_size = tuple(state_t.shape[2:])
     ufn = UpdateFn(get_potential_fn, get_field_fn, sfn)
     slots, c_in, gf_ids = ufn.kernel_layout(C)
+    if not get_potential_fn.fft:
+        return update_conv(state_t, K, gf_params, kernels_weight_per_channel, dt, ufn)
     dt_t = engine.as_device_tensor(dt, torch.float32, dev).reshape(-1)[:1]
     plan = engine.Plan.get(world_size=world_size, nb_channels=C, slots=slots, c_in=c_in, gf_ids=gf_ids,
                            nb_slots=get_potential_fn.nb_slots, state_fn=sfn.slug, weighted_average=get_field_fn.average,
@@ -110,3 +119,46 @@ def update(rng_key, state, K, gf_params, kernels_weight_per_channel, dt, get_pot
                         engine.as_device_tensor(kernels_weight_per_channel, torch.float32, dev)[None], dt_t, 1,
                         keep_trajectory=True)
     return res['final_cells'][0], res['field'][0, 0], res['potential'][0, 0]
+
+
+def update_conv(state: torch.Tensor, K, gf_params, kernels_weight_per_channel, dt, ufn: UpdateFn
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``core.update`` with the direct-convolution potential (core.py:105-146, ``fft=False``): ``lnx_update_conv``.
+
+    ``K`` is the reference's cropped kernel tensor ``[C * max_k, 1, kh, kw]`` (kernels.py:116-117, 153-156).  Any 2-D world
+    size.  This is the cross-check path of the reference, not the throughput path.
+    """
+    import ctypes
+
+    from . import _lib
+    dev = state.device
+    f32 = torch.float32
+    N, C = state.shape[0], state.shape[1]
+    world_size = tuple(state.shape[2:])
+    if len(world_size) != 2:
+        raise NotImplementedError('the direct-convolution potential is 2-D only, as in the reference (core.py:136)')
+    slots, c_in, gf_ids = ufn.kernel_layout(C)
+    Kt = engine.as_device_tensor(K, f32, dev)
+    if Kt.dim() != 4 or Kt.shape[1] != 1 or Kt.shape[0] != ufn.get_potential_fn.nb_slots:
+        raise ValueError(f'fft=False expects K of shape [C * max_k, 1, kh, kw], got {tuple(Kt.shape)}')
+    kh, kw = int(Kt.shape[2]), int(Kt.shape[3])
+    d = _lib.LnxDesc()
+    d.nb_dims = 2
+    d.dims[0], d.dims[1] = int(world_size[0]), int(world_size[1])
+    d.nb_channels, d.nb_kernels, d.nb_slots = C, len(slots), ufn.get_potential_fn.nb_slots
+    for k in range(len(slots)):
+        d.slot[k], d.c_in[k], d.gf_id[k] = int(slots[k]), int(c_in[k]), int(gf_ids[k])
+    d.state_fn = engine.STATE_FN_IDS[ufn.get_state_fn.slug]
+    d.weighted_average = 1 if ufn.get_field_fn.average else 0
+    d.R, d.stats_dt = 1.0, 1.0
+    gf = engine.as_device_tensor(gf_params, f32, dev).reshape(len(slots), 2)
+    w = engine.as_device_tensor(kernels_weight_per_channel, f32, dev).reshape(C, len(slots))
+    dt_f = float(dt.reshape(-1)[0].item()) if isinstance(dt, torch.Tensor) else float(dt)
+    new_state, field = torch.empty_like(state), torch.empty_like(state)
+    potential = torch.empty((N, len(slots)) + world_size, dtype=f32, device=dev)
+    lib = _lib.load_library()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.lnx_update_conv(ctypes.byref(d), N, kh, kw, state.data_ptr(), Kt.data_ptr(), gf.data_ptr(), w.data_ptr(), dt_f,
+                                       new_state.data_ptr(), field.data_ptr(), potential.data_ptr(), stream))
+    return new_state, field, potential

@@ -19,6 +19,7 @@
 #include "lnx_stats_batch.cuh"
 #include "lnx_tmem.cuh"
 #include "lnx_tiled.cuh"
+#include "lnx_conv.cuh"
 
 namespace lnx {
 
@@ -1902,6 +1903,58 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
         pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), st>>>(c);
         pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
     }
+    LNX_CUDA(cudaGetLastError());
+    return LNX_OK;
+}
+
+int lnx_update_conv(const lnx_desc* d, int32_t n_worlds, int32_t kh, int32_t kw, const float* state, const float* kernels,
+                    const float* gf_params, const float* weights, float dt, float* state_out, float* field_out, float* potential_out,
+                    void* stream) {
+    if (!d || !state || !kernels || !gf_params || !weights || !state_out || !field_out || !potential_out)
+        return fail(LNX_ERR_INVALID, "lnx_update_conv: null argument");
+    if (d->nb_dims != 2) return fail(LNX_ERR_UNSUPPORTED, "lnx_update_conv: the direct-convolution potential is 2-D only (core.py:136: strides (1, 1))");
+    if (n_worlds < 1 || n_worlds > 65535 || kh < 1 || kw < 1 || d->dims[0] < 1 || d->dims[1] < 1)
+        return fail(LNX_ERR_INVALID, "lnx_update_conv: bad sizes");
+    if (d->nb_channels < 1 || d->nb_channels > MAX_C || d->nb_kernels < 1 || d->nb_kernels > MAX_K)
+        return fail(LNX_ERR_INVALID, "lnx_update_conv: C must be in [1, %d] and K in [1, %d]", MAX_C, MAX_K);
+    if ((long long)n_worlds * d->nb_kernels > 65535) return fail(LNX_ERR_INVALID, "lnx_update_conv: n_worlds * K must be <= 65535");
+    const int rc = ensure_device_init(nullptr, nullptr);
+    if (rc != LNX_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    lnx::conv::ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.state = state;
+    a.kernels = kernels;
+    a.potential = potential_out;
+    a.C = d->nb_channels;
+    a.K = d->nb_kernels;
+    a.H = d->dims[0];
+    a.W = d->dims[1];
+    a.kh = kh;
+    a.kw = kw;
+    lnx::conv::FieldArgs f;
+    memset(&f, 0, sizeof(f));
+    for (int k = 0; k < a.K; ++k) {
+        if (d->c_in[k] < 0 || d->c_in[k] >= a.C || d->slot[k] < 0 || d->slot[k] >= d->nb_slots || d->gf_id[k] < 0 || d->gf_id[k] >= GF_COUNT)
+            return fail(LNX_ERR_INVALID, "lnx_update_conv: kernel %d: bad c_in / slot / gf_id", k);
+        a.slot[k] = d->slot[k];
+        a.c_in[k] = d->c_in[k];
+        f.gf_id[k] = d->gf_id[k];
+    }
+    lnx::conv::potential_kernel<<<dim3((a.W + 31) / 32, (a.H + 7) / 8, n_worlds * a.K), dim3(32, 8), 0, st>>>(a);
+    f.state = state;
+    f.potential = potential_out;
+    f.gf_params = gf_params;
+    f.weights = weights;
+    f.state_out = state_out;
+    f.field_out = field_out;
+    f.cells = (long long)a.H * a.W;
+    f.C = a.C;
+    f.K = a.K;
+    f.state_fn = d->state_fn;
+    f.mean = d->weighted_average;
+    f.dt = dt;
+    lnx::conv::field_update_kernel<<<dim3((unsigned)((f.cells + 255) / 256), n_worlds), 256, 0, st>>>(f);
     LNX_CUDA(cudaGetLastError());
     return LNX_OK;
 }

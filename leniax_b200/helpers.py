@@ -50,13 +50,17 @@ def init(config: Dict, use_init_cells: bool = True, fft: bool = True, device=Non
 
 def build_get_potential_fn(kernel_shape: Tuple[int, ...], true_channels: Optional[List[bool]] = None, fft: bool = True,
                            channel_first: bool = True) -> leniax_core.PotentialFn:
-    """helpers.py:430-488.  ``kernel_shape`` is ``K.shape`` = ``[1, C, max_k, H, W]`` for the FFT path."""
-    if not fft:
-        raise NotImplementedError('the direct-convolution potential (fft=False, core.py:105-146) is not built; use fft=True')
+    """helpers.py:430-488.  ``kernel_shape`` is ``K.shape`` = ``[1, C, max_k, H, W]`` for the FFT path and
+    ``[C * max_k, 1, kh, kw]`` for the direct-convolution path (``fft=False``)."""
     if not channel_first:
         raise NotImplementedError('channel_first=False layouts are not built')
-    C, max_k = int(kernel_shape[1]), int(kernel_shape[2])
     tc = tuple(i for i, t in enumerate(true_channels) if t) if true_channels is not None else None
+    if not fft:
+        # direct convolution (helpers.py:464-488): K is [C * max_k, 1, kh, kw]; C is only known once the state is seen
+        if len(kernel_shape) != 4:
+            raise NotImplementedError('the direct-convolution potential is 2-D only, as in the reference (core.py:136)')
+        return leniax_core.PotentialFn(tc, int(kernel_shape[0]), 0, False, True)
+    C, max_k = int(kernel_shape[1]), int(kernel_shape[2])
     return leniax_core.PotentialFn(tc, C * max_k, max_k, True, True)
 
 

@@ -23,8 +23,6 @@ def _check_fns(update_fn, compute_stats_fn):
         )
     if not isinstance(compute_stats_fn, ComputeStatsFn):
         raise NotImplementedError('compute_stats_fn must come from leniax_b200.statistics.build_compute_stats_fn')
-    if not update_fn.get_potential_fn.fft:
-        raise NotImplementedError('the direct-convolution potential (fft=False) is not built; use fft=True')
 
 
 def _finite_params(gf_params: torch.Tensor, weights: torch.Tensor, average: bool) -> bool:
@@ -52,7 +50,7 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     gf_params = engine.as_device_tensor(gf_params, f32, dev)
     weights = engine.as_device_tensor(weights, f32, dev)
     T = engine.as_device_tensor(T, f32, dev)
-    K = engine.as_device_tensor(K, torch.complex64, dev)
+    K = engine.as_device_tensor(K, torch.complex64 if update_fn.get_potential_fn.fft else f32, dev)
     if not batched:
         cells0, gf_params, weights, T, K = cells0[None], gf_params[None], weights[None], T.reshape(1), K[None]
     n_sols, n_init, C = cells0.shape[0], cells0.shape[1], cells0.shape[2]
@@ -60,6 +58,8 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     if tuple(stats_fn.world_size) != world_size:
         raise ValueError(f'compute_stats_fn was built for world_size {stats_fn.world_size}, cells are {world_size}')
     pf = update_fn.get_potential_fn
+    if not pf.fft:
+        return _scan_conv(cells0, K, gf_params, weights, T, max_run_iter, update_fn, stats_fn, keep_trajectory)
     slots, c_in, gf_ids = update_fn.kernel_layout(C)
     K = K.reshape((n_sols, pf.nb_slots) + world_size)
     plan = engine.Plan.get(world_size=world_size, nb_channels=C, slots=slots, c_in=c_in, gf_ids=gf_ids, nb_slots=pf.nb_slots,
@@ -79,6 +79,49 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     dt = (1. / T.reshape(n_sols)).contiguous()  # runner.py:307
     return plan.run_scan(cells0.contiguous(), K, gf_params.reshape(n_sols, len(slots), 2), weights.reshape(n_sols, C, len(slots)),
                          dt, max_run_iter, keep_trajectory=keep_trajectory, flags=flags)
+
+
+def _scan_conv(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, stats_fn: ComputeStatsFn, keep_trajectory: bool):
+    """The scan with the direct-convolution potential (``fft=False``): the reference's cross-check path, run as a host loop
+    of ``lnx_update_conv`` + ``lnx_compute_stats`` per step (runner._scan_fn, runner.py:295-334: statistics of the
+    PRE-update cells with this step's field / potential), ``check_heuristics`` afterwards (runner.py:161-162)."""
+    from . import core
+    from .statistics import check_heuristics
+    n_sols, n_init, C = cells0.shape[:3]
+    dev = cells0.device
+    nd = cells0.dim() - 3
+    per_sol = []
+    traj = {'cells': [], 'field': [], 'potential': []}
+    finals = []
+    for s in range(n_sols):
+        cells = cells0[s].contiguous()
+        shift = torch.zeros((n_init, nd), dtype=torch.int32, device=dev)  # runner.py:271-292
+        centroid = torch.zeros((nd, n_init), dtype=torch.float32, device=dev)
+        angle = torch.zeros((n_init, ), dtype=torch.float32, device=dev)
+        rows, tc, tf, tp = [], [], [], []
+        for _ in range(max_run_iter):
+            new_cells, field, potential = core.update_conv(cells, K[s], gf_params[s], weights[s], 1. / T.reshape(-1)[s], update_fn)
+            st, shift, centroid, angle = stats_fn(cells, field, potential, shift, centroid, angle)
+            rows.append(st)
+            if keep_trajectory:
+                tc.append(cells)
+                tf.append(field)
+                tp.append(potential)
+            cells = new_cells
+        stats = {k: torch.stack([r[k] for r in rows]) for k in rows[0]}  # [T, N] / [T, N, C]
+        stats['N'] = check_heuristics(stats).sum(dim=0).to(dev)
+        per_sol.append(stats)
+        finals.append(cells)
+        if keep_trajectory:
+            traj['cells'].append(torch.stack(tc))
+            traj['field'].append(torch.stack(tf))
+            traj['potential'].append(torch.stack(tp))
+    out = {k: torch.stack([p[k] for p in per_sol]) for k in per_sol[0]}
+    res = {'stats': out, 'final_cells': torch.stack(finals), 'cells': None, 'field': None, 'potential': None}
+    if keep_trajectory:
+        for k in traj:
+            res[k] = torch.stack(traj[k])
+    return res
 
 
 def run_scan(rng_key, cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter: int, R: float, update_fn,

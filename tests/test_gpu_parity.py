@@ -520,3 +520,63 @@ def test_per_solution_parameters_weighted_sum_and_odd_batch(golden_dir):
     np.testing.assert_allclose(final.cpu().numpy(), ofinal, atol=2e-5)
     np.testing.assert_allclose(stats['mass'].cpu().numpy(), ostats['mass'], atol=1e-5)
     np.testing.assert_allclose(stats['mass_speed'].cpu().numpy(), ostats['mass_speed'], atol=5e-4)
+
+
+# ---- direct-convolution potential (fft=False, leniax/core.py:105-146): the reference's cross-check path -----------------
+def test_conv_potential_kat():
+    """tests/test_core.py:55-103 of the reference: 2 channels, 3 true kernels of 3x3 on a 2x2 world (wrap padding wider than
+    the world), expected potentials 0.09 / 0.18 / 0.54."""
+    C = 2
+    cells = torch.ones([1, C, 2, 2])
+    cells[0, 0], cells[0, 1] = 0.1, 0.2
+    K = torch.ones([4, 1, 3, 3])
+    K[0], K[1], K[2], K[3] = 0.1, 0.2, 0.3, 0
+    get_potential = helpers.build_get_potential_fn(K.shape, [True, True, True, False], False)
+    pot = get_potential(cells.to(DEV), K.to(DEV)).cpu().numpy()
+    assert pot.shape == (1, 3, 2, 2)
+    np.testing.assert_allclose(pot[0, 0], 0.09, rtol=1e-6)
+    np.testing.assert_allclose(pot[0, 1], 0.18, rtol=1e-6)
+    np.testing.assert_allclose(pot[0, 2], 0.54, rtol=1e-6)
+    opot = lo.get_potential_conv(cells.numpy(), K.numpy(), tc_indices=(0, 1, 2))
+    np.testing.assert_allclose(pot, opot, rtol=1e-6)
+
+
+@pytest.mark.parametrize('name,steps', [('orbium-test', 12), ('aquarium-test', 4)])
+def test_conv_path_matches_oracle_and_fft_path(golden_dir, name, steps):
+    """init_and_run(fft=False) against the oracle's conv path (same wrap-padded cross-correlation) and against the FFT path
+    (the fixtures' kernels are symmetric, so correlation == convolution)."""
+    cfg, ocfg = _setup(golden_dir, name, steps)
+    cells, field, potential, stats = helpers.init_and_run(None, cfg, with_jit=True, fft=False, device=DEV)
+    oc, of, op, ostats = lo.init_and_run(ocfg, with_jit=True, fft=False)
+    assert np.abs(cells.cpu().numpy() - oc).max() < 1e-5
+    assert np.abs(potential.cpu().numpy() - op).max() < 2e-6
+    assert np.abs(field.cpu().numpy() - of).max() < 2e-4
+    assert stats['N'].cpu().numpy().reshape(-1).tolist() == ostats['N'].tolist()
+    np.testing.assert_allclose(stats['mass'].cpu().numpy().reshape(-1), ostats['mass'].reshape(-1), atol=2e-5)
+    fcells = helpers.init_and_run(None, cfg, with_jit=True, fft=True, device=DEV)[0]
+    assert np.abs(cells.cpu().numpy() - fcells.cpu().numpy()).max() < 2e-5
+
+
+def test_conv_update_on_a_non_power_of_two_world(golden_dir):
+    """The conv path has no power-of-two restriction: one core.update on a 100 x 120 world, 2 channels, 3 kernels."""
+    rng = np.random.default_rng(11)
+    C, H, W = 2, 100, 120
+    state = rng.random((3, C, H, W), dtype=np.float32)
+    K = rng.random((4, 1, 7, 6), dtype=np.float32)  # odd and even kernel sides: both padding rules of helpers.py:466-470
+    K /= K.sum(axis=(2, 3), keepdims=True)
+    K[3] = 0
+    mapping = kernels.KernelMapping(C, 3)
+    mapping.cin_gfs = [['poly_quad4', 'gaussian'], ['poly_quad4']]
+    mapping.cin_gf_params = [[[.3, .05], [.4, .1]], [[.5, .08]]]
+    mapping.kernels_weight_per_channel = [[.5, 0., .7], [0., 1., 0.]]
+    mapping.true_channels = [True, True, True, False]
+    ufn = helpers.build_update_fn(K.shape, mapping, 'v1', True, False)
+    new, field, pot = ufn(None, torch.from_numpy(state).to(DEV), torch.from_numpy(K).to(DEV), mapping.get_gf_params(DEV),
+                          mapping.get_kernels_weight_per_channel(DEV), 0.1)
+    opot = lo.get_potential_conv(state, K, tc_indices=(0, 1, 2))
+    np.testing.assert_allclose(pot.cpu().numpy(), opot, atol=2e-6)
+    gfp = np.array([[.3, .05], [.4, .1], [.5, .08]], np.float32)
+    w = np.array([[.5, 0., .7], [0., 1., 0.]], np.float32)
+    ofield = lo.get_field(opot, gfp, w, ['poly_quad4', 'gaussian', 'poly_quad4'], True)
+    np.testing.assert_allclose(field.cpu().numpy(), ofield, atol=2e-5)
+    np.testing.assert_allclose(new.cpu().numpy(), lo.get_state_v1(state, ofield, np.float32(0.1)), atol=2e-5)
