@@ -320,7 +320,10 @@ def run_b200(args):
             'clocks': clocks,
             'roofline': {
                 'bound': 'fp32', 'achieved': achieved_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved_tflops / fp32_peak,
-                'traffic': None, 'kernel': kernel_name, 'kernel_ms': kernel_ms,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this exact workload, from an ncu
+                # capture (profiles/r1_tm_dram_traffic_bench_launch.csv); algorithmic bytes = 268 MB state in + 218 MB rows out
+                'traffic': 762075392 if (kernel_name == 'lnx_world128_tm' and n_worlds == 4096 and sim_steps == 1024) else None,
+                'kernel': kernel_name, 'kernel_ms': kernel_ms,
                 'flop_per_cell_update': FLOP_PER_CELL_UPDATE, 'peak_source': 'measured live: lnx_measure_fp32_peak FMA loop (MEASURED_PEAKS.json has no FP32 entry)',
                 'peak_analytic_tflops': FP32_PEAK_ANALYTIC_TFLOPS, 'frac_of_analytic': achieved_tflops / FP32_PEAK_ANALYTIC_TFLOPS,
                 'hbm_achieved_gbs': stats_bytes / (kernel_ms * 1e-3) / 1e9, 'hbm_peak_gbs': peaks.get('hbm_gbs'),

@@ -1481,7 +1481,7 @@ static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
     return true;
 }
 static size_t smem_a(const Geom& g) { return ((size_t)(g.slab_rows / 2) * g.A2 + (g.nd == 3 ? (size_t)g.A1 * g.half : 0)) * sizeof(float2); }
-static size_t smem_b(const Geom& g) { return 2 * (size_t)g.L * g.tc * sizeof(float2); }
+static size_t smem_b(const Geom& g, bool two_buf = true) { return (two_buf ? 2 : 1) * (size_t)g.L * g.tc * sizeof(float2); }
 static size_t smem_c(const Geom& g, int C) {
     return ((size_t)g.slab_rows * g.half + (size_t)(g.slab_rows / 2) * g.A2) * sizeof(float2) + (size_t)C * g.slab_rows * g.A2 * sizeof(float);
 }
@@ -1888,9 +1888,11 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
     d.max_iter = max_run_iter;
     d.R = p->d.R;
     d.stats_dt = p->d.stats_dt;
+    int per_channel[MAX_C] = {0};
     for (int k = 0; k < K; ++k) {
         b.c_in[k] = p->d.c_in[k];
         c.gf_id[k] = p->d.gf_id[k];
+        if (++per_channel[p->d.c_in[k]] > 1) b.two_buf = 1;
     }
     const long long M = g.spec / g.L;
     const dim3 grid_a(g.n_slabs, C, (unsigned)worlds), grid_b((unsigned)((M + g.tc - 1) / g.tc), C, (unsigned)worlds),
@@ -1899,7 +1901,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
         c.t = t;
         d.t = t;
         pass_a_kernel<<<grid_a, TPB, th::smem_a(g), st>>>(a);
-        pass_b_kernel<<<grid_b, TPB, th::smem_b(g), st>>>(b);
+        pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), st>>>(b);
         pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), st>>>(c);
         pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
     }

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
     block_fft<false, false>(z, A2, g.logA2, 1, pairs, A2, P.tw);
     float2* dst = P.spec + (((size_t)w * P.C + c) * g.rows + row0) * half;
     const bool plane = g.nd == 3;
-    for (int i = threadIdx.x; i < pairs * half; i += blockDim.x) {
-        const int pr = i / half, k = i - pr * half;
+    for (int pr = 0; pr < pairs; ++pr)
+    for (int k = threadIdx.x; k < half; k += blockDim.x) {
         const float2 zk = z[(size_t)pr * A2 + brev_n(k, g.logA2)];
         const float2 zc = z[(size_t)pr * A2 + brev_n((A2 - k) & (A2 - 1), g.logA2)];
         const float2 a = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
@@ -173,6 +173,7 @@ struct PassBArgs {
     const float2* tw;
     Geom g;
     int C, K, n_init;
+    int two_buf;           // 1: some channel feeds several kernels (forward spectrum kept in F, products in T); 0: in place
     int c_in[MAX_K];
 };
 __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
     const int L = g.L, tc = g.tc;
     const long long M = g.spec / L;
     float2* F = reinterpret_cast<float2*>(smem_raw);
-    float2* T = F + (size_t)L * tc;
+    float2* T = P.two_buf ? F + (size_t)L * tc : F;
     const int c = blockIdx.y, w = blockIdx.z;
     const long long m0 = (long long)blockIdx.x * tc;
     const int wdt = (int)((M - m0) < tc ? (M - m0) : tc);
@@ -287,8 +288,8 @@ __global__ void __launch_bounds__(TPB) pass_c_kernel(PassCArgs P) {
             __syncthreads();
         }
         // retangle: Z'[k] = A + iB, Z'[N-k] = conj(A) + i conj(B), stored at bit-reversed positions for the DIT
-        for (int i = threadIdx.x; i < pairs * half; i += blockDim.x) {
-            const int pr = i / half, kk = i - pr * half;
+        for (int pr = 0; pr < pairs; ++pr)
+        for (int kk = threadIdx.x; kk < half; kk += blockDim.x) {
             const float2 a = pl[(size_t)(2 * pr) * half + kk], b = pl[(size_t)(2 * pr + 1) * half + kk];
             z[(size_t)pr * A2 + brev_n(kk, g.logA2)] = make_float2(a.x - b.y, a.y + b.x);
             if (kk != 0 && kk != A2 / 2) z[(size_t)pr * A2 + brev_n(A2 - kk, g.logA2)] = make_float2(a.x + b.y, b.x - a.y);
@@ -333,29 +334,31 @@ __global__ void __launch_bounds__(TPB) pass_c_kernel(PassCArgs P) {
             if (fout) fout[i] = f;
             st[i] = state_update_dyn<true>(P.state_fn, a, f, dt);
             // coordinates of this cell in the rolled (centred) world, statistics.py:28-33 + utils.py:269-293
-            int idx[3];
-            if (g.nd == 3) {
-                idx[0] = (int)(grow >> g.logA1);
-                idx[1] = (int)(grow & (g.A1 - 1));
-                idx[2] = n;
-            } else {
-                idx[0] = (int)grow;
-                idx[1] = n;
-                idx[2] = 0;
-            }
+            const int i0 = g.nd == 3 ? (int)(grow >> g.logA1) : (int)grow;
+            const int i1 = g.nd == 3 ? (int)(grow & (g.A1 - 1)) : n;
             const float gp = fmaxf(f, 0.f);
             m00 += a;
             acc[0] += a > EPS ? 1.f : 0.f;
             acc[1] += gp;
             acc[2] += gp > EPS ? 1.f : 0.f;
-            for (int d = 0; d < g.nd; ++d) {
-                const float x = (float)(((idx[d] - cr.shift[d]) & (g.dims[d] - 1)) - g.dims[d] / 2);
-                acc[4 + d] += a * x;
-                acc[4 + MAXD + d] += a * x * x;
-                acc[4 + 2 * MAXD + d] += gp * x;
+            const float x0 = (float)(((i0 - cr.shift[0]) & (g.dims[0] - 1)) - g.dims[0] / 2);
+            const float x1 = (float)(((i1 - cr.shift[1]) & (g.dims[1] - 1)) - g.dims[1] / 2);
+            acc[4] += a * x0;
+            acc[4 + MAXD] += a * x0 * x0;
+            acc[4 + 2 * MAXD] += gp * x0;
+            acc[5] += a * x1;
+            acc[5 + MAXD] += a * x1 * x1;
+            acc[5 + 2 * MAXD] += gp * x1;
+            if (g.nd == 3) {
+                const float x2 = (float)(((n - cr.shift[2]) & (g.dims[2] - 1)) - g.dims[2] / 2);
+                acc[6] += a * x2;
+                acc[6 + MAXD] += a * x2 * x2;
+                acc[6 + 2 * MAXD] += gp * x2;
             }
         }
-        acc[4 + 3 * MAXD + c] = m00;
+#pragma unroll
+        for (int cc = 0; cc < MAX_C; ++cc)
+            if (cc == c) acc[4 + 3 * MAXD + cc] = m00;
     }
     // block reduction of the partials
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -105,3 +105,17 @@ def update_individuals(inds: List[LeniaIndividual], stats: Dict[str, torch.Tenso
             tmp['behaviours'] = {k: float(block_h[i, int(best_h[i]), 1 + j]) for j, k in enumerate(keys)} if block_h is not None else {}
             ind.features = [leniax_utils.get_param(tmp, key) for key in ind.qd_config['phenotype']]
     return inds
+
+
+def grid_archive_index(features: torch.Tensor, grid_shape: List[int], features_domain: List[List[float]]) -> torch.Tensor:
+    """Cell of a pyribs ``GridArchive(grid_shape, features_domain)`` (examples/qd_cmame.py:60-64) a behaviour descriptor
+    falls into: ``[..., D]`` float -> ``[..., D]`` int64.  Restates ``GridArchive.get_index`` of ribs 0.4.0 (the reference's
+    pin, setup.py:21) — clip ``bc + eps`` to ``[lower, upper - eps]`` with eps = 1e-6, then
+    ``int((bc - lower) / (upper - lower) * dims)``.  pyribs is not in this image: **parity unpinned** (SURVEY §8c)."""
+    f = features.to(torch.float64)
+    lower = torch.tensor([d[0] for d in features_domain], dtype=torch.float64, device=f.device)
+    upper = torch.tensor([d[1] for d in features_domain], dtype=torch.float64, device=f.device)
+    dims = torch.tensor(list(grid_shape), dtype=torch.float64, device=f.device)
+    eps = 1e-6
+    f = torch.minimum(torch.maximum(f + eps, lower), upper - eps)
+    return ((f - lower) / (upper - lower) * dims).to(torch.int64)

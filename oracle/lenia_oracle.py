@@ -623,6 +623,17 @@ def run(cells, K, gf_params, weights, T, max_run_iter, update_fn, compute_stats_
 # ---------------------------------------------------------------------------
 # QD consumer                                            leniax/qd.py:150-188
 # ---------------------------------------------------------------------------
+def grid_archive_index(features: np.ndarray, grid_shape: Sequence[int], features_domain: Sequence[Sequence[float]]) -> np.ndarray:
+    """ribs 0.4.0 ``GridArchive.get_index`` (third-party, absent from /root/reference; restated from its published source,
+    unpinned): clip ``bc + 1e-6`` to ``[lower, upper - 1e-6]`` then ``int((bc - lower) / interval * dims)`` per axis."""
+    f = np.asarray(features, np.float64)
+    lower = np.array([d[0] for d in features_domain], np.float64)
+    upper = np.array([d[1] for d in features_domain], np.float64)
+    eps = 1e-6
+    f = np.clip(f + eps, lower, upper - eps)
+    return ((f - lower) / (upper - lower) * np.array(grid_shape, np.float64)).astype(np.int64)
+
+
 def behaviours_of(stats: Dict[str, np.ndarray], fitness_coef: float = 1.):
     """qd.py:168-186: fitness = coef*max_init N; behaviours = mean of the last 128 rows before ns."""
     Ns = stats['N']
