@@ -46,19 +46,25 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     assert max_run_iter > 0, f"max_run_iter must be positive, value given: {max_run_iter}"  # runner.py:51
     dev = engine.require_cuda_device(cells0.device if isinstance(cells0, torch.Tensor) and cells0.is_cuda else None)
     f32 = torch.float32
-    cells0 = engine.as_device_tensor(cells0, f32, dev)
+    host_cells = cells0 if (isinstance(cells0, torch.Tensor) and not cells0.is_cuda and cells0.dtype == f32 and batched
+                            and cells0.is_contiguous()) else None
+    if host_cells is None:
+        cells0 = engine.as_device_tensor(cells0, f32, dev)
     gf_params = engine.as_device_tensor(gf_params, f32, dev)
     weights = engine.as_device_tensor(weights, f32, dev)
     T = engine.as_device_tensor(T, f32, dev)
     K = engine.as_device_tensor(K, torch.complex64 if update_fn.get_potential_fn.fft else f32, dev)
-    if not batched:
+    if not batched:  # (host_cells is only kept for batched calls)
         cells0, gf_params, weights, T, K = cells0[None], gf_params[None], weights[None], T.reshape(1), K[None]
-    n_sols, n_init, C = cells0.shape[0], cells0.shape[1], cells0.shape[2]
-    world_size = tuple(cells0.shape[3:])
+    shape = tuple(host_cells.shape) if host_cells is not None else tuple(cells0.shape)
+    n_sols, n_init, C = shape[0], shape[1], shape[2]
+    world_size = shape[3:]
     if tuple(stats_fn.world_size) != world_size:
         raise ValueError(f'compute_stats_fn was built for world_size {stats_fn.world_size}, cells are {world_size}')
     pf = update_fn.get_potential_fn
     if not pf.fft:
+        if host_cells is not None:
+            cells0 = host_cells.to(dev)
         return _scan_conv(cells0, K, gf_params, weights, T, max_run_iter, update_fn, stats_fn, keep_trajectory)
     slots, c_in, gf_ids = update_fn.kernel_layout(C)
     K = K.reshape((n_sols, pf.nb_slots) + world_size)
@@ -77,8 +83,41 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     if _finite_params(gf_params, weights, update_fn.get_field_fn.average):
         flags |= _lib.LNX_RUN_ASSUME_FINITE
     dt = (1. / T.reshape(n_sols)).contiguous()  # runner.py:307
-    return plan.run_scan(cells0.contiguous(), K, gf_params.reshape(n_sols, len(slots), 2), weights.reshape(n_sols, C, len(slots)),
-                         dt, max_run_iter, keep_trajectory=keep_trajectory, flags=flags)
+    gfp, wts = gf_params.reshape(n_sols, len(slots), 2), weights.reshape(n_sols, C, len(slots))
+    if host_cells is not None:
+        n_first = 2 * torch.cuda.get_device_properties(dev).multi_processor_count  # one full wave of CTAs of the fused kernel
+        if n_sols == 1 and not keep_trajectory and n_init >= 4 * n_first:
+            return _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev)
+        cells0 = host_cells.to(dev, non_blocking=True)
+    return plan.run_scan(cells0.contiguous(), K, gfp, wts, dt, max_run_iter, keep_trajectory=keep_trajectory, flags=flags)
+
+
+_COPY_STREAMS: Dict[str, torch.cuda.Stream] = {}
+
+
+def _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev):
+    """Initial states given in host memory (one solution, many initialisations): the first wave of worlds is uploaded and
+    started at once, the rest of the batch is uploaded on a copy stream while that wave computes, then runs as a second
+    launch.  Worlds are independent, so the two launches give bit-identical rows to a single one."""
+    main = torch.cuda.current_stream(dev)
+    side = _COPY_STREAMS.setdefault(str(dev), torch.cuda.Stream(device=dev))
+    with torch.cuda.device(dev):
+        side.wait_stream(main)
+        first = host_cells[:, :n_first].to(dev, non_blocking=True)
+        with torch.cuda.stream(side):
+            rest = host_cells[:, n_first:].to(dev, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(side)
+        r1 = plan.run_scan(first, K, gfp, wts, dt, max_run_iter, keep_trajectory=False, flags=flags)
+        main.wait_event(uploaded)
+        rest.record_stream(main)
+        r2 = plan.run_scan(rest, K, gfp, wts, dt, max_run_iter, keep_trajectory=False, flags=flags)
+    stats = {}
+    for k, v in r1['stats'].items():
+        axis = 2 if k == 'channel_mass' else (1 if k == 'N' else 2)  # [S, T, I, C] / [S, I] / [S, T, I]
+        stats[k] = torch.cat([v, r2['stats'][k]], dim=axis)
+    return {'stats': stats, 'final_cells': torch.cat([r1['final_cells'], r2['final_cells']], dim=1), 'cells': None, 'field': None,
+            'potential': None}
 
 
 def _scan_conv(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, stats_fn: ComputeStatsFn, keep_trajectory: bool):

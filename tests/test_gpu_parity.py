@@ -641,3 +641,22 @@ def test_integer_outputs_identical_for_99_percent_of_worlds(golden_dir):
     assert same_n >= 0.99
     assert same_idx >= 0.99
     assert ours_late >= twin_late - 0.25  # no worse than the reference arithmetic's own reproducibility on chaotic worlds
+
+
+def test_host_input_pipelined_upload_is_bit_identical(golden_dir):
+    """Initial states passed as a pinned HOST tensor are uploaded in two pieces (first wave of CTAs, then the rest under its
+    compute, runner._scan_pipelined_upload): rows and final states must equal the single-launch run on device inputs."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    n = 4 * 2 * torch.cuda.get_device_properties(0).multi_processor_count + 5
+    g = torch.Generator(device='cpu').manual_seed(3)
+    shifts = torch.randint(0, 128, (n, 2), generator=g)
+    base = cells[0, 0].cpu()
+    host = torch.stack([torch.roll(base, (int(a), int(b)), dims=(0, 1)) for a, b in shifts.tolist()])[None, :, None].contiguous().pin_memory()
+    T = torch.tensor([10.], device=DEV)
+    s_dev, f_dev = runner.run_scan_mem_optimized(None, host.to(DEV), K[None], gf[None], w[None], T, 9, 13, ufn, sfn)
+    s_host, f_host = runner.run_scan_mem_optimized(None, host, K[None], gf[None], w[None], T, 9, 13, ufn, sfn)
+    assert f_host.shape == f_dev.shape and torch.equal(f_host, f_dev)
+    for k in s_dev:
+        assert s_host[k].shape == s_dev[k].shape and torch.equal(s_host[k], s_dev[k]), k
