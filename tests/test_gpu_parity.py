@@ -660,3 +660,43 @@ def test_host_input_pipelined_upload_is_bit_identical(golden_dir):
     assert f_host.shape == f_dev.shape and torch.equal(f_host, f_dev)
     for k in s_dev:
         assert s_host[k].shape == s_dev[k].shape and torch.equal(s_host[k], s_dev[k]), k
+
+
+def test_generic_kernels_early_stop_and_old_vs_new(golden_dir):
+    """Multi-kernel worlds (orbium-scutium: 2 channels, 2 kernels -> the generic kernels): (i) early stop keeps N and the rows
+    qd.py:181-185 reads; (ii) the TMEM generic kernel and the older global-scratch generic kernel agree."""
+    steps, n = 260, 7
+    cfg, ocfg = _setup(golden_dir, 'orbium-scutium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    rng = np.random.default_rng(8)
+    base = cells.cpu().numpy()  # [1, C, 128, 128]
+    worlds = np.stack([np.roll(base[0], (int(rng.integers(128)), int(rng.integers(128))), axis=(1, 2)) * a for a in np.linspace(.1, 1.3, n)])
+    cells0 = torch.from_numpy(np.clip(worlds, 0, 1).astype(np.float32)).to(DEV)[None]
+    T = torch.tensor([float(cfg['world_params']['T'])], device=DEV)
+    R = cfg['world_params']['R']
+    args = (cells0, K[None], gf[None], w[None], T, steps, R, ufn, sfn)
+    full, ffull = runner.run_scan_mem_optimized(None, *args)
+    fast, _ = runner.run_scan_mem_optimized(None, *args, early_stop=True)
+    np.testing.assert_array_equal(full['N'].cpu().numpy(), fast['N'].cpu().numpy())
+    N = full['N'][0].cpu().numpy()
+    assert len(set(N.tolist())) > 1 and N.min() < steps
+    for i in range(n):
+        ns = max(int(N[i]), 128)
+        for k in ('mass', 'mass_speed', 'inertia', 'channel_mass'):
+            np.testing.assert_array_equal(full[k][0, :ns, i].cpu().numpy(), fast[k][0, :ns, i].cpu().numpy())
+    runner.FUSED_VARIANT = 'smem'  # also selects the older generic kernel (per-CTA global scratch, statistics warp)
+    try:
+        old, fold = runner.run_scan_mem_optimized(None, *args)
+    finally:
+        runner.FUSED_VARIANT = 'tmem'
+    np.testing.assert_array_equal(old['N'].cpu().numpy(), full['N'].cpu().numpy())
+    early = slice(0, 40)  # before rounding differences between the two kernels are amplified
+    np.testing.assert_allclose(old['mass'][0, early].cpu().numpy(), full['mass'][0, early].cpu().numpy(), atol=2e-5)
+    np.testing.assert_allclose(old['channel_mass'][0, early].cpu().numpy(), full['channel_mass'][0, early].cpu().numpy(), atol=2e-5)
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(ocfg['kernels_params']), [128, 128], ocfg['world_params']['nb_channels'],
+                                        ocfg['world_params']['R'])
+    ostats, _ = lo.run_scan(np.clip(worlds, 0, 1).astype(np.float32), oK, om.get_gf_params(), om.get_kernels_weight_per_channel(),
+                            np.float32(ocfg['world_params']['T']), steps, lo.build_update_fn(om),
+                            lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), False)
+    assert N.tolist() == ostats['N'].tolist()
