@@ -105,3 +105,65 @@ def init_and_run(rng_key, config: Dict, use_init_cells: bool = True, with_jit: b
         n = int(stats['N'])
         all_cells, all_fields, all_potentials = all_cells[:n], all_fields[:n], all_potentials[:n]
     return all_cells, all_fields, all_potentials, stats
+
+
+def multi_init_and_run(rng_key, main_config: Dict, configs: List[Dict], use_init_cells: bool = True, fft: bool = True, device=None):
+    """Several configurations of the same structure in one launch (helpers.py:192-237: ``vmap`` of ``run_scan`` over
+    cells / K / gf_params / weights / T).  Returns ``(cells, field, potential, stats)`` with a leading configuration axis."""
+    main_config = copy.deepcopy(main_config)
+    wp = main_config['world_params']
+    _, K0, mapping0 = init(main_config, use_init_cells, fft, device=device)
+    dev = K0.device
+    update_fn = build_update_fn(K0.shape, mapping0, wp.get('get_state_fn_slug', 'v1'), wp.get('weighted_average', True), fft)
+    stats_fn = leniax_stat.build_compute_stats_fn(wp, main_config['render_params'])
+    cells_l, K_l, gf_l, w_l, T_l = [], [], [], [], []
+    for config in configs:
+        cells, K, mapping = init(copy.deepcopy(config), use_init_cells, fft, device=dev)
+        cells_l.append(cells)
+        K_l.append(K)
+        gf_l.append(mapping.get_gf_params(dev))
+        w_l.append(mapping.get_kernels_weight_per_channel(dev))
+        T_l.append(float(config['world_params']['T']))
+    res = leniax_runner._scan(torch.stack(cells_l), torch.stack(K_l), torch.stack(gf_l), torch.stack(w_l),
+                              torch.tensor(T_l, dtype=torch.float32, device=dev), main_config['run_params']['max_run_iter'], update_fn,
+                              stats_fn, batched=True, keep_trajectory=True)
+    stats = {k: v.squeeze() for k, v in res['stats'].items()}
+    return res['cells'], res['field'], res['potential'], stats
+
+
+def search_for_init(rng_key, config: Dict, fft: bool = True, device=None) -> Tuple[Dict, int]:
+    """Search for a stable initial state (helpers.py:318-397).
+
+    The reference simulates the ``nb_init_search`` initialisations one after the other with ``run_scan`` and stops at the
+    first one that survives ``max_run_iter`` steps; the best run is the first one reaching the running maximum of ``N``.
+    Here all initialisations run at once (statistics only), the loop's stopping index and best index are read off ``N``,
+    and only the best initialisation is re-simulated with its trajectory.  Returns ``(best_run, i)`` like the reference.
+    """
+    from . import initializations as leniax_init
+    wp = config['world_params']
+    nb_channels, R = wp['nb_channels'], wp['R']
+    world_size = list(config['render_params']['world_size'])
+    kernels_params = config['kernels_params']
+    nb_init_search = config['run_params']['nb_init_search']
+    max_run_iter = config['run_params']['max_run_iter']
+    K, mapping = leniax_kernels.get_kernels_and_mapping(kernels_params, world_size, nb_channels, R, fft, device=device)
+    dev = K.device
+    gf_params, weights = mapping.get_gf_params(dev), mapping.get_kernels_weight_per_channel(dev)
+    T = torch.tensor(float(wp['T']), dtype=torch.float32, device=dev)
+    update_fn = build_update_fn(K.shape, mapping, wp.get('get_state_fn_slug', 'v1'), wp.get('weighted_average', True), fft)
+    stats_fn = leniax_stat.build_compute_stats_fn(wp, config['render_params'])
+    rng_key, noises = leniax_init.register[config['algo']['init_slug']](rng_key, nb_channels * nb_init_search, world_size, R,
+                                                                         kernels_params[0]['gf_params'], device=dev)
+    all_cells0 = noises.reshape([nb_init_search, 1, nb_channels] + world_size).to(torch.float32)  # one world per "run_scan"
+    stats, _ = leniax_runner.run_scan_mem_optimized(rng_key, all_cells0.reshape([1, nb_init_search, nb_channels] + world_size), K[None],
+                                                    gf_params[None], weights[None], T.reshape(1), max_run_iter, R, update_fn, stats_fn)
+    N = stats['N'][0].cpu()
+    survivors = torch.nonzero(N >= max_run_iter).flatten()
+    i_stop = int(survivors[0]) if len(survivors) else nb_init_search - 1  # where the reference's loop breaks
+    best = int(torch.argmax(N[:i_stop + 1]))  # first index reaching the running maximum
+    best_run: Dict = {}
+    if float(N[best]) > 0:  # the reference keeps {} when no run survives its first step (current_max < N is strict)
+        all_cells, _, _, all_stats = leniax_runner.run_scan(rng_key, all_cells0[best], K, gf_params, weights, T, max_run_iter, R,
+                                                             update_fn, stats_fn)
+        best_run = {'N': all_stats['N'], 'all_cells': all_cells, 'all_stats': all_stats}
+    return best_run, i_stop

@@ -700,3 +700,34 @@ def test_generic_kernels_early_stop_and_old_vs_new(golden_dir):
                             np.float32(ocfg['world_params']['T']), steps, lo.build_update_fn(om),
                             lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), False)
     assert N.tolist() == ostats['N'].tolist()
+
+
+def test_search_for_init_and_multi_init_and_run(golden_dir):
+    """Callers of the scan (helpers.py:192-237, 318-397): search_for_init returns the first initialisation reaching the running
+    maximum of N together with the loop's stopping index; multi_init_and_run equals per-configuration init_and_run."""
+    from leniax_b200 import initializations
+    cfg, _ = _setup(golden_dir, 'orbium-test', 140)
+    cfg['run_params']['nb_init_search'] = 12
+    cfg['algo'] = dict(cfg.get('algo', {}), init_slug='perlin')
+    key = initializations.RngKey(4)
+    best, i_stop = helpers.search_for_init(key, copy.deepcopy(cfg), device=DEV)
+    # the same noises through the batched statistics-only path
+    K, mapping = kernels.get_kernels_and_mapping(copy.deepcopy(cfg['kernels_params']), [128, 128], 1, 13, device=DEV)
+    _, noises = initializations.perlin(key, 12, [128, 128], 13, cfg['kernels_params'][0]['gf_params'], device=DEV)
+    ufn = helpers.build_update_fn(K.shape, mapping)
+    sfn = statistics.build_compute_stats_fn(cfg['world_params'], cfg['render_params'])
+    stats, _ = runner.run_scan_mem_optimized(None, noises.reshape(1, 12, 1, 128, 128), K[None], mapping.get_gf_params(DEV)[None],
+                                             mapping.get_kernels_weight_per_channel(DEV)[None], torch.tensor([10.], device=DEV), 140, 13, ufn, sfn)
+    N = stats['N'][0].cpu().numpy()
+    surv = np.nonzero(N >= 140)[0]
+    assert i_stop == (int(surv[0]) if len(surv) else 11)
+    assert float(best['N']) == float(N[:i_stop + 1].max())
+    assert best['all_cells'].shape == (140, 1, 1, 128, 128)
+    # multi_init_and_run: two parameter variants of the fixture in one launch
+    cfg2 = copy.deepcopy(cfg)
+    cfg2['kernels_params'][0]['gf_params'] = [0.16, 0.016]
+    mc, mf, mp, ms = helpers.multi_init_and_run(None, cfg, [cfg, cfg2], True, True, device=DEV)
+    for j, c in enumerate((cfg, cfg2)):
+        sc = helpers.init_and_run(None, c, with_jit=True, device=DEV)[0]
+        assert torch.equal(mc[j], sc)
+    assert ms['N'].shape == (2, )
