@@ -129,9 +129,13 @@ __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
     const int pairs = g.slab_rows / 2, A2 = g.A2, half = g.half;
     const size_t row0 = (size_t)slab * g.slab_rows;
     const float* src = P.state + (((size_t)w * P.C + c) * g.rows + row0) * A2;
-    for (int i = threadIdx.x; i < pairs * A2; i += blockDim.x) {
+    for (int i = threadIdx.x * 4; i < pairs * A2; i += blockDim.x * 4) {  // 128-bit loads of both rows of the pair
         const int pr = i >> g.logA2, n = i & (A2 - 1);
-        z[i] = make_float2(src[(size_t)(2 * pr) * A2 + n], src[(size_t)(2 * pr + 1) * A2 + n]);
+        const float4 ra = *reinterpret_cast<const float4*>(src + (size_t)(2 * pr) * A2 + n);
+        const float4 rb = *reinterpret_cast<const float4*>(src + (size_t)(2 * pr + 1) * A2 + n);
+        float4* zp = reinterpret_cast<float4*>(z + i);
+        zp[0] = make_float4(ra.x, rb.x, ra.y, rb.y);
+        zp[1] = make_float4(ra.z, rb.z, ra.w, rb.w);
     }
     __syncthreads();
     block_fft<false, false>(z, A2, g.logA2, 1, pairs, A2, P.tw);
@@ -254,7 +258,7 @@ struct PassCArgs {
     int state_fn, mean;
     int gf_id[MAX_K];
 };
-__global__ void __launch_bounds__(TPB) pass_c_kernel(PassCArgs P) {
+__global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red[NP_T][TPB / 32];
     const Geom& g = P.g;
@@ -277,9 +281,9 @@ __global__ void __launch_bounds__(TPB) pass_c_kernel(PassCArgs P) {
         const float2* src = P.pot_spec + (((size_t)w * P.K + k) * g.rows + row0) * half;
         __syncthreads();
         if (plane) {
-            for (int i = threadIdx.x; i < R * half; i += blockDim.x) {
-                const int m1 = i / half, kk = i - m1 * half;
-                pl[(size_t)brev_n(m1, g.logA1) * half + kk] = src[i];
+            for (int m1 = threadIdx.x / 64; m1 < R; m1 += blockDim.x / 64) {  // rows of `half` values, no integer division
+                const int dst_row = brev_n(m1, g.logA1);
+                for (int kk = threadIdx.x & 63; kk < half; kk += 64) pl[(size_t)dst_row * half + kk] = src[(size_t)m1 * half + kk];
             }
             __syncthreads();
             block_fft<true, true>(pl, g.A1, g.logA1, half, half, 1, P.tw);
@@ -301,16 +305,31 @@ __global__ void __launch_bounds__(TPB) pass_c_kernel(PassCArgs P) {
         float wk[MAX_C];
 #pragma unroll
         for (int c = 0; c < MAX_C; ++c) wk[c] = c < P.C ? P.weights[((size_t)sol * P.C + c) * P.K + k] : 0.f;
-        for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) {
+        // four consecutive cells of a row per thread and iteration: 128-bit shared / global accesses, loads in flight together
+        for (int i = threadIdx.x * 4; i < slab_cells; i += blockDim.x * 4) {
             const int r = i >> g.logA2, n = i & (A2 - 1);
-            const float2 zz = z[(size_t)(r >> 1) * A2 + n];
-            const float pot = (r & 1) ? zz.y : zz.x;
-            acc[3] += pot > EPS ? 1.f : 0.f;
-            if (pout) pout[i] = pot;
-            const float gv = growth_dyn<true>(P.gf_id[k], pot, gc);
+            const float4* zp = reinterpret_cast<const float4*>(z + (size_t)(r >> 1) * A2 + n);
+            const float4 z01 = zp[0], z23 = zp[1];
+            const bool odd = r & 1;
+            const float pot[4] = {odd ? z01.y : z01.x, odd ? z01.w : z01.z, odd ? z23.y : z23.x, odd ? z23.w : z23.z};
+            float gv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc[3] += pot[e] > EPS ? 1.f : 0.f;
+                gv[e] = growth_dyn<true>(P.gf_id[k], pot[e], gc);
+            }
+            if (pout) *reinterpret_cast<float4*>(pout + i) = make_float4(pot[0], pot[1], pot[2], pot[3]);
 #pragma unroll
             for (int c = 0; c < MAX_C; ++c)
-                if (c < P.C && wk[c] != 0.f) field[(size_t)c * slab_cells + i] += wk[c] * gv;
+                if (c < P.C && wk[c] != 0.f) {
+                    float4* fp = reinterpret_cast<float4*>(field + (size_t)c * slab_cells + i);
+                    float4 f = *fp;
+                    f.x += wk[c] * gv[0];
+                    f.y += wk[c] * gv[1];
+                    f.z += wk[c] * gv[2];
+                    f.w += wk[c] * gv[3];
+                    *fp = f;
+                }
         }
     }
     __syncthreads();
@@ -324,37 +343,53 @@ __global__ void __launch_bounds__(TPB) pass_c_kernel(PassCArgs P) {
         float* cout = P.cells_out ? P.cells_out + (traj * P.C + c) * g.cells + row0 * A2 : nullptr;
         float* fout = P.field_out ? P.field_out + (traj * P.C + c) * g.cells + row0 * A2 : nullptr;
         float m00 = 0.f;
-        for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) {
-            const int r = i >> g.logA2, n = i & (A2 - 1);
+#pragma unroll 2
+        for (int i = threadIdx.x * 4; i < slab_cells; i += blockDim.x * 4) {
+            const int r = i >> g.logA2, n0 = i & (A2 - 1);
             const size_t grow = row0 + r;            // global row index = l * A1 + a1
-            float f = field[(size_t)c * slab_cells + i];
-            if (P.mean) f = f / wsum;
-            const float a = st[i];
-            if (cout) cout[i] = a;
-            if (fout) fout[i] = f;
-            st[i] = state_update_dyn<true>(P.state_fn, a, f, dt);
-            // coordinates of this cell in the rolled (centred) world, statistics.py:28-33 + utils.py:269-293
+            const float4 fv = *reinterpret_cast<const float4*>(field + (size_t)c * slab_cells + i);
+            const float4 av = *reinterpret_cast<const float4*>(st + i);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            float f4[4] = {fv.x, fv.y, fv.z, fv.w};
+            float n4[4];
+            // coordinates of these cells in the rolled (centred) world, statistics.py:28-33 + utils.py:269-293
             const int i0 = g.nd == 3 ? (int)(grow >> g.logA1) : (int)grow;
-            const int i1 = g.nd == 3 ? (int)(grow & (g.A1 - 1)) : n;
-            const float gp = fmaxf(f, 0.f);
-            m00 += a;
-            acc[0] += a > EPS ? 1.f : 0.f;
-            acc[1] += gp;
-            acc[2] += gp > EPS ? 1.f : 0.f;
             const float x0 = (float)(((i0 - cr.shift[0]) & (g.dims[0] - 1)) - g.dims[0] / 2);
-            const float x1 = (float)(((i1 - cr.shift[1]) & (g.dims[1] - 1)) - g.dims[1] / 2);
-            acc[4] += a * x0;
-            acc[4 + MAXD] += a * x0 * x0;
-            acc[4 + 2 * MAXD] += gp * x0;
-            acc[5] += a * x1;
-            acc[5 + MAXD] += a * x1 * x1;
-            acc[5 + 2 * MAXD] += gp * x1;
-            if (g.nd == 3) {
-                const float x2 = (float)(((n - cr.shift[2]) & (g.dims[2] - 1)) - g.dims[2] / 2);
-                acc[6] += a * x2;
-                acc[6 + MAXD] += a * x2 * x2;
-                acc[6 + 2 * MAXD] += gp * x2;
+            const float x1row = (float)((((int)(grow & (g.A1 - 1)) - cr.shift[1]) & (g.dims[1] - 1)) - g.dims[1] / 2);  // 3-D only
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int n = n0 + e;
+                float f = f4[e];
+                if (P.mean) f = f / wsum;
+                f4[e] = f;
+                const float a = a4[e];
+                n4[e] = state_update_dyn<true>(P.state_fn, a, f, dt);
+                const float gp = fmaxf(f, 0.f);
+                m00 += a;
+                acc[0] += a > EPS ? 1.f : 0.f;
+                acc[1] += gp;
+                acc[2] += gp > EPS ? 1.f : 0.f;
+                acc[4] += a * x0;
+                acc[4 + MAXD] += a * x0 * x0;
+                acc[4 + 2 * MAXD] += gp * x0;
+                if (g.nd == 3) {
+                    const float x2 = (float)(((n - cr.shift[2]) & (g.dims[2] - 1)) - g.dims[2] / 2);
+                    acc[5] += a * x1row;
+                    acc[5 + MAXD] += a * x1row * x1row;
+                    acc[5 + 2 * MAXD] += gp * x1row;
+                    acc[6] += a * x2;
+                    acc[6 + MAXD] += a * x2 * x2;
+                    acc[6 + 2 * MAXD] += gp * x2;
+                } else {
+                    const float x1 = (float)(((n - cr.shift[1]) & (g.dims[1] - 1)) - g.dims[1] / 2);
+                    acc[5] += a * x1;
+                    acc[5 + MAXD] += a * x1 * x1;
+                    acc[5 + 2 * MAXD] += gp * x1;
+                }
             }
+            *reinterpret_cast<float4*>(st + i) = make_float4(n4[0], n4[1], n4[2], n4[3]);
+            if (cout) *reinterpret_cast<float4*>(cout + i) = av;
+            if (fout) *reinterpret_cast<float4*>(fout + i) = make_float4(f4[0], f4[1], f4[2], f4[3]);
         }
 #pragma unroll
         for (int cc = 0; cc < MAX_C; ++cc)
