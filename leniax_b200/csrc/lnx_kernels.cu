@@ -1480,10 +1480,15 @@ static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
     g->tc = tc;
     return true;
 }
-static size_t smem_a(const Geom& g) { return ((size_t)(g.slab_rows / 2) * g.A2 + (g.nd == 3 ? (size_t)g.A1 * g.half : 0)) * sizeof(float2); }
-static size_t smem_b(const Geom& g, bool two_buf = true) { return (two_buf ? 2 : 1) * (size_t)g.L * g.tc * sizeof(float2); }
+static size_t tw_bytes(int logn) { return ((size_t)1 << (logn - 1)) * sizeof(float2); }  // shared-memory twiddle table of one pass
+static int log_inner(const Geom& g) { return g.logA2 > g.logA1 ? g.logA2 : g.logA1; }
+static size_t smem_a(const Geom& g) {
+    return ((size_t)(g.slab_rows / 2) * g.A2 + (g.nd == 3 ? (size_t)g.A1 * g.half : 0)) * sizeof(float2) + tw_bytes(log_inner(g));
+}
+static size_t smem_b(const Geom& g, bool two_buf = true) { return (two_buf ? 2 : 1) * (size_t)g.L * g.tc * sizeof(float2) + tw_bytes(g.logL); }
 static size_t smem_c(const Geom& g, int C) {
-    return ((size_t)g.slab_rows * g.half + (size_t)(g.slab_rows / 2) * g.A2) * sizeof(float2) + (size_t)C * g.slab_rows * g.A2 * sizeof(float);
+    return ((size_t)g.slab_rows * g.half + (size_t)(g.slab_rows / 2) * g.A2) * sizeof(float2) + (size_t)C * g.slab_rows * g.A2 * sizeof(float) +
+           tw_bytes(log_inner(g));
 }
 constexpr size_t SMEM_LIMIT = 220 * 1024;  // dynamic part; pass C also has ~1 KB of static shared memory
 

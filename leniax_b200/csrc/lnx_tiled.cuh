@@ -48,7 +48,7 @@ static_assert((1 << LOG_NMAX) == NMAX, "LOG_NMAX");
 
 // one pass of LOGR stages; lsp = log2 of the smallest span of the pass
 template <bool INV, bool LF, int LOGR>
-__device__ __forceinline__ void radix_pass(float2* s, int n, int logn, int is, int nl, int js, const float2* __restrict__ tw, int lsp) {
+__device__ __forceinline__ void radix_pass(float2* s, int n, int logn, int is, int nl, int js, const float2* tw, int log_tw, int lsp) {
     constexpr int R = 1 << LOGR;
     const int per_line = n >> LOGR, total = per_line * nl;
     const int sp = 1 << lsp;
@@ -72,11 +72,11 @@ __device__ __forceinline__ void radix_pass(float2* s, int n, int logn, int is, i
             // forward: largest span first; inverse: smallest span first
             const int lh = INV ? j : LOGR - 1 - j;  // log2 of the pair distance in units of m
             const int hs = 1 << lh;
-            const int tshift = LOG_NMAX - 1 - (lsp + lh);  // twiddle index = pos * NMAX / (2 * span), span = sp << lh
+            const int tshift = log_tw - 1 - (lsp + lh);  // twiddle index = pos * 2^log_tw / (2 * span), span = sp << lh
 #pragma unroll
             for (int b2 = 0; b2 < R / 2; ++b2) {  // fixed trip count: every register index below is a compile-time constant
                 const int u = b2 & (hs - 1), lo = ((b2 >> lh) << (lh + 1)) + u, hi = lo + hs;
-                const float2 w = __ldg(tw + ((p + u * sp) << tshift));
+                const float2 w = tw[(p + u * sp) << tshift];
                 if (!INV) {
                     const float2 d = csub(x[lo], x[hi]);
                     x[lo] = cadd(x[lo], x[hi]);
@@ -92,18 +92,24 @@ __device__ __forceinline__ void radix_pass(float2* s, int n, int logn, int is, i
         for (int m = 0; m < R; ++m) base[m * st] = x[m];
     }
 }
+// copy the part of the master table an FFT of length 2^logn needs into shared memory: stw[k] = (cos, sin)(2 pi k / 2^logn),
+// k < 2^(logn-1).  (The butterflies read 7 twiddles per radix-8 group: from L1/L2 that was the top stall of every pass.)
+__device__ __forceinline__ void load_twiddles(float2* stw, int logn, const float2* __restrict__ tw) {
+    const int cnt = 1 << (logn - 1), sh = LOG_NMAX - logn;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) stw[k] = __ldg(tw + (k << sh));
+}
 template <bool INV, bool LF>
-__device__ void block_fft(float2* s, int n, int logn, int is, int nl, int js, const float2* __restrict__ tw) {
+__device__ void block_fft(float2* s, int n, int logn, int is, int nl, int js, const float2* tw, int log_tw) {
     int done = 0;
     while (done < logn) {
         const int r = logn - done >= 3 ? 3 : logn - done;
         const int lsp = INV ? done : logn - done - r;
         if (r == 3)
-            radix_pass<INV, LF, 3>(s, n, logn, is, nl, js, tw, lsp);
+            radix_pass<INV, LF, 3>(s, n, logn, is, nl, js, tw, log_tw, lsp);
         else if (r == 2)
-            radix_pass<INV, LF, 2>(s, n, logn, is, nl, js, tw, lsp);
+            radix_pass<INV, LF, 2>(s, n, logn, is, nl, js, tw, log_tw, lsp);
         else
-            radix_pass<INV, LF, 1>(s, n, logn, is, nl, js, tw, lsp);
+            radix_pass<INV, LF, 1>(s, n, logn, is, nl, js, tw, log_tw, lsp);
         __syncthreads();
         done += r;
     }
@@ -125,6 +131,9 @@ __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
     const Geom& g = P.g;
     float2* z = reinterpret_cast<float2*>(smem_raw);                      // [pairs][A2]
     float2* pl = z + (size_t)(g.slab_rows / 2) * g.A2;                    // [slab_rows][half] (3-D only)
+    const int log_tw = g.logA2 > g.logA1 ? g.logA2 : g.logA1;
+    float2* stw = pl + (g.nd == 3 ? (size_t)g.A1 * g.half : 0);           // twiddles of the longest inner axis
+    load_twiddles(stw, log_tw, P.tw);
     const int slab = blockIdx.x, c = blockIdx.y, w = blockIdx.z;
     const int pairs = g.slab_rows / 2, A2 = g.A2, half = g.half;
     const size_t row0 = (size_t)slab * g.slab_rows;
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
         zp[1] = make_float4(ra.z, rb.z, ra.w, rb.w);
     }
     __syncthreads();
-    block_fft<false, false>(z, A2, g.logA2, 1, pairs, A2, P.tw);
+    block_fft<false, false>(z, A2, g.logA2, 1, pairs, A2, stw, log_tw);
     float2* dst = P.spec + (((size_t)w * P.C + c) * g.rows + row0) * half;
     const bool plane = g.nd == 3;
     for (int pr = 0; pr < pairs; ++pr)
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
     }
     if (plane) {
         __syncthreads();
-        block_fft<false, true>(pl, g.A1, g.logA1, half, half, 1, P.tw);  // along axis 1, `half` interleaved lines
+        block_fft<false, true>(pl, g.A1, g.logA1, half, half, 1, stw, log_tw);  // along axis 1, `half` interleaved lines
         for (int i = threadIdx.x; i < g.A1 * half; i += blockDim.x) {
             const int m1 = i / half, k = i - m1 * half;
             dst[i] = pl[(size_t)brev_n(m1, g.logA1) * half + k];
@@ -187,6 +196,8 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
     const long long M = g.spec / L;
     float2* F = reinterpret_cast<float2*>(smem_raw);
     float2* T = P.two_buf ? F + (size_t)L * tc : F;
+    float2* stw = F + (size_t)(P.two_buf ? 2 : 1) * L * tc;
+    load_twiddles(stw, g.logL, P.tw);
     const int c = blockIdx.y, w = blockIdx.z;
     const long long m0 = (long long)blockIdx.x * tc;
     const int wdt = (int)((M - m0) < tc ? (M - m0) : tc);
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
         F[i] = j < wdt ? src[(size_t)l * M + j] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    block_fft<false, true>(F, L, g.logL, tc, tc, 1, P.tw);
+    block_fft<false, true>(F, L, g.logL, tc, tc, 1, stw, g.logL);
     if (P.fwd_out) {
         float2* dst = P.fwd_out + ((size_t)w * P.C + c) * g.spec + m0;
         for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
             T[i] = v;
         }
         __syncthreads();
-        block_fft<true, true>(T, L, g.logL, tc, tc, 1, P.tw);
+        block_fft<true, true>(T, L, g.logL, tc, tc, 1, stw, g.logL);
         float2* dst = P.pot_spec + ((size_t)w * P.K + k) * g.spec + m0;
         for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
             const int l = i / tc, j = i - l * tc;
@@ -266,6 +277,9 @@ __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
     float2* pl = reinterpret_cast<float2*>(smem_raw);       // [R][half]
     float2* z = pl + (size_t)R * half;                       // [pairs][A2]
     float* field = reinterpret_cast<float*>(z + (size_t)pairs * A2);  // [C][R][A2]
+    const int log_tw = g.logA2 > g.logA1 ? g.logA2 : g.logA1;
+    float2* stw = reinterpret_cast<float2*>(field + (size_t)P.C * R * A2);
+    load_twiddles(stw, log_tw, P.tw);
     const int slab = blockIdx.x, w = blockIdx.z;
     const int sol = w / P.n_init, init = w - sol * P.n_init;
     const size_t row0 = (size_t)slab * R;
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
                 for (int kk = threadIdx.x & 63; kk < half; kk += 64) pl[(size_t)dst_row * half + kk] = src[(size_t)m1 * half + kk];
             }
             __syncthreads();
-            block_fft<true, true>(pl, g.A1, g.logA1, half, half, 1, P.tw);
+            block_fft<true, true>(pl, g.A1, g.logA1, half, half, 1, stw, log_tw);
         } else {
             for (int i = threadIdx.x; i < R * half; i += blockDim.x) pl[i] = src[i];
             __syncthreads();
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
             if (kk != 0 && kk != A2 / 2) z[(size_t)pr * A2 + brev_n(A2 - kk, g.logA2)] = make_float2(a.x + b.y, b.x - a.y);
         }
         __syncthreads();
-        block_fft<true, false>(z, A2, g.logA2, 1, pairs, A2, P.tw);
+        block_fft<true, false>(z, A2, g.logA2, 1, pairs, A2, stw, log_tw);
         const GfConst gc = gf_prepare(P.gf_id[k], P.gf_params[((size_t)sol * P.K + k) * 2], P.gf_params[((size_t)sol * P.K + k) * 2 + 1]);
         float* pout = P.potential_out ? P.potential_out + (traj * P.K + k) * g.cells + row0 * A2 : nullptr;
         float wk[MAX_C];
