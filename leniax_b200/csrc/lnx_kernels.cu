@@ -400,11 +400,16 @@ constexpr int TM_OFF_TW = TM_OFF_SCRATCH + SCRATCH_BYTES;
 constexpr int TM_OFF_XT = TM_OFF_TW + TW_BYTES;
 constexpr int TM_OFF_CTRL = TM_OFF_XT + XT_F4 * 16;
 struct TmCtrl {
+    // written by thread 0 at world start / by warp 7 at batch boundaries; kept in their own 16 bytes so that a vectorised read of
+    // them never touches the words warp 1 updates every step (compute-sanitizer racecheck flagged exactly that overlap)
     int world;
-    int shift0, shift1;  // total_shift_idx used by the next cell phase (advanced by warp 1)
     int stop;
     uint32_t tmem_base;
-    BatchCarry carry;    // statistics carry between batches (warp 7)
+    int pad0;
+    alignas(16) int shift0;  // total_shift_idx used by the next cell phase (advanced by warp 1)
+    int shift1;
+    int pad1[2];
+    alignas(16) BatchCarry carry;  // statistics carry between batches (warp 7)
 };
 constexpr int TM_SMEM = TM_OFF_CTRL + 160;
 static_assert(sizeof(TmCtrl) <= 160, "TmCtrl does not fit its shared-memory slot");
