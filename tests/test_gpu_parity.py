@@ -731,3 +731,50 @@ def test_search_for_init_and_multi_init_and_run(golden_dir):
         sc = helpers.init_and_run(None, c, with_jit=True, device=DEV)[0]
         assert torch.equal(mc[j], sc)
     assert ms['N'].shape == (2, )
+
+
+@pytest.mark.parametrize('seed', [0, 1, 2, 3, 4, 5])
+def test_random_multichannel_configs_match_oracle(seed):
+    """Randomised structure through the generic kernels: C in 1..5 channels (C = 5 takes the older global-scratch kernel),
+    up to 9 kernels with random input / output channels (channels without any kernel, kernels sharing an input channel),
+    random smooth growth functions, kernel shapes and weights, mean or sum mixing, every state function; 6 steps of 3 worlds
+    with trajectory, statistics and N against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    C = int(rng.integers(1, 6))
+    nk = int(rng.integers(max(1, C - 1), 10))
+    gfs = ['poly_quad4', 'gaussian', 'gaussian_target', 'triangle', 'identity']
+    kfs = [('poly_quad', [4]), ('gauss_bump', [4]), ('gauss', [0.5, 0.15]), ('triangle', [0.5, 0.3])]
+    kp = []
+    for k in range(nk):
+        gf = gfs[int(rng.integers(len(gfs)))]
+        kf, kfp = kfs[int(rng.integers(len(kfs)))]
+        nb = int(rng.integers(1, 4))
+        params = [round(float(rng.uniform(.1, .4)), 4), round(float(rng.uniform(.02, .1)), 4)] if gf != 'identity' else [0., 1.]
+        kp.append(dict(k_slug='circle_2d', k_params=[round(float(rng.uniform(.5, 1.)), 3), [round(float(x), 3) for x in rng.uniform(.2, 1., nb)]],
+                       kf_slug=kf, kf_params=kfp, gf_slug=gf, gf_params=params, h=round(float(rng.uniform(.2, 1.)), 3),
+                       c_in=int(rng.integers(C)), c_out=int(rng.integers(C))))
+    sf = ['v1', 'v2', 'simple'][seed % 3]
+    average = bool(seed % 2 == 0)
+    if average:  # weighted_mean divides by the row sum: give every channel at least one incoming kernel
+        for c in range(C):
+            kp[c % nk]['c_out'] = c if c < nk else kp[c % nk]['c_out']
+        if nk < C:
+            average = False
+    R, T, steps, n = 9, 7., 6, 3
+    state = (rng.random((n, C, 128, 128), dtype=np.float32) * 0.6).astype(np.float32)
+    K, mapping = kernels.get_kernels_and_mapping(copy.deepcopy(kp), [128, 128], C, R, device=DEV)
+    ufn = helpers.build_update_fn(K.shape, mapping, sf, average, True)
+    sfn = statistics.build_compute_stats_fn({'R': R, 'T': T}, {'world_size': [128, 128]})
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    cells, field, pot, stats = runner.run_scan(None, torch.from_numpy(state).to(DEV), K, gf, w, torch.tensor(T), steps, R, ufn, sfn)
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(kp), [128, 128], C, R)
+    oc, of, op, ostats = lo.run_scan(state, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(T), steps,
+                                     lo.build_update_fn(om, sf, average), lo.build_compute_stats_fn({'R': R, 'T': T}, {'world_size': [128, 128]}))
+    scale = max(1., float(np.abs(oc).max()))  # 'simple' / 'v2' states are not clipped
+    assert np.abs(pot.cpu().numpy() - op).max() < 2e-5 * scale, (C, nk, sf, average)
+    # growth widths down to s = 0.02 give slopes of 50-100 per unit of potential: a 2e-6 potential difference is a 2e-4 field one
+    assert np.abs(field.cpu().numpy() - of).max() < 4e-4 * scale
+    assert np.abs(cells.cpu().numpy() - oc).max() < 2e-4 * scale
+    np.testing.assert_allclose(stats['mass'].cpu().numpy(), ostats['mass'], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(stats['channel_mass'].cpu().numpy(), ostats['channel_mass'], rtol=2e-5, atol=2e-5)
+    assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()
