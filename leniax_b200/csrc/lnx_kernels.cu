@@ -558,14 +558,14 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
             float kbuf[2][8];
             tm::ld8(kt_addr, kbuf[0]);  // first multiplier chunk: lands during the column transforms
             phase3_load_fft(tid, R, W);
-            if (tid < 32) {  // warp 0 owns the packed DC|Nyquist column
-                phase3_col0_stash(tid, R, scratch);
+            if (tid < 32) phase3_col0_stash(tid, R, scratch);  // warp 0 owns the packed DC|Nyquist column (threads 0..3)
+            phase3_multiply_tm(R, kt_addr, kbuf);              // (their plain products are overwritten by the fetch below)
+            if (tid < 32) {  // the stash has landed behind the multiply; G' = G Kp + conj(G[-m]) Kq through the scratch
                 __syncwarp();
                 phase3_col0_compute(tid, scratch, Kpq);
                 __syncwarp();
+                phase3_col0_fetch(tid, R, scratch);
             }
-            phase3_multiply_tm(R, kt_addr, kbuf);
-            if (tid < 32) phase3_col0_fetch(tid, R, scratch);
             phase3_ifft_store(tid, R, W);
             __syncthreads();
             if (warp == 7 && t > 0 && (t & (RING_ROWS - 1)) == 0) {  // rows t-32 .. t-1 are complete

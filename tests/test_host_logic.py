@@ -140,3 +140,19 @@ def test_host_heuristics_kats():  # tests/test_statistics.py:14-50
     st = {'mass': mass, 'channel_mass': mass[..., None].clone(), 'mass_volume': torch.ones(T, N)}
     ref = lo.check_heuristics({k: v.numpy() for k, v in st.items()})
     np.testing.assert_array_equal(statistics.check_heuristics(st).numpy(), ref)
+
+
+def test_grid_archive_index_matches_oracle_restatement():
+    """qd.grid_archive_index (torch, any device) against the oracle's restatement of ribs 0.4.0 GridArchive.get_index, including
+    values on and beyond the domain borders."""
+    import numpy as np
+    import torch
+    from leniax_b200 import qd
+    from oracle import lenia_oracle as lo
+    rng = np.random.default_rng(0)
+    feats = np.concatenate([rng.uniform(-0.2, 1.2, (500, 2)), [[0., 0.], [1., 1.], [0.05, 0.999999], [0.5, 0.05 * 7]]])
+    dom, shape = [[0., 1.], [0., 1.]], [20, 20]
+    got = qd.grid_archive_index(torch.from_numpy(feats), shape, dom).numpy()
+    want = lo.grid_archive_index(feats, shape, dom)
+    assert (got == want).all()
+    assert got.min() >= 0 and got.max() <= 19

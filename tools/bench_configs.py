@@ -101,9 +101,12 @@ def config_c(steps):
     sfn = statistics.build_compute_stats_fn({'R': 13, 'T': 10}, {'world_size': [128, 128]})
     args = (torch.stack(cells), torch.stack(Ks), torch.stack(gfs), torch.stack(ws), torch.full((n_sols, ), 10., device=DEV))
     ms, out = timed(lambda: runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn), reps=2)
+    ms_early, _ = timed(lambda: runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn, early_stop=True), reps=2)
     cu = n_sols * n_init * 128 * 128 * steps
     tfl = cu * 486 / (ms * 1e-3) / 1e12
     return {'config': 'C: 3 channels 6 kernels 128x128, 16 solutions x 128 perlin inits, generic resident kernel', 'steps': steps, 'ms': ms,
+            'early_stop_ms': ms_early, 'early_stop_note': 'extension (early_stop=True): a world stops once its stop criteria fired and 128 rows exist; '
+            'everything qd.update_individuals reads is unchanged.  Not used for the throughput figure (it skips steps).',
             'cell_updates_per_s': cu / (ms * 1e-3), 'roofline': {'bound': 'fp32', 'flop_per_cell_update': 486, 'achieved_tflops': tfl,
                                                                'peak_tflops': fp32_peak(), 'frac': tfl / fp32_peak()},
             'mean_N': float(out[0]['N'].mean())}
