@@ -192,7 +192,7 @@ struct PassBArgs {
 __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Geom& g = P.g;
-    const int L = g.L, tc = g.tc;
+    const int L = g.L, tc = g.tc, ltc = __ffs(g.tc) - 1;  // tc is a power of two
     const long long M = g.spec / L;
     float2* F = reinterpret_cast<float2*>(smem_raw);
     float2* T = P.two_buf ? F + (size_t)L * tc : F;
@@ -202,16 +202,17 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
     const long long m0 = (long long)blockIdx.x * tc;
     const int wdt = (int)((M - m0) < tc ? (M - m0) : tc);
     const float2* src = P.spec + ((size_t)w * P.C + c) * g.spec + m0;
-    for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
-        const int l = i / tc, j = i - l * tc;
-        F[i] = j < wdt ? src[(size_t)l * M + j] : make_float2(0.f, 0.f);
+#pragma unroll 8
+    for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {  // independent loads: keep eight in flight per thread
+        const int l = i >> ltc, j = i & (tc - 1);
+        F[i] = j < wdt ? __ldg(src + (size_t)l * M + j) : make_float2(0.f, 0.f);
     }
     __syncthreads();
     block_fft<false, true>(F, L, g.logL, tc, tc, 1, stw, g.logL);
     if (P.fwd_out) {
         float2* dst = P.fwd_out + ((size_t)w * P.C + c) * g.spec + m0;
         for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
-            const int m = i / tc, j = i - m * tc;
+            const int m = i >> ltc, j = i & (tc - 1);
             if (j < wdt) dst[(size_t)m * M + j] = F[(size_t)brev_n(m, g.logL) * tc + j];
         }
         return;
@@ -220,8 +221,9 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
     for (int k = 0; k < P.K; ++k) {
         if (P.c_in[k] != c) continue;
         const float2* kt = P.ktab + ((size_t)sol * P.K + k) * g.spec + m0;
+#pragma unroll 8
         for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
-            const int pos = i / tc, j = i - pos * tc;
+            const int pos = i >> ltc, j = i & (tc - 1);
             float2 v = make_float2(0.f, 0.f);
             if (j < wdt) {
                 const float2 f = F[i], q = __ldg(kt + (size_t)brev_n(pos, g.logL) * M + j);
@@ -232,8 +234,9 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
         __syncthreads();
         block_fft<true, true>(T, L, g.logL, tc, tc, 1, stw, g.logL);
         float2* dst = P.pot_spec + ((size_t)w * P.K + k) * g.spec + m0;
+#pragma unroll 8
         for (int i = threadIdx.x; i < L * tc; i += blockDim.x) {
-            const int l = i / tc, j = i - l * tc;
+            const int l = i >> ltc, j = i & (tc - 1);
             if (j < wdt) dst[(size_t)l * M + j] = T[i];
         }
         __syncthreads();
@@ -302,7 +305,8 @@ __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
             __syncthreads();
             block_fft<true, true>(pl, g.A1, g.logA1, half, half, 1, stw, log_tw);
         } else {
-            for (int i = threadIdx.x; i < R * half; i += blockDim.x) pl[i] = src[i];
+#pragma unroll 8
+            for (int i = threadIdx.x; i < R * half; i += blockDim.x) pl[i] = __ldg(src + i);
             __syncthreads();
         }
         // retangle: Z'[k] = A + iB, Z'[N-k] = conj(A) + i conj(B), stored at bit-reversed positions for the DIT
