@@ -778,3 +778,26 @@ def test_random_multichannel_configs_match_oracle(seed):
     np.testing.assert_allclose(stats['mass'].cpu().numpy(), ostats['mass'], rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(stats['channel_mass'].cpu().numpy(), ostats['channel_mass'], rtol=2e-5, atol=2e-5)
     assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()
+
+
+@pytest.mark.parametrize('steps', [1, 2, 31, 32, 33, 64, 65])
+def test_fused_kernel_row_batches_at_their_boundaries(golden_dir, steps):
+    """The TMEM kernel finalises its statistics 32 rows at a time (plus a flush): run lengths just below, at and just above the
+    batch size, several solutions with one initialisation each (multipliers reloaded into tensor memory per world)."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    n_sols = 3
+    worlds = torch.stack([torch.roll(cells[0], (11 * i, 5 * i), dims=(1, 2)) * (1. - 0.3 * i) for i in range(n_sols)])[:, None]  # [S, 1, 1, H, W]
+    gfs = torch.stack([gf + torch.tensor([[0.002 * i, 0.]], device=DEV) for i in range(n_sols)])
+    T = torch.tensor([10., 9., 11.], device=DEV)
+    stats, final = runner.run_scan_mem_optimized(None, worlds, torch.stack([K] * n_sols), gfs, torch.stack([w] * n_sols), T, steps, 13, ufn, sfn)
+    assert stats['mass'].shape == (n_sols, steps, 1) and final.shape == worlds.shape
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(ocfg['kernels_params']), [128, 128], 1, 13)
+    for i in range(n_sols):
+        ost, ofin = lo.run_scan(worlds[i].cpu().numpy(), oK, gfs[i].cpu().numpy(), om.get_kernels_weight_per_channel(), np.float32(T[i].item()),
+                                steps, lo.build_update_fn(om), lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), False)
+        assert stats['N'][i].cpu().numpy().tolist() == ost['N'].tolist()
+        for k in ('mass', 'mass_volume', 'growth', 'mass_speed', 'inertia'):
+            np.testing.assert_allclose(stats[k][i].cpu().numpy(), ost[k], atol=STAT_TOL[k] * 2, err_msg=k)
+        assert np.abs(final[i].cpu().numpy() - ofin).max() < 2e-5
