@@ -287,10 +287,10 @@ LNX_HD int col0_partner_rt(bool b0, int s) {
     return (1 - h) * 16 + (15 - pos);
 }
 LNX_HD void phase3_col0_stash(int tid, const Regs& R, float2* scratch) {
-    if (tid < 4) {
-        float4* d = reinterpret_cast<float4*>(scratch + tid * 32);
+    if (tid < 4) {  // 64-bit stores straight from the (re, im) register pairs: 128-bit ones cost four register moves each
+        float2* d = scratch + tid * 32;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) d[i] = make_float4(R.v[2 * i].x, R.v[2 * i].y, R.v[2 * i + 1].x, R.v[2 * i + 1].y);
+        for (int i = 0; i < 32; ++i) d[i] = R.v[i];
     }
 }
 LNX_HD void phase3_col0_compute(int tid, float2* scratch, const float4* Kpq) {  // tid < 32
@@ -313,13 +313,9 @@ LNX_HD void phase3_col0_compute(int tid, float2* scratch, const float4* Kpq) {  
 }
 LNX_HD void phase3_col0_fetch(int tid, Regs& R, const float2* scratch) {
     if (tid < 4) {
-        const float4* d = reinterpret_cast<const float4*>(scratch + 128 + tid * 32);
+        const float2* d = scratch + 128 + tid * 32;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 v = d[i];
-            R.v[2 * i] = make_float2(v.x, v.y);
-            R.v[2 * i + 1] = make_float2(v.z, v.w);
-        }
+        for (int i = 0; i < 32; ++i) R.v[i] = d[i];
     }
 }
 LNX_HD void phase3_multiply(int tid, Regs& R, const float4* Kt) { p3_mul_generic<0>(R, Kt, tid); }
