@@ -38,8 +38,10 @@ def init(config: Dict, use_init_cells: bool = True, fft: bool = True, device=Non
     assert len(world_size) == nb_dims
     assert nb_channels > 0
     raw_cells = leniax_loader.load_raw_cells(config, use_init_cells)
-    if wp.get('scale', 1.) != 1.:
-        raise NotImplementedError('world_params.scale != 1 (scipy.ndimage.zoom, helpers.py:59-66) is outside the accelerated path')
+    scale = wp.get('scale', 1.)
+    if scale != 1.:  # helpers.py:58-66: nearest-neighbour zoom of every channel; the new R is used by the kernels and the statistics
+        raw_cells = torch.stack([leniax_utils.zoom_nearest(raw_cells[i], scale) for i in range(nb_channels)]).to(torch.float32)
+        wp['R'] *= scale
     if raw_cells.dim() > 1 + nb_dims:
         init_cells = create_init_cells(world_size, nb_channels, raw_cells)
     else:

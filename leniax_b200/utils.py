@@ -116,3 +116,15 @@ def merge_cells(cells: torch.Tensor, other_cells: torch.Tensor, offset: List[int
         start = int(max((cells.shape[i] - other_cells.shape[i]) // 2 + offset[i], 0))
         pads += [start, int(cells.shape[i] - other_cells.shape[i] - start)]
     return cells + torch.nn.functional.pad(other_cells.to(cells.dtype), pads)
+
+
+def zoom_nearest(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """``scipy.ndimage.zoom(x, scale, order=0)`` (the call of leniax/helpers.py:61): output size ``round(n * scale)`` per axis,
+    output index ``i`` reads input index ``floor(i * (n_in - 1) / (n_out - 1) + 0.5)``.  Checked bit for bit against scipy in
+    tests/test_host_logic.py."""
+    out_shape = [int(round(n * scale)) for n in x.shape]
+    idx = []
+    for n_in, n_out in zip(x.shape, out_shape):
+        c = torch.arange(n_out, dtype=torch.float64) * ((n_in - 1) / (n_out - 1)) if n_out > 1 else torch.zeros(1, dtype=torch.float64)
+        idx.append(torch.floor(c + 0.5).long().clamp(0, n_in - 1).to(x.device))
+    return x[torch.meshgrid(*idx, indexing='ij')]

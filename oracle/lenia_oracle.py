@@ -793,11 +793,15 @@ def merge_cells(cells: np.ndarray, other: np.ndarray, offset=None) -> np.ndarray
 
 
 def init(config: Dict, use_init_cells: bool = True, fft: bool = True, dtype=np.float32):
-    """helpers.py:35-88 (scale == 1 only) → (cells [1,C,*dims], K, mapping)."""
+    """helpers.py:35-88 → (cells [1,C,*dims], K, mapping).  Mutates config['world_params']['R'] when scale != 1, like the reference."""
     wp = config['world_params']
     world_size = list(config['render_params']['world_size'])
     raw_cells = load_raw_cells(config, use_init_cells)
-    assert wp.get('scale', 1.) == 1., 'scipy.ndimage.zoom path (helpers.py:59-66) is out of scope'
+    scale = wp.get('scale', 1.)
+    if scale != 1.:  # helpers.py:58-66
+        import scipy.ndimage
+        raw_cells = np.array([scipy.ndimage.zoom(raw_cells[i], scale, order=0) for i in range(wp['nb_channels'])], dtype=np.float32)
+        wp['R'] *= scale  # "the new R value will be used in the statistics" (helpers.py:65-66)
     if raw_cells.ndim > 1 + wp['nb_dims']:
         cells = raw_cells  # already [N, C, *dims]  (helpers.py:118-121)
     else:

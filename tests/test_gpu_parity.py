@@ -801,3 +801,18 @@ def test_fused_kernel_row_batches_at_their_boundaries(golden_dir, steps):
         for k in ('mass', 'mass_volume', 'growth', 'mass_speed', 'inertia'):
             np.testing.assert_allclose(stats[k][i].cpu().numpy(), ost[k], atol=STAT_TOL[k] * 2, err_msg=k)
         assert np.abs(final[i].cpu().numpy() - ofin).max() < 2e-5
+
+
+def test_scaled_world_matches_oracle(golden_dir):
+    """world_params.scale = 2 (helpers.py:58-66): initial cells zoomed x2, R doubled, 256 x 256 world (tiled engine)."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test', 6)
+    for c in (cfg, ocfg):
+        c['world_params']['scale'] = 2
+        c['render_params']['world_size'] = [256, 256]
+    cells, field, pot, stats = helpers.init_and_run(None, cfg, with_jit=True, device=DEV)
+    oc, of, op, ostats = lo.init_and_run(ocfg, with_jit=True)
+    assert cells.shape == (6, 1, 1, 256, 256)
+    assert np.abs(cells.cpu().numpy() - oc).max() < 1e-5
+    np.testing.assert_allclose(stats['mass'].cpu().numpy().reshape(-1), ostats['mass'].reshape(-1), atol=2e-5)
+    np.testing.assert_allclose(stats['mass_speed'].cpu().numpy().reshape(-1), ostats['mass_speed'].reshape(-1), atol=5e-4)
+    assert stats['N'].cpu().numpy().reshape(-1).tolist() == ostats['N'].tolist()

@@ -156,3 +156,18 @@ def test_grid_archive_index_matches_oracle_restatement():
     want = lo.grid_archive_index(feats, shape, dom)
     assert (got == want).all()
     assert got.min() >= 0 and got.max() <= 19
+
+
+def test_zoom_nearest_is_scipy_order0_zoom():
+    """utils.zoom_nearest restates scipy.ndimage.zoom(x, scale, order=0) (leniax/helpers.py:61)."""
+    import numpy as np
+    import scipy.ndimage
+    import torch
+    from leniax_b200 import utils
+    rng = np.random.default_rng(0)
+    for shape in [(20, 20), (17, 23), (5, 9), (20, 18, 7)]:
+        for sc in [2, 3, 4, 1.5, 0.5, 2.5]:
+            a = rng.random(shape).astype(np.float32)
+            ref = scipy.ndimage.zoom(a, sc, order=0)
+            got = utils.zoom_nearest(torch.from_numpy(a), sc).numpy()
+            assert ref.shape == got.shape and np.array_equal(ref, got), (shape, sc)
