@@ -169,3 +169,43 @@ def search_for_init(rng_key, config: Dict, fft: bool = True, device=None) -> Tup
                                                              update_fn, stats_fn)
         best_run = {'N': all_stats['N'], 'all_cells': all_cells, 'all_stats': all_stats}
     return best_run, i_stop
+
+
+def search_for_mutation(rng_key, config: Dict, nb_scale_for_stability: int = 1, use_init_cells: bool = True, fft: bool = True,
+                        mutation_rate: float = 1e-5, device=None) -> Tuple[Dict, int]:
+    """Search for a stable mutation (helpers.py:240-315): every gene gets Gaussian noise of std ``mutation_rate``, the mutated
+    configuration is simulated at ``nb_scale_for_stability`` scales (world size and ``scale`` doubled each time) and the one
+    with the most steps done over all scales wins; stops at the first one surviving everywhere.  ``rng_key`` is a
+    ``leniax_b200.initializations.RngKey`` (the Gaussian draws are torch's, not jax.random's: parity of the stream is
+    unpinned)."""
+    world_size = config['render_params']['world_size']
+    nb_mut_search = config['run_params']['nb_mut_search']
+    max_run_iter = config['run_params']['max_run_iter']
+    best_run: Dict = {}
+    current_max = 0
+    nb_genes = len(config['genotype'])
+    subkeys = rng_key.split(nb_mut_search * nb_genes + 1)[1:]
+    i = 0
+    for i in range(nb_mut_search):
+        copied_config = copy.deepcopy(config)
+        for gene_i, gene in enumerate(config['genotype']):
+            val = leniax_utils.get_param(copied_config, gene['key'])
+            noise = torch.randn((), generator=subkeys[i * nb_genes + gene_i].generator('cpu'), dtype=torch.float32)
+            leniax_utils.set_param(copied_config, gene['key'], float(val + float(noise) * mutation_rate))
+        total_iter_done, nb_iter_done = 0, 0
+        for scale_power in range(nb_scale_for_stability):
+            scaled_config = copy.deepcopy(copied_config)
+            scaled_config['render_params']['world_size'] = [ws * 2**scale_power for ws in world_size]
+            scaled_config['world_params']['scale'] = 2**scale_power
+            all_cells, _, _, stats_dict = init_and_run(rng_key, scaled_config, use_init_cells=use_init_cells, with_jit=True, fft=fft,
+                                                       device=device)
+            all_cells = all_cells[:, 0]
+            n = int(stats_dict['N'])
+            nb_iter_done = max(nb_iter_done, n)
+            total_iter_done += n
+        if current_max < total_iter_done:
+            current_max = total_iter_done
+            best_run = {'N': nb_iter_done, 'all_cells': all_cells, 'all_stats': stats_dict, 'config': copied_config}
+        if total_iter_done >= max_run_iter * nb_scale_for_stability:
+            break
+    return best_run, i

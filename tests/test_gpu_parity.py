@@ -816,3 +816,16 @@ def test_scaled_world_matches_oracle(golden_dir):
     np.testing.assert_allclose(stats['mass'].cpu().numpy().reshape(-1), ostats['mass'].reshape(-1), atol=2e-5)
     np.testing.assert_allclose(stats['mass_speed'].cpu().numpy().reshape(-1), ostats['mass_speed'].reshape(-1), atol=5e-4)
     assert stats['N'].cpu().numpy().reshape(-1).tolist() == ostats['N'].tolist()
+
+
+def test_search_for_mutation_two_scales(golden_dir):
+    """helpers.search_for_mutation (helpers.py:240-315): the Orbium survives at both scales (128 and 256), so the first mutation
+    is returned with the step count of one scale as N."""
+    from leniax_b200 import initializations
+    cfg, _ = _setup(golden_dir, 'orbium-test', 40)
+    cfg['run_params']['nb_mut_search'] = 3
+    cfg['genotype'] = [{'key': 'kernels_params.0.gf_params.0', 'domain': [0.1, 0.3], 'type': 'float'}]
+    best, i = helpers.search_for_mutation(initializations.RngKey(1), cfg, nb_scale_for_stability=2, device=DEV)
+    assert i == 0 and best['N'] == 40
+    assert abs(best['config']['kernels_params'][0]['gf_params'][0] - 0.15) < 1e-4
+    assert best['all_cells'].shape == (40, 1, 256, 256)
