@@ -157,6 +157,13 @@ int lnx_run_scan(const lnx_plan* plan, int32_t n_sols, int32_t n_init, int32_t m
 int lnx_compute_stats(const lnx_plan* plan, int32_t n_worlds, const float* cells, const float* field, const float* potential,
                       int32_t* total_shift_idx, float* mass_centroid, float* mass_angle, float* stats, float* channel_mass, void* stream);
 
+/* One step: replaces a call of the update_fn built by helpers.build_update_fn, i.e. core.update (leniax/core.py:13-49):
+ * state [n_worlds][C][dims...] -> state_out (same shape), field_out [n_worlds][C][dims...], potential_out [n_worlds][K][dims...].
+ * table: lnx_kernels_prepare() output for ONE solution; gf_params [K][2], weights [C][K], dt [1] (device).  Thin wrapper over
+ * lnx_run_scan with max_run_iter = 1 (its scratch is stream-ordered, cudaMallocAsync on `stream`). */
+int lnx_update(const lnx_plan* plan, int32_t n_worlds, const float* state, const void* table, const float* gf_params,
+               const float* weights, const float* dt, float* state_out, float* field_out, float* potential_out, void* stream);
+
 /* One step of core.update with the DIRECT-CONVOLUTION potential (leniax/core.py:105-146 get_potential, selected by
  * fft=False in helpers.build_get_potential_fn, helpers.py:464-488) followed by get_field / weighted mean-sum / get_state.
  * 2-D worlds of any size (desc->dims, no power-of-two restriction); desc also gives C, K, slot[], c_in[], gf_id[],

@@ -115,10 +115,8 @@ def update(rng_key, state, K, gf_params, kernels_weight_per_channel, dt, get_pot
                            nb_slots=get_potential_fn.nb_slots, state_fn=sfn.slug, weighted_average=get_field_fn.average,
                            R=1.0, stats_dt=1.0, device=dev)
     Kt = engine.as_device_tensor(K, torch.complex64, dev).reshape((1, get_potential_fn.nb_slots) + world_size)
-    res = plan.run_scan(state_t[None], Kt, engine.as_device_tensor(gf_params, torch.float32, dev)[None],
-                        engine.as_device_tensor(kernels_weight_per_channel, torch.float32, dev)[None], dt_t, 1,
-                        keep_trajectory=True)
-    return res['final_cells'][0], res['field'][0, 0], res['potential'][0, 0]
+    return plan.update(state_t, Kt, engine.as_device_tensor(gf_params, torch.float32, dev).reshape(len(slots), 2),
+                       engine.as_device_tensor(kernels_weight_per_channel, torch.float32, dev).reshape(C, len(slots)), dt_t.contiguous())
 
 
 def update_conv(state: torch.Tensor, K, gf_params, kernels_weight_per_channel, dt, ufn: UpdateFn

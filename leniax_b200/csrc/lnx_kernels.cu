@@ -679,4 +679,32 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
     return LNX_OK;
 }
 
+int lnx_update(const lnx_plan* p, int32_t n_worlds, const float* state, const void* table, const float* gf_params, const float* weights,
+               const float* dt, float* state_out, float* field_out, float* potential_out, void* stream) {
+    if (!p || !state || !table || !gf_params || !weights || !dt || !state_out || !field_out || !potential_out || n_worlds < 1)
+        return fail(LNX_ERR_INVALID, "lnx_update: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int C = p->d.nb_channels;
+    const size_t ws_bytes = lnx_workspace_bytes_for(p, 1, n_worlds);
+    // one step of the scan with the trajectory outputs = (pre-update cells, field, potential); the statistics it also produces
+    // go to stream-ordered scratch and are dropped
+    const size_t cells_bytes = (size_t)n_worlds * C * (p->tiled ? (size_t)p->g.cells : (size_t)WS * WS) * sizeof(float);
+    float *stats = nullptr, *cm = nullptr, *na = nullptr, *cells_tmp = nullptr;
+    void* ws = nullptr;
+    LNX_CUDA(cudaMallocAsync(&stats, (size_t)LNX_NB_STATS * n_worlds * sizeof(float), st));
+    LNX_CUDA(cudaMallocAsync(&cm, (size_t)n_worlds * C * sizeof(float), st));
+    LNX_CUDA(cudaMallocAsync(&na, (size_t)n_worlds * sizeof(float), st));
+    LNX_CUDA(cudaMallocAsync(&cells_tmp, cells_bytes, st));
+    LNX_CUDA(cudaMallocAsync(&ws, ws_bytes, st));
+    const int rc = lnx_run_scan(p, 1, n_worlds, 1, 0, state, table, gf_params, weights, dt, stats, cm, na, state_out, cells_tmp, field_out,
+                                potential_out, ws, ws_bytes, st);
+    cudaFreeAsync(stats, st);
+    cudaFreeAsync(cm, st);
+    cudaFreeAsync(na, st);
+    cudaFreeAsync(cells_tmp, st);
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+
 }  // extern "C"

@@ -140,5 +140,20 @@ class Plan:
         out['N'] = n_alive
         return {'stats': out, 'final_cells': final, 'cells': traj_c, 'field': traj_f, 'potential': traj_p}
 
+    def update(self, state: torch.Tensor, K: torch.Tensor, gf_params: torch.Tensor, weights: torch.Tensor, dt: torch.Tensor
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """One step (``lnx_update``): state ``[N, C, *dims]``, K ``[1, nb_slots, *dims]`` -> ``(state', field, potential)``."""
+        dev = self.device
+        N = state.shape[0]
+        dims = tuple(state.shape[2:])
+        table = self.prepare_kernels(K, 1)
+        new_state, field = torch.empty_like(state), torch.empty_like(state)
+        potential = torch.empty((N, self.desc.nb_kernels) + dims, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.lnx_update(self.handle, N, state.data_ptr(), table.data_ptr(), gf_params.data_ptr(), weights.data_ptr(),
+                                           dt.data_ptr(), new_state.data_ptr(), field.data_ptr(), potential.data_ptr(), stream))
+        return new_state, field, potential
+
     def variant(self, with_trajectory: bool) -> str:
         return self.lib.lnx_run_scan_variant(self.handle, 1 if with_trajectory else 0).decode()
