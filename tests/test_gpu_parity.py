@@ -829,3 +829,24 @@ def test_search_for_mutation_two_scales(golden_dir):
     assert i == 0 and best['N'] == 40
     assert abs(best['config']['kernels_params'][0]['gf_params'][0] - 0.15) < 1e-4
     assert best['all_cells'].shape == (40, 1, 256, 256)
+
+
+def test_fused_kernel_state_within_bar_up_to_64_steps(golden_dir):
+    """The north-star bar on the headline kernel itself (lnx_world128_tm only returns final states, so one run per horizon):
+    state after 8, 16, 32 steps within 1e-5 L-inf of the fp32 oracle; after 48 and 64 steps no further from the reference
+    arithmetic than that arithmetic is from its fp64 twin (same bar as test_per_step_state_within_1e5_for_64_steps)."""
+    cfg, ocfg = _setup(golden_dir, 'orbium-test', 65)
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    oc = lo.init_and_run(ocfg, with_jit=True)[0]
+    oc64 = lo.init_and_run(ocfg, with_jit=True, dtype=np.float64)[0]
+    T = torch.tensor([10.], device=DEV)
+    for steps in (8, 16, 32, 48, 64):
+        _, final = runner.run_scan_mem_optimized(None, cells[None], K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
+        f = final[0, 0].cpu().numpy()
+        err32, err64 = np.abs(f - oc[steps, 0]).max(), np.abs(f - oc64[steps, 0]).max()
+        floor = np.abs(oc[steps, 0] - oc64[steps, 0]).max()
+        print('fused kernel, %2d steps: Linf vs fp32 oracle %.2e, vs fp64 twin %.2e, fp32 oracle vs fp64 %.2e' % (steps, err32, err64, floor))
+        if steps <= 32:
+            assert err32 <= 1e-5, (steps, err32)
+        assert min(err32, err64) <= max(1e-5, floor), (steps, err32, err64, floor)
