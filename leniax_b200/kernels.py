@@ -166,14 +166,19 @@ def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_chan
     world_size = list(world_size)
     mapping = KernelMapping(nb_channels, len(kernels_params))
     kernels_params.sort(key=lambda d: d['c_in'])
+    # K only depends on the kernel shapes (not on growth parameters or weights): in a QD generation every individual usually
+    # shares them (conf/config_qd_cmame*.yaml mutate gf_params and h), so the rasterisation + FFT is done once and reused.
+    cache_key = _kernel_cache_key(kernels_params, world_size, nb_channels, R, fft, device)
+    cached = _K_CACHE.get(cache_key) if cache_key is not None else None
     padded = []
     for idx, p in enumerate(kernels_params):
-        k = register[p['k_slug']](R, p['k_params'], p['kf_slug'], p['kf_params'], device=device)
-        pads: List[int] = []
-        for ws, ks in reversed(list(zip(world_size, k.shape[1:]))):  # F.pad wants the last dim first
-            lo = (ws - ks) // 2
-            pads += [lo, lo if (ws - ks) % 2 == 0 else lo + 1]
-        padded.append(torch.nn.functional.pad(k, pads))
+        if cached is None:
+            k = register[p['k_slug']](R, p['k_params'], p['kf_slug'], p['kf_params'], device=device)
+            pads: List[int] = []
+            for ws, ks in reversed(list(zip(world_size, k.shape[1:]))):  # F.pad wants the last dim first
+                lo = (ws - ks) // 2
+                pads += [lo, lo if (ws - ks) % 2 == 0 else lo + 1]
+            padded.append(torch.nn.functional.pad(k, pads))
         mapping.cin_kernels[p['c_in']].append(idx)
         mapping.cin_gfs[p['c_in']].append(p['gf_slug'])
         mapping.cin_gf_params[p['c_in']].append(p['gf_params'])
@@ -181,20 +186,25 @@ def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_chan
         mapping.cin_k_params[p['c_in']].append(p['k_params'])
         mapping.kernels_weight_per_channel[p['c_out']][idx] = p['h']
 
+    max_k = max(len(lst) for lst in mapping.cin_kernels)
+    true_channels: List[bool] = []
+    for lst in mapping.cin_kernels:  # kernels.py:122-143
+        true_channels += [True] * len(lst) + [False] * (max_k - len(lst))
+    mapping.true_channels = None if all(true_channels) else true_channels
+    if cached is not None:
+        return cached.clone(), mapping
+
     kernels = torch.cat(padded)  # [nb_kernels, *dims]
     if not fft:
         kernels = crop_zero(kernels)
     kshape = tuple(kernels.shape[1:])
-    max_k = max(len(lst) for lst in mapping.cin_kernels)
-    per_channel, true_channels = [], []
-    for lst in mapping.cin_kernels:  # kernels.py:122-143
+    per_channel = []
+    for lst in mapping.cin_kernels:
         kc = kernels[torch.tensor(lst, dtype=torch.long, device=device)] if lst else kernels.new_zeros((0, ) + kshape)
         missing = max_k - kc.shape[0]
-        true_channels += [True] * kc.shape[0] + [False] * missing
         if missing:
             kc = torch.cat([kc, kernels.new_zeros((missing, ) + kshape)])
         per_channel.append(kc)
-    mapping.true_channels = None if all(true_channels) else true_channels
 
     if fft:
         nd = len(world_size)
@@ -204,4 +214,30 @@ def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_chan
         K = rfftn_full(K, nd)  # kernels.py:148
     else:
         K = torch.cat(per_channel)[:, None]  # [C*max_k, 1, kh, kw]
+    if cache_key is not None and _K_CACHE_MAX > 0:
+        if len(_K_CACHE) >= _K_CACHE_MAX:
+            _K_CACHE.pop(next(iter(_K_CACHE)))
+        _K_CACHE[cache_key] = K.clone()
     return K, mapping
+
+
+_K_CACHE: Dict[Tuple, torch.Tensor] = {}
+_K_CACHE_MAX = 64
+
+
+def _freeze(x):
+    if isinstance(x, (list, tuple)):
+        return tuple(_freeze(v) for v in x)
+    if isinstance(x, (int, float, str, bool)) or x is None:
+        return x
+    return None  # tensors / arrays (k_slug 'raw'): not cached
+
+
+def _kernel_cache_key(kernels_params: List, world_size: List[int], nb_channels: int, R: float, fft: bool, device) -> Optional[Tuple]:
+    parts = []
+    for p in kernels_params:
+        kp, kfp = _freeze(p['k_params']), _freeze(p['kf_params'])
+        if kp is None or kfp is None or (isinstance(kp, tuple) and any(v is None for v in kp)):
+            return None
+        parts.append((p['k_slug'], kp, p['kf_slug'], kfp, int(p['c_in'])))
+    return (tuple(parts), tuple(world_size), int(nb_channels), float(R), bool(fft), str(torch.device(device)))
