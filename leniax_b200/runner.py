@@ -148,7 +148,7 @@ def _scan_conv(cells0, K, gf_params, weights, T, max_run_iter, update_fn: Update
                 tp.append(potential)
             cells = new_cells
         stats = {k: torch.stack([r[k] for r in rows]) for k in rows[0]}  # [T, N] / [T, N, C]
-        stats['N'] = check_heuristics(stats).sum(dim=0).to(dev)
+        stats['N'] = check_heuristics(stats).sum(dim=0)
         per_sol.append(stats)
         finals.append(cells)
         if keep_trajectory:

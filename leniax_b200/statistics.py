@@ -79,17 +79,17 @@ def max_mass_heuristic(init_mass, mass):  # statistics.py:269-281
 
 
 def check_heuristics(stats: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """statistics.py:134-205 on host tensors ``[T, N]`` (the scan kernels compute the same thing on device and return
-    its time-sum as ``stats['N']``; this host version exists for callers that post-process stored statistics)."""
-    mass = stats['mass'].detach().cpu()
-    cm = stats['channel_mass'].detach().cpu()
-    mv = stats['mass_volume'].detach().cpu()
+    """statistics.py:134-205 on tensors ``[T, N]`` wherever they live (the scan kernels compute the same thing in-kernel and
+    return its time-sum as ``stats['N']``; this version serves callers that post-process stored statistics and the
+    direct-convolution scans)."""
+    mass, cm, mv = stats['mass'].detach(), stats['channel_mass'].detach(), stats['mass_volume'].detach()
     T, N = mass.shape
-    should_continue = torch.ones(N)
-    init_cm, prev_mass, prev_sign = cm[0], mass[0], torch.zeros(N)
-    mono = torch.zeros(N, dtype=torch.int32)
-    vol = torch.zeros(N, dtype=torch.int32)
-    out = torch.empty((T, N))
+    dev = mass.device
+    should_continue = torch.ones(N, device=dev)
+    init_cm, prev_mass, prev_sign = cm[0], mass[0], torch.zeros(N, device=dev)
+    mono = torch.zeros(N, dtype=torch.int32, device=dev)
+    vol = torch.zeros(N, dtype=torch.int32, device=dev)
+    out = torch.empty((T, N), device=dev)
     for t in range(T):
         cond = (cm[t] >= EPSILON).all(dim=1) & (cm[t] <= 3 * init_cm).all(dim=1)
         sign = torch.sign(mass[t] - prev_mass)

@@ -17,7 +17,11 @@ the numeric values of the 12 statistics and of ``stats['N']`` on real runs.
 Third-party arithmetic that is not in /root/reference: the reference lowers
 ``jnp.fft.fftn`` / reductions through JAX/XLA (pinned env jax 0.2.26 / jaxlib
 0.1.75, ``environment_linux.yml:57-58``); on CPU that is pocketfft in complex64.
-Here ``scipy.fft`` (also pocketfft, keeps complex64) plays that role.
+Here ``scipy.fft`` (also pocketfft, keeps complex64) plays that role.  Also
+third-party: ``scipy.ndimage.zoom`` (``helpers.py:61``, called directly here, as
+the reference does) and pyribs ``ribs==0.4.0`` ``GridArchive.get_index``
+(``setup.py:21``; restated in ``grid_archive_index`` from its published source,
+no reference test pins an archive index: unpinned).
 
 Every function carries the reference file:line it follows.  ``dtype`` selects
 the float32 oracle (default, what JAX computes) or its float64 twin (used to
