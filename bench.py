@@ -188,7 +188,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import leniax_b200
-    from leniax_b200 import _lib, helpers, kernels, runner, statistics
+    from leniax_b200 import _lib, helpers, kernels, qd, runner, statistics
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -219,9 +219,7 @@ def run_b200(args):
 
     def gather_block(stats):
         """What the QD archive consumes per world (qd.py:168-186): N + mean of the last 128 rows of each statistic."""
-        keys = [k for k in stats if k not in ('N', 'channel_mass')]
-        means = torch.stack([stats[k][0, sim_steps - min(128, sim_steps):sim_steps].mean(dim=0) for k in keys], dim=1)
-        block = torch.cat([stats['N'][0][:, None], means], dim=1).contiguous()  # [worlds, 12]
+        block = qd.summarize_stats(stats)[0][0].contiguous()  # [worlds, 12], lnx_summarize_stats on the device
         if world > 1:
             out = [torch.empty_like(block) for _ in range(world)]
             dist.all_gather(out, block)
@@ -317,7 +315,7 @@ def run_b200(args):
             },
             'e2e': {'value': e2e_value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': int(host_cells.numel() * 4) * world,
                     'd2h_bytes_per_step': int(block_h.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': 2 * args.steps,  # per step: lnx_prepare_kernel + the fused world kernel
+            'gpu_launches': 3 * args.steps,  # per step: lnx_prepare_kernel + the fused world kernel + lnx_summarize_kernel
             'clocks': clocks,
             'roofline': {
                 'bound': 'fp32', 'achieved': achieved_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved_tflops / fp32_peak,

@@ -157,6 +157,13 @@ int lnx_run_scan(const lnx_plan* plan, int32_t n_sols, int32_t n_init, int32_t m
 int lnx_compute_stats(const lnx_plan* plan, int32_t n_worlds, const float* cells, const float* field, const float* potential,
                       int32_t* total_shift_idx, float* mass_centroid, float* mass_angle, float* stats, float* channel_mass, void* stream);
 
+/* What qd.update_individuals consumes of a scan (leniax/qd.py:168-186), reduced on the device: for every world N and the mean of
+ * rows [ns - window, ns) of each scalar statistic, ns = max(int(N), window) clamped to T.  planes: HOST array of LNX_NB_STATS
+ * device pointers (order lnx_stat_key), each [n_sols][T][n_init]; n_alive [n_sols][n_init]; out [n_sols][n_init][1 + LNX_NB_STATS]
+ * = (N, means...).  This block is what a sharded run all-gathers per generation. */
+int lnx_summarize_stats(const float* const* planes, const float* n_alive, int32_t n_sols, int32_t T, int32_t n_init, int32_t window,
+                        float* out, void* stream);
+
 /* One step: replaces a call of the update_fn built by helpers.build_update_fn, i.e. core.update (leniax/core.py:13-49):
  * state [n_worlds][C][dims...] -> state_out (same shape), field_out [n_worlds][C][dims...], potential_out [n_worlds][K][dims...].
  * table: lnx_kernels_prepare() output for ONE solution; gf_params [K][2], weights [C][K], dt [1] (device).  Thin wrapper over

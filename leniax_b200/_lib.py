@@ -62,6 +62,7 @@ EXPORTS = {
     'lnx_run_scan': (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_uint32] + [c_void_p] * 12 + [c_void_p, c_size_t, c_void_p]),
     'lnx_compute_stats': (ctypes.c_int, [c_void_p, c_int32] + [c_void_p] * 8 + [c_void_p]),
     'lnx_run_scan_variant': (c_char_p, [c_void_p, c_int32]),
+    'lnx_summarize_stats': (ctypes.c_int, [POINTER(c_void_p), c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'lnx_update': (ctypes.c_int, [c_void_p, c_int32] + [c_void_p] * 9),
     'lnx_update_conv': (ctypes.c_int, [POINTER(LnxDesc), c_int32, c_int32, c_int32] + [c_void_p] * 4 + [c_float] + [c_void_p] * 4),
 }

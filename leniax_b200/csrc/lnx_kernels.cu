@@ -21,6 +21,34 @@
 #include "lnx_conv.cuh"
 
 
+namespace lnx {
+// What qd.update_individuals reads of a scan (leniax/qd.py:168-186): per world N and, for every scalar statistic, the mean of
+// rows [ns - window, ns) with ns = max(int(N), window) (clamped to the T rows that exist).  planes: one [n_sols][T][n_init]
+// array per statistic; out [n_sols][n_init][1 + LNX_NB_STATS].  One thread per (statistic, world); threads of a warp are
+// consecutive initialisations, so every row read is coalesced.
+struct SummArgs {
+    const float* planes[ST_COUNT];
+    const float* n_alive;
+    float* out;
+    int n_sols, T, n_init, window;
+};
+__global__ void __launch_bounds__(128) lnx_summarize_kernel(SummArgs P) {
+    const int i = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y, k = blockIdx.z;
+    if (i >= P.n_init) return;
+    const float N = P.n_alive[(size_t)s * P.n_init + i];
+    const int w = P.window < P.T ? P.window : P.T;
+    int ns = (int)N;
+    ns = ns < w ? w : (ns > P.T ? P.T : ns);
+    const int lo = ns - P.window > 0 ? ns - P.window : 0;
+    const float* col = P.planes[k] + (size_t)s * P.T * P.n_init + i;
+    float acc = 0.f;
+    for (int t = lo; t < ns; ++t) acc += col[(size_t)t * P.n_init];
+    float* o = P.out + ((size_t)s * P.n_init + i) * (1 + ST_COUNT);
+    o[1 + k] = acc / (float)(ns - lo);
+    if (k == 0) o[0] = N;
+}
+}  // namespace lnx
+
 // =====================================================================================================================
 // C ABI
 // =====================================================================================================================
@@ -675,6 +703,28 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
     } else {
         lnx_world128_generic<<<grid, NTHREADS, GENERIC_SMEM, st>>>(a);
     }
+    LNX_CUDA(cudaGetLastError());
+    return LNX_OK;
+}
+
+int lnx_summarize_stats(const float* const* planes, const float* n_alive, int32_t n_sols, int32_t T, int32_t n_init, int32_t window,
+                        float* out, void* stream) {
+    if (!planes || !n_alive || !out || n_sols < 1 || T < 1 || n_init < 1 || window < 1 || n_sols > 65535)
+        return fail(LNX_ERR_INVALID, "lnx_summarize_stats: bad argument");
+    const int rc = ensure_device_init(nullptr, nullptr);
+    if (rc != LNX_OK) return rc;
+    SummArgs a;
+    for (int k = 0; k < ST_COUNT; ++k) {
+        if (!planes[k]) return fail(LNX_ERR_INVALID, "lnx_summarize_stats: null statistics plane %d", k);
+        a.planes[k] = planes[k];
+    }
+    a.n_alive = n_alive;
+    a.out = out;
+    a.n_sols = n_sols;
+    a.T = T;
+    a.n_init = n_init;
+    a.window = window;
+    lnx_summarize_kernel<<<dim3((n_init + 127) / 128, n_sols, ST_COUNT), 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
     LNX_CUDA(cudaGetLastError());
     return LNX_OK;
 }

@@ -13,6 +13,7 @@ from . import initializations as leniax_init
 from . import kernels as leniax_kernels
 from . import runner as leniax_runner
 from . import utils as leniax_utils
+from . import _lib
 from .constant import NB_STATS_STEPS
 from .lenia import LeniaIndividual
 from .statistics import build_compute_stats_fn
@@ -75,6 +76,18 @@ def summarize_stats(stats: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, List[
     block all-gathered across GPUs."""
     keys = [k for k in stats if k not in ('N', 'channel_mass')]
     N = stats['N']  # [S, I]
+    if N.is_cuda and tuple(keys) == tuple(_lib.STAT_KEYS) and all(stats[k].is_cuda and stats[k].dtype == torch.float32 for k in keys):
+        import ctypes
+        S, T, I = stats[keys[0]].shape
+        planes = [stats[k].contiguous() for k in keys]
+        ptrs = (ctypes.c_void_p * len(planes))(*[p.data_ptr() for p in planes])
+        n_alive = N.contiguous().float()
+        out = torch.empty((S, I, 1 + len(keys)), dtype=torch.float32, device=N.device)
+        with torch.cuda.device(N.device):
+            _lib.check(_lib.load_library().lnx_summarize_stats(ptrs, n_alive.data_ptr(), S, T, I, NB_STATS_STEPS, out.data_ptr(),
+                                                               torch.cuda.current_stream().cuda_stream))
+        return out, keys
+    # host-side tensors (post-processing of stored statistics): same reduction with torch
     T = stats[keys[0]].shape[1]
     ns = torch.clamp(N.long(), min=min(NB_STATS_STEPS, T), max=T)
     lo = torch.clamp(ns - NB_STATS_STEPS, min=0)

@@ -850,3 +850,21 @@ def test_fused_kernel_state_within_bar_up_to_64_steps(golden_dir):
         if steps <= 32:
             assert err32 <= 1e-5, (steps, err32)
         assert min(err32, err64) <= max(1e-5, floor), (steps, err32, err64, floor)
+
+
+def test_device_side_summary_matches_host_reduction(golden_dir):
+    """qd.summarize_stats on CUDA tensors runs lnx_summarize_stats; on host tensors the same reduction in torch (float64 prefix
+    sums).  Worlds with different N (windows [ns - 128, ns) at different places), T both above and below the window."""
+    from leniax_b200 import qd
+    for steps in (200, 60):
+        cfg, ocfg, worlds, K, mapping, ufn, sfn = _orbium_batch(golden_dir, 9, seed=4)
+        gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+        cells0 = torch.from_numpy(worlds).to(DEV).reshape(3, 3, 1, 128, 128)
+        args = (cells0, torch.stack([K] * 3), torch.stack([gf] * 3), torch.stack([w] * 3), torch.tensor([10.] * 3, device=DEV))
+        stats, _ = runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn)
+        dev_block, keys = qd.summarize_stats(stats)
+        host_block, hkeys = qd.summarize_stats({k: v.cpu() for k, v in stats.items()})
+        assert keys == hkeys and dev_block.shape == (3, 3, 12)
+        assert torch.equal(dev_block[..., 0].cpu(), stats['N'].cpu())
+        # (fp32 running sums on the device, float64 prefix sums on the host; mass_angle_speed rows are O(100) with both signs)
+        torch.testing.assert_close(dev_block.cpu(), host_block, rtol=2e-6, atol=2e-5)
