@@ -115,6 +115,22 @@ __device__ void block_fft(float2* s, int n, int logn, int is, int nl, int js, co
     }
 }
 
+// Threads spread over a [rows][half] index space without an integer division by `half` (not a power of two): kw = smallest
+// power of two >= half (at most the block size) lanes run along k, the remaining blockDim / kw along the rows.
+struct RowK {
+    int k0, kstep, r0, rstep;
+};
+__device__ __forceinline__ RowK rowk_map(int half) {
+    int kw = 32;
+    while (kw < half && kw < (int)blockDim.x) kw <<= 1;
+    RowK m;
+    m.k0 = threadIdx.x & (kw - 1);
+    m.kstep = kw;
+    m.r0 = threadIdx.x / kw;  // kw is a power of two: a shift
+    m.rstep = blockDim.x / kw;
+    return m;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // pass A: real rows -> half spectrum (natural order), optional axis-1 transform for 3-D planes
 //   grid (n_slabs, C, worlds).  smem: zbuf [slab_rows/2][A2] complex, then (3-D) plane [A1][half] complex
@@ -150,8 +166,9 @@ __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
     block_fft<false, false>(z, A2, g.logA2, 1, pairs, A2, stw, log_tw);
     float2* dst = P.spec + (((size_t)w * P.C + c) * g.rows + row0) * half;
     const bool plane = g.nd == 3;
-    for (int pr = 0; pr < pairs; ++pr)
-    for (int k = threadIdx.x; k < half; k += blockDim.x) {
+    const RowK rk = rowk_map(half);
+    for (int pr = rk.r0; pr < pairs; pr += rk.rstep)
+    for (int k = rk.k0; k < half; k += rk.kstep) {
         const float2 zk = z[(size_t)pr * A2 + brev_n(k, g.logA2)];
         const float2 zc = z[(size_t)pr * A2 + brev_n((A2 - k) & (A2 - 1), g.logA2)];
         const float2 a = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
@@ -167,9 +184,9 @@ __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
     if (plane) {
         __syncthreads();
         block_fft<false, true>(pl, g.A1, g.logA1, half, half, 1, stw, log_tw);  // along axis 1, `half` interleaved lines
-        for (int i = threadIdx.x; i < g.A1 * half; i += blockDim.x) {
-            const int m1 = i / half, k = i - m1 * half;
-            dst[i] = pl[(size_t)brev_n(m1, g.logA1) * half + k];
+        for (int m1 = rk.r0; m1 < g.A1; m1 += rk.rstep) {
+            const int srow = brev_n(m1, g.logA1);
+            for (int k = rk.k0; k < half; k += rk.kstep) dst[(size_t)m1 * half + k] = pl[(size_t)srow * half + k];
         }
     }
 }
@@ -298,10 +315,17 @@ __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
         const float2* src = P.pot_spec + (((size_t)w * P.K + k) * g.rows + row0) * half;
         __syncthreads();
         if (plane) {
-            for (int m1 = threadIdx.x / 64; m1 < R; m1 += blockDim.x / 64) {  // rows of `half` values, no integer division
-                const int dst_row = brev_n(m1, g.logA1);
-                for (int kk = threadIdx.x & 63; kk < half; kk += 64) pl[(size_t)dst_row * half + kk] = src[(size_t)m1 * half + kk];
-            }
+            const RowK rk = rowk_map(half);
+            for (int kk = rk.k0; kk < half; kk += rk.kstep)
+                for (int m1 = rk.r0; m1 < R; m1 += 4 * rk.rstep) {  // four independent rows per thread in flight
+                    float2 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (m1 + j * rk.rstep < R) v[j] = __ldg(src + (size_t)(m1 + j * rk.rstep) * half + kk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (m1 + j * rk.rstep < R) pl[(size_t)brev_n(m1 + j * rk.rstep, g.logA1) * half + kk] = v[j];
+                }
             __syncthreads();
             block_fft<true, true>(pl, g.A1, g.logA1, half, half, 1, stw, log_tw);
         } else {
@@ -310,8 +334,9 @@ __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
             __syncthreads();
         }
         // retangle: Z'[k] = A + iB, Z'[N-k] = conj(A) + i conj(B), stored at bit-reversed positions for the DIT
-        for (int pr = 0; pr < pairs; ++pr)
-        for (int kk = threadIdx.x; kk < half; kk += blockDim.x) {
+        const RowK rk2 = rowk_map(half);
+        for (int pr = rk2.r0; pr < pairs; pr += rk2.rstep)
+        for (int kk = rk2.k0; kk < half; kk += rk2.kstep) {
             const float2 a = pl[(size_t)(2 * pr) * half + kk], b = pl[(size_t)(2 * pr + 1) * half + kk];
             z[(size_t)pr * A2 + brev_n(kk, g.logA2)] = make_float2(a.x - b.y, a.y + b.x);
             if (kk != 0 && kk != A2 / 2) z[(size_t)pr * A2 + brev_n(A2 - kk, g.logA2)] = make_float2(a.x + b.y, b.x - a.y);
