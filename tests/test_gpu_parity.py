@@ -868,3 +868,20 @@ def test_device_side_summary_matches_host_reduction(golden_dir):
         assert torch.equal(dev_block[..., 0].cpu(), stats['N'].cpu())
         # (fp32 running sums on the device, float64 prefix sums on the host; mass_angle_speed rows are O(100) with both signs)
         torch.testing.assert_close(dev_block.cpu(), host_block, rtol=2e-6, atol=2e-5)
+
+
+def test_inputs_as_numpy_float64_and_unpinned_host_tensors(golden_dir):
+    """The entry points take what a leniax caller may hold: numpy arrays (any float dtype), host tensors, python scalars."""
+    cfg, _ = _setup(golden_dir, 'orbium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    worlds = torch.stack([torch.roll(cells[0], (5 * i, 3 * i), dims=(1, 2)) for i in range(4)])[None]
+    ref, fref = runner.run_scan_mem_optimized(None, worlds, K[None], gf[None], w[None], torch.tensor([10.], device=DEV), 20, 13, ufn, sfn)
+    got, fgot = runner.run_scan_mem_optimized(None, worlds.cpu().numpy().astype(np.float64), K[None].cpu().numpy(), gf[None].cpu().numpy().astype(np.float64),
+                                              w[None].cpu(), np.array([10.]), 20, 13, ufn, sfn)
+    assert torch.equal(fref, fgot)
+    for k in ref:
+        assert torch.equal(ref[k], got[k]), k
+    c1 = runner.run_scan(None, worlds[0].cpu(), K.cpu(), gf.cpu().numpy(), w.cpu().numpy(), 10., 5, 13, ufn, sfn)[0]
+    c2 = runner.run_scan(None, worlds[0], K, gf, w, torch.tensor(10., device=DEV), 5, 13, ufn, sfn)[0]
+    assert torch.equal(c1, c2)
