@@ -188,6 +188,25 @@ static Workspace carve(const Geom& g, int C, int K, long long worlds, unsigned c
 }
 }  // namespace th
 
+// the TMEM fused kernel is instantiated for every growth function (state function v1): one-channel one-kernel worlds of any
+// registered growth function take the fast path
+static const void* tm_kernel_for(int gf, bool np) {
+#define LNX_TM_CASE(G) \
+    case G: return np ? reinterpret_cast<const void*>(&lnx_world128_tm<G, SF_V1, true>) : reinterpret_cast<const void*>(&lnx_world128_tm<G, SF_V1, false>);
+    switch (gf) {
+        LNX_TM_CASE(GF_POLY_QUAD4)
+        LNX_TM_CASE(GF_GAUSSIAN)
+        LNX_TM_CASE(GF_GAUSSIAN_TARGET)
+        LNX_TM_CASE(GF_STEP)
+        LNX_TM_CASE(GF_STAIRCASE)
+        LNX_TM_CASE(GF_TRIANGLE)
+        default: break;
+    }
+    return np ? reinterpret_cast<const void*>(&lnx_world128_tm<GF_IDENTITY, SF_V1, true>)
+              : reinterpret_cast<const void*>(&lnx_world128_tm<GF_IDENTITY, SF_V1, false>);
+#undef LNX_TM_CASE
+}
+
 // one-time per-device setup: architecture check (no fallback), twiddle constants, dynamic shared memory opt-in
 static int ensure_device_init(int* dev_out, int* sms_out) {
     static bool done[64] = {false};
@@ -210,12 +229,12 @@ static int ensure_device_init(int* dev_out, int* sms_out) {
         LNX_CUDA(cudaMemcpyToSymbol(c_tw128, tw, sizeof(tw)));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_tm<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_tm<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_tm<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_tm<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
+        for (int gf = 0; gf < GF_COUNT; ++gf)
+            for (int np = 0; np < 2; ++np) {
+                const void* fn = tm_kernel_for(gf, np != 0);
+                LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
+                LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, GENERIC_SMEM));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_gen_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_r16<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R16_SMEM));
@@ -614,9 +633,11 @@ int lnx_update_conv(const lnx_desc* d, int32_t n_worlds, int32_t kh, int32_t kw,
     return LNX_OK;
 }
 
-static bool use_fused(const lnx_plan* p, bool trajectory) {
+static bool use_fused(const lnx_plan* p, bool trajectory, uint32_t run_flags = 0) {
     const lnx_desc& d = p->d;
-    return d.nb_channels == 1 && d.nb_kernels == 1 && !trajectory && d.gf_id[0] == GF_POLY_QUAD4 && d.state_fn == SF_V1;
+    if (d.nb_channels != 1 || d.nb_kernels != 1 || trajectory || d.state_fn != SF_V1) return false;
+    // the two earlier fused kernels (A/B flags) only exist for poly_quad4; the default TMEM kernel for every growth function
+    return d.gf_id[0] == GF_POLY_QUAD4 || !(run_flags & (LNX_RUN_FUSED_R16 | LNX_RUN_FUSED_SMEM));
 }
 
 const char* lnx_run_scan_variant(const lnx_plan* p, int32_t with_trajectory) {
@@ -638,7 +659,7 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
         return run_scan_tiled(p, n_sols, n_init, max_run_iter, cells0, table, gf_params, weights, dt, stats, channel_mass, n_alive, final_cells,
                               cells_out, field_out, potential_out, workspace, workspace_bytes, stream);
     const bool trajectory = cells_out || field_out || potential_out;
-    const bool fused = use_fused(p, trajectory);
+    const bool fused = use_fused(p, trajectory, run_flags);
     if (!workspace || workspace_bytes < (fused ? (size_t)256 : lnx_workspace_bytes(p)))
         return fail(LNX_ERR_INVALID, "lnx_run_scan: workspace too small (%zu < %zu)", workspace_bytes, lnx_workspace_bytes(p));
 
@@ -683,10 +704,8 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
         const bool t32 = (run_flags & LNX_RUN_FUSED_R16) == 0;
         if (!(run_flags & (LNX_RUN_FUSED_R16 | LNX_RUN_FUSED_SMEM))) {  // default: TMEM-resident state, two worlds per SM
             const int grid2 = (int)(n_worlds < 2 * p->sm_count ? n_worlds : 2 * p->sm_count);
-            if (run_flags & LNX_RUN_ASSUME_FINITE)
-                lnx_world128_tm<GF_POLY_QUAD4, SF_V1, false><<<grid2, NT, TM_SMEM, st>>>(a);
-            else
-                lnx_world128_tm<GF_POLY_QUAD4, SF_V1, true><<<grid2, NT, TM_SMEM, st>>>(a);
+            void* kargs[] = {&a};
+            LNX_CUDA(cudaLaunchKernel(tm_kernel_for(p->d.gf_id[0], !(run_flags & LNX_RUN_ASSUME_FINITE)), dim3(grid2), dim3(NT), kargs, TM_SMEM, st));
         } else if (t32) {
             if (run_flags & LNX_RUN_ASSUME_FINITE)
                 lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false><<<grid, NTHREADS, FUSED_SMEM, st>>>(a);

@@ -316,7 +316,7 @@ LNX_HD float2 field_fused_pk(float2 X, const FusedConsts& K) {
         const float2 o2 = pk_mul(o, o);
         return pk_fma(pk_mul(o2, o2), pk_bc(K.c2), pk_bc(-K.c));
     } else {
-        return make_float2(K.c * growth<GF, NP>(X.x, K.gf), K.c * growth<GF, NP>(X.y, K.gf));
+        return make_float2(K.c * growth<GF, NP, true>(X.x, K.gf), K.c * growth<GF, NP, true>(X.y, K.gf));  // true divisions, as the generic kernel
     }
 }
 template <int GF, int SF, bool NP, class Store>
