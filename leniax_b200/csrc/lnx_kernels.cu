@@ -190,7 +190,11 @@ static Workspace carve(const Geom& g, int C, int K, long long worlds, unsigned c
 
 // the TMEM fused kernel is instantiated for every growth function (state function v1): one-channel one-kernel worlds of any
 // registered growth function take the fast path
-static const void* tm_kernel_for(int gf, bool np) {
+static bool tm_kernel_exists(int gf, int sf) { return sf == SF_V1 || (sf == SF_V2 && gf == GF_GAUSSIAN_TARGET); }
+static const void* tm_kernel_for(int gf, int sf, bool np) {
+    if (sf == SF_V2)  // the asymptotic update of conf/config_qd_cmame_v2.yaml and species/2d/1c-1k-v2 (gaussian_target growth)
+        return np ? reinterpret_cast<const void*>(&lnx_world128_tm<GF_GAUSSIAN_TARGET, SF_V2, true>)
+                  : reinterpret_cast<const void*>(&lnx_world128_tm<GF_GAUSSIAN_TARGET, SF_V2, false>);
 #define LNX_TM_CASE(G) \
     case G: return np ? reinterpret_cast<const void*>(&lnx_world128_tm<G, SF_V1, true>) : reinterpret_cast<const void*>(&lnx_world128_tm<G, SF_V1, false>);
     switch (gf) {
@@ -229,9 +233,9 @@ static int ensure_device_init(int* dev_out, int* sms_out) {
         LNX_CUDA(cudaMemcpyToSymbol(c_tw128, tw, sizeof(tw)));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
         LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        for (int gf = 0; gf < GF_COUNT; ++gf)
+        for (int gf = 0; gf <= GF_COUNT; ++gf)  // (the extra round sets up the v2 instantiation)
             for (int np = 0; np < 2; ++np) {
-                const void* fn = tm_kernel_for(gf, np != 0);
+                const void* fn = gf < GF_COUNT ? tm_kernel_for(gf, SF_V1, np != 0) : tm_kernel_for(GF_GAUSSIAN_TARGET, SF_V2, np != 0);
                 LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
                 LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             }
@@ -635,9 +639,11 @@ int lnx_update_conv(const lnx_desc* d, int32_t n_worlds, int32_t kh, int32_t kw,
 
 static bool use_fused(const lnx_plan* p, bool trajectory, uint32_t run_flags = 0) {
     const lnx_desc& d = p->d;
-    if (d.nb_channels != 1 || d.nb_kernels != 1 || trajectory || d.state_fn != SF_V1) return false;
-    // the two earlier fused kernels (A/B flags) only exist for poly_quad4; the default TMEM kernel for every growth function
-    return d.gf_id[0] == GF_POLY_QUAD4 || !(run_flags & (LNX_RUN_FUSED_R16 | LNX_RUN_FUSED_SMEM));
+    if (d.nb_channels != 1 || d.nb_kernels != 1 || trajectory) return false;
+    // the two earlier fused kernels (A/B flags) only exist for poly_quad4 / v1; the default TMEM kernel for every growth function
+    // with v1 and for gaussian_target with v2
+    if (run_flags & (LNX_RUN_FUSED_R16 | LNX_RUN_FUSED_SMEM)) return d.gf_id[0] == GF_POLY_QUAD4 && d.state_fn == SF_V1;
+    return tm_kernel_exists(d.gf_id[0], d.state_fn);
 }
 
 const char* lnx_run_scan_variant(const lnx_plan* p, int32_t with_trajectory) {
@@ -705,7 +711,8 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
         if (!(run_flags & (LNX_RUN_FUSED_R16 | LNX_RUN_FUSED_SMEM))) {  // default: TMEM-resident state, two worlds per SM
             const int grid2 = (int)(n_worlds < 2 * p->sm_count ? n_worlds : 2 * p->sm_count);
             void* kargs[] = {&a};
-            LNX_CUDA(cudaLaunchKernel(tm_kernel_for(p->d.gf_id[0], !(run_flags & LNX_RUN_ASSUME_FINITE)), dim3(grid2), dim3(NT), kargs, TM_SMEM, st));
+            LNX_CUDA(cudaLaunchKernel(tm_kernel_for(p->d.gf_id[0], p->d.state_fn, !(run_flags & LNX_RUN_ASSUME_FINITE)), dim3(grid2), dim3(NT), kargs,
+                                      TM_SMEM, st));
         } else if (t32) {
             if (run_flags & LNX_RUN_ASSUME_FINITE)
                 lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false><<<grid, NTHREADS, FUSED_SMEM, st>>>(a);

@@ -887,25 +887,28 @@ def test_inputs_as_numpy_float64_and_unpinned_host_tensors(golden_dir):
     assert torch.equal(c1, c2)
 
 
-@pytest.mark.parametrize('gf_slug,params', [('gaussian', [.15, .02]), ('gaussian_target', [.2, .05]), ('step', [.15, .03]),
-                                            ('staircase', [.15, .04]), ('triangle', [.15, .05]), ('identity', [0., 1.])])
-def test_fused_tmem_kernel_for_every_growth_function(golden_dir, gf_slug, params):
+@pytest.mark.parametrize('gf_slug,params,sf', [('gaussian', [.15, .02], 'v1'), ('gaussian_target', [.2, .05], 'v1'), ('step', [.15, .03], 'v1'),
+                                               ('staircase', [.15, .04], 'v1'), ('triangle', [.15, .05], 'v1'), ('identity', [0., 1.], 'v1'),
+                                               ('gaussian_target', [.2, .05], 'v2')])
+def test_fused_tmem_kernel_for_every_growth_function(golden_dir, gf_slug, params, sf):
     """One-channel one-kernel worlds of any registered growth function (state function v1) run in lnx_world128_tm, not only
     poly_quad4: statistics, N and final state against the oracle."""
     cfg, ocfg = _setup(golden_dir, 'orbium-test')
     for cc in (cfg, ocfg):
         cc['kernels_params'][0]['gf_slug'] = gf_slug
         cc['kernels_params'][0]['gf_params'] = params
+        cc['world_params']['get_state_fn_slug'] = sf  # v2: the asymptotic update of conf/config_qd_cmame_v2.yaml
     cells, K, mapping, ufn, sfn = _engine_parts(cfg)
     gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
     steps = 12
     worlds = torch.stack([torch.roll(cells[0], (7 * i, 2 * i), dims=(1, 2)) * (1. - 0.2 * i) for i in range(3)])[None]
     stats, final = runner.run_scan_mem_optimized(None, worlds, K[None], gf[None], w[None], torch.tensor([10.], device=DEV), steps, 13, ufn, sfn)
-    plan = next(p for p in leniax_b200.engine.Plan._cache.values() if p.desc.nb_kernels == 1 and p.desc.gf_id[0] == ufn.kernel_layout(1)[2][0])
+    plan = next(p for p in leniax_b200.engine.Plan._cache.values()
+                if p.desc.nb_kernels == 1 and p.desc.gf_id[0] == ufn.kernel_layout(1)[2][0] and p.desc.state_fn == {'v1': 0, 'v2': 1}[sf])
     assert plan.variant(False) == 'fused'
     oK, om = lo.get_kernels_and_mapping(copy.deepcopy(ocfg['kernels_params']), [128, 128], 1, 13)
     ost, ofin = lo.run_scan(worlds[0].cpu().numpy(), oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), steps,
-                            lo.build_update_fn(om), lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), False)
+                            lo.build_update_fn(om, sf), lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), False)
     assert stats['N'][0].cpu().numpy().tolist() == ost['N'].tolist()
     discontinuous = gf_slug in ('step', 'staircase')  # a potential within rounding of a threshold may flip a few cells
     bad = (np.abs(final[0].cpu().numpy() - ofin) > 1e-4).mean()
