@@ -15,6 +15,7 @@ LNX_RUN_EARLY_STOP = 1
 LNX_RUN_ASSUME_FINITE = 0x100
 LNX_RUN_FUSED_R16 = 0x200
 LNX_RUN_FUSED_SMEM = 0x400
+LNX_RUN_TILED_GENERIC = 0x800
 LNX_PLAN_FORCE_TILED = 1
 
 LNX_OK, LNX_ERR_INVALID, LNX_ERR_UNSUPPORTED, LNX_ERR_CUDA, LNX_ERR_NO_DEVICE = 0, -1, -2, -3, -4

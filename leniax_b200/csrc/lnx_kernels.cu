@@ -18,6 +18,7 @@
 #include "lnx_kernel_fused_smem.cuh"
 #include "lnx_kernel_generic.cuh"
 #include "lnx_tiled.cuh"
+#include "lnx_tiled64.cuh"
 #include "lnx_conv.cuh"
 
 
@@ -128,6 +129,7 @@ static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
     g->tc = tc;
     return true;
 }
+static bool is_cube64(const Geom& g) { return g.nd == 3 && g.dims[0] == 64 && g.dims[1] == 64 && g.dims[2] == 64; }
 static size_t tw_bytes(int logn) { return ((size_t)1 << (logn - 1)) * sizeof(float2); }  // shared-memory twiddle table of one pass
 static int log_inner(const Geom& g) { return g.logA2 > g.logA1 ? g.logA2 : g.logA1; }
 static size_t smem_a(const Geom& g) {
@@ -399,7 +401,11 @@ int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const floa
     a.tw = th::g_tw[dev];
     a.g = g;
     a.C = 1;
-    lnx::tiled::pass_a_kernel<<<dim3(g.n_slabs, 1, n_images), lnx::tiled::TPB, th::smem_a(g), st>>>(a);
+    const bool line64 = th::is_cube64(g) && n_images <= 65535;
+    if (line64)
+        lnx::t64::plane_fwd_kernel<<<dim3(64, 1, n_images), 32, 0, st>>>(a);
+    else
+        lnx::tiled::pass_a_kernel<<<dim3(g.n_slabs, 1, n_images), lnx::tiled::TPB, th::smem_a(g), st>>>(a);
     lnx::tiled::PassBArgs b;
     memset(&b, 0, sizeof(b));
     b.spec = sa;
@@ -410,7 +416,10 @@ int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const floa
     b.K = 0;
     b.n_init = 1;
     const long long M = g.spec / g.L;
-    lnx::tiled::pass_b_kernel<<<dim3((unsigned)((M + g.tc - 1) / g.tc), 1, n_images), lnx::tiled::TPB, th::smem_b(g), st>>>(b);
+    if (line64)
+        lnx::t64::lead_kernel<<<dim3(lnx::t64::COLS / lnx::t64::LEAD_TPB, 1, n_images), lnx::t64::LEAD_TPB, 0, st>>>(b);
+    else
+        lnx::tiled::pass_b_kernel<<<dim3((unsigned)((M + g.tc - 1) / g.tc), 1, n_images), lnx::tiled::TPB, th::smem_b(g), st>>>(b);
     lnx::tiled::expand_hermitian_kernel<<<dim3(1024, 1, n_images), 256, 0, st>>>(sb, static_cast<float2*>(spectra), g);
     LNX_CUDA(cudaGetLastError());
     LNX_CUDA(cudaFreeAsync(sa, st));
@@ -500,7 +509,7 @@ int lnx_measure_fp32_peak(int32_t iters, double* tflops, double* ms, void* strea
 static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_run_iter, const float* cells0, const void* table,
                           const float* gf_params, const float* weights, const float* dt, float* stats, float* channel_mass, float* n_alive,
                           float* final_cells, float* cells_out, float* field_out, float* potential_out, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          size_t workspace_bytes, void* stream, uint32_t run_flags) {
     using namespace lnx::tiled;
     const Geom& g = p->g;
     const int C = p->d.nb_channels, K = p->d.nb_kernels;
@@ -573,12 +582,20 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
     const long long M = g.spec / g.L;
     const dim3 grid_a(g.n_slabs, C, (unsigned)worlds), grid_b((unsigned)((M + g.tc - 1) / g.tc), C, (unsigned)worlds),
         grid_c(g.n_slabs, 1, (unsigned)worlds);
+    // 64^3 worlds with one channel and one kernel (BASELINE config E): thread-per-line passes of lnx_tiled64.cuh
+    const bool line64 = th::is_cube64(g) && C == 1 && K == 1 && !(run_flags & LNX_RUN_TILED_GENERIC);
     for (int t = 0; t < max_run_iter; ++t) {
         c.t = t;
         d.t = t;
-        pass_a_kernel<<<grid_a, TPB, th::smem_a(g), st>>>(a);
-        pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), st>>>(b);
-        pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), st>>>(c);
+        if (line64) {
+            lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);
+            lnx::t64::lead_kernel<<<dim3(lnx::t64::COLS / lnx::t64::LEAD_TPB, 1, (unsigned)worlds), lnx::t64::LEAD_TPB, 0, st>>>(b);
+            lnx::t64::plane_inv_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(c);
+        } else {
+            pass_a_kernel<<<grid_a, TPB, th::smem_a(g), st>>>(a);
+            pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), st>>>(b);
+            pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), st>>>(c);
+        }
         pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
     }
     LNX_CUDA(cudaGetLastError());
@@ -663,7 +680,7 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
         return fail(LNX_ERR_INVALID, "lnx_run_scan: null required pointer");
     if (p->tiled)
         return run_scan_tiled(p, n_sols, n_init, max_run_iter, cells0, table, gf_params, weights, dt, stats, channel_mass, n_alive, final_cells,
-                              cells_out, field_out, potential_out, workspace, workspace_bytes, stream);
+                              cells_out, field_out, potential_out, workspace, workspace_bytes, stream, run_flags);
     const bool trajectory = cells_out || field_out || potential_out;
     const bool fused = use_fused(p, trajectory, run_flags);
     if (!workspace || workspace_bytes < (fused ? (size_t)256 : lnx_workspace_bytes(p)))

@@ -38,6 +38,7 @@ def _finite_params(gf_params: torch.Tensor, weights: torch.Tensor, average: bool
 # The last two are kept for A/B runs and as cross-checks in the tests.
 FUSED_VARIANT = 'tmem'
 FUSED_R16 = False  # older spelling of FUSED_VARIANT = 'r16'
+TILED_GENERIC = False  # tests / A-B runs: 64^3 one-channel one-kernel worlds through the generic tiled passes instead of lnx_tiled64.cuh
 FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the tiled multi-pass engine as a cross-check
 
 
@@ -80,6 +81,8 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
         flags |= _lib.LNX_RUN_FUSED_SMEM
     elif FUSED_VARIANT != 'tmem':
         raise ValueError(f'unknown FUSED_VARIANT {FUSED_VARIANT!r}')
+    if TILED_GENERIC:
+        flags |= _lib.LNX_RUN_TILED_GENERIC
     if _finite_params(gf_params, weights, update_fn.get_field_fn.average):
         flags |= _lib.LNX_RUN_ASSUME_FINITE
     dt = (1. / T.reshape(n_sols)).contiguous()  # runner.py:307

@@ -255,3 +255,72 @@ def test_r16_layouts_conflict_free_and_bijective(emul):
         assert _conflict_degree([e2((w * 32 + ln) >> 3, (w * 32 + ln) & 7, swz((w * 32 + ln) >> 3)) * 8 for ln in lanes], 8) == 1
     assert sorted(e1(i, k, l) for i in range(8) for k in range(16) for l in range(4)) == list(range(512))
     assert sorted(e2(c, m, swz(c)) for c in range(64) for m in range(8)) == list(range(512))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 64^3 thread-per-line engine (leniax_b200/csrc/lnx_tiled64.cuh), emulated lane by lane (tests/emul/lnx_t64_emul.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+EMUL64 = os.path.join(ROOT, 'tests', 'emul', 'liblnx_t64_emul.so')
+
+
+@pytest.fixture(scope='module')
+def emul64():
+    if not os.path.exists(EMUL64):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(EMUL64)
+    f, i, v = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
+    lib.lnx_t64_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v]
+    return lib
+
+
+def _shell_kernel_3d(R):
+    r = np.arange(-R, R)
+    g = np.stack(np.meshgrid(r, r, r, indexing='ij')).astype(np.float32) / R
+    dist = np.sqrt((g ** 2).sum(0))
+    kern = ((dist < 1) * (4 * dist * (1 - dist)) ** 4).astype(np.float32)
+    return (kern / kern.sum())[None]
+
+
+def test_t64_rfftn_matches_numpy(emul64):
+    rng = np.random.default_rng(0)
+    w = rng.random((64, 64, 64), dtype=np.float32)
+    spec = np.zeros((64, 64, 33), np.complex64)
+    emul64.lnx_t64_emul_rfftn(P(w), P(spec))
+    ref = np.fft.rfftn(w.astype(np.float64))
+    assert np.abs(spec - ref).max() < 2e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('gf_slug,gf_id,sf_slug,sf_id,mean', [('poly_quad4', 0, 'v1', 0, 1), ('gaussian', 1, 'v2', 1, 0)])
+def test_t64_step_matches_oracle(emul64, gf_slug, gf_id, sf_slug, sf_id, mean):
+    """One Lenia step of a 64^3 world (plane_fwd -> lead -> plane_inv) against the oracle, and the per-plane statistics
+    partial sums against direct sums in the rolled frame (statistics.py:64-100)."""
+    D, R = 64, 13
+    kp = [dict(k_slug='raw', k_params=_shell_kernel_3d(R), kf_slug='poly_quad', kf_params=[4], gf_slug=gf_slug, gf_params=[.15, .015], h=.7,
+               c_in=0, c_out=0)]
+    oK, om = lo.get_kernels_and_mapping(kp, [D, D, D], 1, R)
+    ktab = np.ascontiguousarray((oK[0, 0, 0][:, :, :33] / D ** 3).astype(np.complex64))
+    rng = np.random.default_rng(1)
+    state = (rng.random((D, D, D), dtype=np.float32) * 0.3).astype(np.float32)
+    gf, wt = om.get_gf_params(), om.get_kernels_weight_per_channel()
+    ns, of, op = lo.build_update_fn(om, sf_slug, bool(mean))(state[None, None], oK, gf, wt, np.float32(0.1))
+    st, pot, fld = state.copy(), np.zeros_like(state), np.zeros_like(state)
+    NP = emul64.lnx_t64_emul_np()
+    part = np.zeros((64, NP), np.float32)
+    shift = np.array([5, 60, 17], np.int32)
+    emul64.lnx_t64_emul_step(P(st), P(ktab), gf_id, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), mean, sf_id, 0.1, P(shift), P(pot), P(fld),
+                             P(part))
+    assert np.abs(pot - op[0, 0]).max() < 1e-6
+    assert np.abs(fld - of[0, 0]).max() < 2e-5
+    assert np.abs(st - ns[0, 0]).max() < 2e-6
+    a, f = state.astype(np.float64), of[0, 0].astype(np.float64)
+    gp = np.maximum(f, 0)
+    idx = np.indices((D, D, D))
+    xs = [((idx[d] - shift[d]) % D) - D // 2 for d in range(3)]
+    exp = ([(a > 1e-7).sum(), gp.sum(), (gp > 1e-7).sum(), (op[0, 0] > 1e-7).sum()] + [(a * x).sum() for x in xs] + [(a * x * x).sum() for x in xs] +
+           [(gp * x).sum() for x in xs] + [a.sum()])
+    tot = part.astype(np.float64).sum(0)
+    scale = [1, 1, 1, 1] + [np.abs(a * x).sum() for x in xs] + [1] * 3 + [np.abs(gp * x).sum() + 1 for x in xs] + [1]
+    for i, e in enumerate(exp):
+        assert abs(tot[i] - e) <= 3e-5 * max(abs(e), scale[i]), (i, tot[i], e)
+    assert np.all(tot[len(exp):] == 0)

@@ -409,10 +409,54 @@ def test_large_2d_world_matches_oracle(size, scale, steps):
     np.testing.assert_allclose(stats['inertia'].cpu().numpy(), ostats['inertia'], rtol=1e-3)
 
 
-def test_3d_worlds_match_oracle():
+@pytest.mark.parametrize('engine', ['line64', 'generic'])
+def test_3d_worlds_match_oracle(engine):
     """BASELINE config E shape (64^3, 1 channel / 1 kernel, raw spherical-shell kernel); the reference has no 3-D kernel
-    generator and no 3-D test: parity is oracle-only."""
+    generator and no 3-D test: parity is oracle-only.  Both engines: the thread-per-line kernels of
+    lnx_tiled64.cuh (default for this shape) and the generic tiled passes."""
     D, R, steps, n = 64, 13, 4, 3
+    runner.TILED_GENERIC = engine == 'generic'
+    try:
+        _check_3d_worlds(D, R, steps, n)
+    finally:
+        runner.TILED_GENERIC = False
+
+
+def test_3d_line64_engine_agrees_with_generic_tiled_passes_over_a_long_run():
+    """64^3 worlds, statistics-only scan of 48 steps with moving shift carries: every statistic and N of the thread-per-line
+    engine against the generic tiled passes (independent FFT code, same layouts)."""
+    D, R, steps, n = 64, 13, 48, 6
+    kern = kernels.sphere_nd(R, [1., [1.]], 'poly_quad', [4], device=DEV)
+    kp = [dict(k_slug='raw', k_params=kern, kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1., c_in=0, c_out=0)]
+    K, mapping = kernels.get_kernels_and_mapping(kp, [D, D, D], 1, R, device=DEV)
+    rng = np.random.default_rng(11)
+    worlds = np.zeros((n, 1, D, D, D), np.float32)
+    for i in range(n):  # off-centre blobs: the centroid (hence total_shift_idx) moves away from 0 on every axis
+        o = rng.integers(0, D - 24, 3)
+        worlds[i, 0, o[0]:o[0] + 24, o[1]:o[1] + 24, o[2]:o[2] + 24] = rng.random((24, 24, 24), dtype=np.float32) * (0.3 + 0.1 * i)
+    ufn = helpers.build_update_fn(K.shape, mapping)
+    sfn = statistics.build_compute_stats_fn({'R': R, 'T': 10}, {'world_size': [D, D, D]})
+    gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
+    cells = torch.from_numpy(worlds).to(DEV)[None]
+    res = {}
+    for eng in ('line64', 'generic'):
+        runner.TILED_GENERIC = eng == 'generic'
+        try:
+            res[eng] = runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn)
+        finally:
+            runner.TILED_GENERIC = False
+    (sa, fa), (sb, fb) = res['line64'], res['generic']
+    assert sa['N'].cpu().numpy().tolist() == sb['N'].cpu().numpy().tolist()
+    assert np.abs(fa.cpu().numpy() - fb.cpu().numpy()).max() < 2e-5
+    for k in sa:
+        if k == 'N':
+            continue
+        a, b = sa[k].cpu().numpy(), sb[k].cpu().numpy()
+        tol = dict(rtol=2e-3, atol=2e-3) if k in ('mass_angle_speed', 'mass_speed', 'mass_growth_dist') else dict(rtol=2e-4, atol=1e-5)
+        np.testing.assert_allclose(a, b, err_msg=k, **tol)
+
+
+def _check_3d_worlds(D, R, steps, n):
     kern = kernels.sphere_nd(R, [1., [1.]], 'poly_quad', [4], device=DEV)  # [1, 26, 26, 26]
     kp = [dict(k_slug='raw', k_params=kern, kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1., c_in=0, c_out=0)]
     K, mapping = kernels.get_kernels_and_mapping(kp, [D, D, D], 1, R, device=DEV)

@@ -150,16 +150,22 @@ def config_e(steps):
     cu = n * D**3 * steps
     tfl = cu * 136 / (ms * 1e-3) / 1e12
     gbs = cu * 32 / (ms * 1e-3) / 1e9
-    return {'config': 'E: 256 worlds 64^3, 1c1k, tiled multi-pass engine', 'steps': steps, 'ms': ms, 'cell_updates_per_s': cu / (ms * 1e-3),
-            'roofline': {'bound': 'fp32 (SURVEY) / hbm (this engine)', 'flop_per_cell_update': 136, 'achieved_tflops': tfl, 'peak_tflops': fp32_peak(),
-                         'frac': tfl / fp32_peak(), 'achieved_gbs_at_32B': gbs}, 'mean_N': float(out[0]['N'].mean())}
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    engine = 'generic tiled passes' if runner.TILED_GENERIC else 'thread-per-line passes (lnx_tiled64.cuh)'
+    return {'config': 'E: 256 worlds 64^3, 1c1k, ' + engine, 'steps': steps, 'ms': ms, 'cell_updates_per_s': cu / (ms * 1e-3),
+            'roofline': {'bound': 'fp32 (SURVEY) / hbm (multi-pass engines: 256 MB of state > L2)', 'flop_per_cell_update': 136, 'achieved_tflops': tfl,
+                         'peak_tflops': fp32_peak(), 'frac': tfl / fp32_peak(), 'achieved_gbs_at_32B': gbs, 'hbm_peak_gbs': hbm,
+                         'frac_hbm': gbs / hbm}, 'mean_N': float(out[0]['N'].mean())}
 
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--configs', default='A,C,D,E')
     ap.add_argument('--steps', type=int, default=0)
+    ap.add_argument('--tiled-generic', action='store_true', help='config E through the generic tiled passes (A/B run)')
     a = ap.parse_args()
+    runner.TILED_GENERIC = a.tiled_generic
     default_steps = {'A': 1024, 'C': 1024, 'D': 256, 'E': 64}
     fns = {'A': config_a, 'C': config_c, 'D': config_d, 'E': config_e}
     for c in a.configs.split(','):
