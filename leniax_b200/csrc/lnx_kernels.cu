@@ -9,6 +9,7 @@
 // There is no CPU fallback anywhere in this file.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -128,6 +129,21 @@ static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
     if (tc > 64) tc = 64;
     g->tc = tc;
     return true;
+}
+// experiment switch: resident CTAs per SM the lead kernel is compiled for (6: no spills, 166 registers; 8: 128 registers)
+static void launch_lead64(const PassBArgs& b, unsigned images, cudaStream_t st) {
+    static int minb = -1;
+    if (minb < 0) {
+        const char* e = getenv("LNX_T64_LEAD_MINB");
+        minb = e ? atoi(e) : 6;
+    }
+    const dim3 grid(lnx::t64::COLS / lnx::t64::LEAD_TPB, b.C, images);
+    if (minb == 8)
+        lnx::t64::lead_kernel<8><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
+    else if (minb == 10)
+        lnx::t64::lead_kernel<10><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
+    else
+        lnx::t64::lead_kernel<6><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
 }
 static bool is_cube64(const Geom& g) { return g.nd == 3 && g.dims[0] == 64 && g.dims[1] == 64 && g.dims[2] == 64; }
 static size_t tw_bytes(int logn) { return ((size_t)1 << (logn - 1)) * sizeof(float2); }  // shared-memory twiddle table of one pass
@@ -417,7 +433,7 @@ int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const floa
     b.n_init = 1;
     const long long M = g.spec / g.L;
     if (line64)
-        lnx::t64::lead_kernel<<<dim3(lnx::t64::COLS / lnx::t64::LEAD_TPB, 1, n_images), lnx::t64::LEAD_TPB, 0, st>>>(b);
+        th::launch_lead64(b, (unsigned)n_images, st);
     else
         lnx::tiled::pass_b_kernel<<<dim3((unsigned)((M + g.tc - 1) / g.tc), 1, n_images), lnx::tiled::TPB, th::smem_b(g), st>>>(b);
     lnx::tiled::expand_hermitian_kernel<<<dim3(1024, 1, n_images), 256, 0, st>>>(sb, static_cast<float2*>(spectra), g);
@@ -589,7 +605,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
         d.t = t;
         if (line64) {
             lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);
-            lnx::t64::lead_kernel<<<dim3(lnx::t64::COLS / lnx::t64::LEAD_TPB, 1, (unsigned)worlds), lnx::t64::LEAD_TPB, 0, st>>>(b);
+            th::launch_lead64(b, (unsigned)worlds, st);
             lnx::t64::plane_inv_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(c);
         } else {
             pass_a_kernel<<<grid_a, TPB, th::smem_a(g), st>>>(a);

@@ -218,44 +218,64 @@ LNX_HD void inv_pot_store(int lane, const float2* v, float* ps, float* pot_plane
         }
     }
 }
-// coalesced growth / mix / update of the plane + this lane's statistics partials (acc[NP_T], layout of tiled::pass_d_kernel)
+// coalesced growth / mix / update of the plane + this lane's statistics partials (acc[NP_T], layout of tiled::pass_d_kernel).
+// GF / SF >= 0: growth and state function fixed at compile time (reciprocal forms of the divisions, like the resident fused
+// kernel); GF < 0: selected per cell from cp (true divisions, like the generic tiled pass C).  Eight row pairs per batch: the
+// sixteen 128-bit loads of a batch are in flight together.
+template <int GF, int SF>
 LNX_HD void inv_update(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
                        const CellParams& cp, float* acc) {
+    constexpr int B = 8;
     const int hi = lane >> 4, n0 = (lane & 15) * 4;
     float colA[4] = {0.f, 0.f, 0.f, 0.f}, colG[4] = {0.f, 0.f, 0.f, 0.f};
     float mx1 = 0.f, mx21 = 0.f, gx1 = 0.f, cnt_a = 0.f, cnt_g = 0.f, cnt_p = 0.f;
-#pragma unroll 2
-    for (int it = 0; it < 32; ++it) {
-        const int r = 2 * it + hi, i = it * 128 + lane * 4;
-        const float4 pv = *reinterpret_cast<const float4*>(ps + (it + 32 * hi) * SRS + n0);
-        const float4 av = *reinterpret_cast<const float4*>(st + i);
-        const float a4[4] = {av.x, av.y, av.z, av.w};
-        const float p4[4] = {pv.x, pv.y, pv.z, pv.w};
-        float f4[4], n4[4];
-        const float x1 = (float)(((r - cp.sh1) & (N - 1)) - N / 2);
-        float rowa = 0.f, rowg = 0.f;
+    const float inv_wsum = cp.mean ? 1.0f / cp.wsum : 1.0f;
+#pragma unroll 1
+    for (int it0 = 0; it0 < 32; it0 += B) {
+        float4 avs[B], pvs[B];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            cnt_p += p4[e] > EPS ? 1.f : 0.f;
-            float f = 0.f + cp.wk * growth_dyn<true>(cp.gf_id, p4[e], cp.gc);
-            if (cp.mean) f = f / cp.wsum;
-            f4[e] = f;
-            const float a = a4[e];
-            n4[e] = state_update_dyn<true>(cp.state_fn, a, f, cp.dt);
-            const float gp = fmaxf(f, 0.f);
-            colA[e] += a;
-            colG[e] += gp;
-            rowa += a;
-            rowg += gp;
-            cnt_a += a > EPS ? 1.f : 0.f;
-            cnt_g += gp > EPS ? 1.f : 0.f;
+        for (int b = 0; b < B; ++b) avs[b] = *reinterpret_cast<const float4*>(st + (it0 + b) * 128 + lane * 4);
+#pragma unroll
+        for (int b = 0; b < B; ++b) pvs[b] = *reinterpret_cast<const float4*>(ps + (it0 + b + 32 * hi) * SRS + n0);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int it = it0 + b, r = 2 * it + hi, i = it * 128 + lane * 4;
+            const float a4[4] = {avs[b].x, avs[b].y, avs[b].z, avs[b].w};
+            const float p4[4] = {pvs[b].x, pvs[b].y, pvs[b].z, pvs[b].w};
+            float f4[4], n4[4];
+            const float x1 = (float)(((r - cp.sh1) & (N - 1)) - N / 2);
+            float rowa = 0.f, rowg = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                cnt_p += p4[e] > EPS ? 1.f : 0.f;
+                float f;
+                if constexpr (GF >= 0) {
+                    f = (cp.wk * growth<GF, true, GF != GF_POLY_QUAD4>(p4[e], cp.gc)) * inv_wsum;
+                } else {
+                    f = 0.f + cp.wk * growth_dyn<true>(cp.gf_id, p4[e], cp.gc);
+                    if (cp.mean) f = f / cp.wsum;
+                }
+                f4[e] = f;
+                const float a = a4[e];
+                if constexpr (GF >= 0)
+                    n4[e] = state_update<SF, true>(a, f, cp.dt);
+                else
+                    n4[e] = state_update_dyn<true>(cp.state_fn, a, f, cp.dt);
+                const float gp = fmaxf(f, 0.f);
+                colA[e] += a;
+                colG[e] += gp;
+                rowa += a;
+                rowg += gp;
+                cnt_a += a > EPS ? 1.f : 0.f;
+                cnt_g += gp > EPS ? 1.f : 0.f;
+            }
+            mx1 += rowa * x1;
+            mx21 += rowa * x1 * x1;
+            gx1 += rowg * x1;
+            *reinterpret_cast<float4*>(st + i) = make_float4(n4[0], n4[1], n4[2], n4[3]);
+            if (cells_out) *reinterpret_cast<float4*>(cells_out + i) = avs[b];
+            if (field_out) *reinterpret_cast<float4*>(field_out + i) = make_float4(f4[0], f4[1], f4[2], f4[3]);
         }
-        mx1 += rowa * x1;
-        mx21 += rowa * x1 * x1;
-        gx1 += rowg * x1;
-        *reinterpret_cast<float4*>(st + i) = make_float4(n4[0], n4[1], n4[2], n4[3]);
-        if (cells_out) *reinterpret_cast<float4*>(cells_out + i) = av;
-        if (field_out) *reinterpret_cast<float4*>(field_out + i) = make_float4(f4[0], f4[1], f4[2], f4[3]);
     }
     float m00 = 0.f, g00 = 0.f, mx2 = 0.f, mx22 = 0.f, gx2 = 0.f;
 #pragma unroll
@@ -285,6 +305,16 @@ LNX_HD void inv_update(int lane, const float* ps, float* __restrict__ st, float*
     acc[6 + 2 * MAXD] = gx2;
     acc[4 + 3 * MAXD] = m00;
 }
+// the common growth functions with the v1 update get compile-time variants, everything else the per-cell selection
+LNX_HD void inv_update_dispatch(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                                const CellParams& cp, float* acc) {
+    if (cp.state_fn == SF_V1 && cp.gf_id == GF_POLY_QUAD4)
+        inv_update<GF_POLY_QUAD4, SF_V1>(lane, ps, st, cells_out, field_out, cp, acc);
+    else if (cp.state_fn == SF_V1 && cp.gf_id == GF_GAUSSIAN)
+        inv_update<GF_GAUSSIAN, SF_V1>(lane, ps, st, cells_out, field_out, cp, acc);
+    else
+        inv_update<-1, -1>(lane, ps, st, cells_out, field_out, cp, acc);
+}
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------------
@@ -306,7 +336,8 @@ __global__ void __launch_bounds__(32) plane_fwd_kernel(PassAArgs P) {
 }
 
 // grid (33, C, worlds), 64 threads: thread = one spectral column
-__global__ void __launch_bounds__(LEAD_TPB) lead_kernel(PassBArgs P) {
+template <int MINB>
+__global__ void __launch_bounds__(LEAD_TPB, MINB) lead_kernel(PassBArgs P) {
     const int col = blockIdx.x * LEAD_TPB + threadIdx.x, c = blockIdx.y, w = blockIdx.z;
     const float2* src = P.spec + ((size_t)w * P.C + c) * ((size_t)N * COLS) + col;
     float2 v[64];
@@ -330,6 +361,9 @@ __global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P) {
     const int sol = w / P.n_init, init = w - sol * P.n_init;
     const size_t plane = (size_t)w * N + l;
     float2* pl = reinterpret_cast<float2*>(sm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)  // the state plane is needed after the two transform phases: have it in L2 by then
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.state + plane * PLANE_CELLS + (j * 32 + lane) * 32));
     inv_load(lane, P.pot_spec + plane * PLANE_SPEC, pl);
     __syncwarp();
     inv_cols(lane, pl);
@@ -356,8 +390,8 @@ __global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P) {
     inv_pot_store(lane, v, sm, P.potential_out ? P.potential_out + toff : nullptr);
     __syncwarp();
     float acc[NP_T];
-    inv_update(lane, sm, P.state + plane * PLANE_CELLS, P.cells_out ? P.cells_out + toff : nullptr, P.field_out ? P.field_out + toff : nullptr, cp,
-               acc);
+    inv_update_dispatch(lane, sm, P.state + plane * PLANE_CELLS, P.cells_out ? P.cells_out + toff : nullptr,
+                        P.field_out ? P.field_out + toff : nullptr, cp, acc);
 #pragma unroll
     for (int i = 0; i < NP_T; ++i) {
         float x = acc[i];

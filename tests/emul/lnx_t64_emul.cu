@@ -69,7 +69,7 @@ void lnx_t64_emul_step(float* state, const float2* ktab, int gf_id, float m, flo
         for (int i = 0; i < NP_T; ++i) tot[i] = 0.f;
         for (int lane = 0; lane < 32; ++lane) {
             float acc[NP_T];
-            inv_update(lane, sm.data(), state + (size_t)l * PLANE_CELLS, nullptr, field + (size_t)l * PLANE_CELLS, cp, acc);
+            inv_update_dispatch(lane, sm.data(), state + (size_t)l * PLANE_CELLS, nullptr, field + (size_t)l * PLANE_CELLS, cp, acc);
             for (int i = 0; i < NP_T; ++i) tot[i] += acc[i];
         }
         for (int i = 0; i < NP_T; ++i) partials[l * NP_T + i] = tot[i];

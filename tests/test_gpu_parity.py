@@ -452,7 +452,9 @@ def test_3d_line64_engine_agrees_with_generic_tiled_passes_over_a_long_run():
         if k == 'N':
             continue
         a, b = sa[k].cpu().numpy(), sb[k].cpu().numpy()
-        tol = dict(rtol=2e-3, atol=2e-3) if k in ('mass_angle_speed', 'mass_speed', 'mass_growth_dist') else dict(rtol=2e-4, atol=1e-5)
+        # potential_volume counts cells whose potential exceeds 1e-7: far from the blobs the potential IS rounding noise of that size
+        tol = (dict(rtol=2e-3, atol=2e-3) if k in ('mass_angle_speed', 'mass_speed', 'mass_growth_dist', 'potential_volume')
+               else dict(rtol=2e-4, atol=1e-5))
         np.testing.assert_allclose(a, b, err_msg=k, **tol)
 
 
