@@ -20,6 +20,7 @@
 #include "lnx_kernel_generic.cuh"
 #include "lnx_tiled.cuh"
 #include "lnx_tiled64.cuh"
+#include "lnx_tiled2k.cuh"
 #include "lnx_conv.cuh"
 
 
@@ -145,6 +146,16 @@ static void launch_lead64(const PassBArgs& b, unsigned images, cudaStream_t st) 
     else
         lnx::t64::lead_kernel<6><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
 }
+static bool line2k_plan(const Geom& g, int C, int K);
+static bool is_sq2k(const Geom& g) { return g.nd == 2 && g.dims[0] == 2048 && g.dims[1] == 2048; }
+// one thread per slab of partial sums while there are few worlds (a single 2048^2 world has 1024 slabs); 128 threads otherwise
+static unsigned pass_d_threads(const Geom& g, long long worlds) {
+    if (worlds >= 64) return 128;
+    unsigned t = 128;
+    while ((int)t < g.n_slabs && t < 32 * PASS_D_MAX_WARPS) t <<= 1;
+    return t;
+}
+static bool line2k_plan(const Geom& g, int C, int K) { return is_sq2k(g) && C == 1 && K == 1; }
 static bool is_cube64(const Geom& g) { return g.nd == 3 && g.dims[0] == 64 && g.dims[1] == 64 && g.dims[2] == 64; }
 static size_t tw_bytes(int logn) { return ((size_t)1 << (logn - 1)) * sizeof(float2); }  // shared-memory twiddle table of one pass
 static int log_inner(const Geom& g) { return g.logA2 > g.logA1 ? g.logA2 : g.logA1; }
@@ -158,6 +169,7 @@ static size_t smem_c(const Geom& g, int C) {
 }
 constexpr size_t SMEM_LIMIT = 220 * 1024;  // dynamic part; pass C also has ~1 KB of static shared memory
 
+static float2* g_tw2k[64] = {nullptr};  // (cos, sin)(2 pi i / 2048), i < 2048: twiddles of the four-step engine (lnx_tiled2k.cuh)
 static float2* g_tw[64] = {nullptr};  // library-owned twiddle master table per device: (cos, sin)(2 pi k / NMAX)
 static int ensure_tiled_init(int dev) {
     if (g_tw[dev]) return LNX_OK;
@@ -175,6 +187,21 @@ static int ensure_tiled_init(int dev) {
     if (e != cudaSuccess) {
         fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(e));
         return -1;
+    }
+    {
+        static float2 host2k[2048];
+        for (int k = 0; k < 2048; ++k) {
+            const double a = 2.0 * 3.14159265358979323846 * k / 2048;
+            host2k[k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        float2* d2 = nullptr;
+        e = cudaMalloc(&d2, sizeof(host2k));
+        if (e == cudaSuccess) e = cudaMemcpy(d2, host2k, sizeof(host2k), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        g_tw2k[dev] = d2;
     }
     g_tw[dev] = d;
     return LNX_OK;
@@ -343,7 +370,8 @@ size_t lnx_workspace_bytes(const lnx_plan* p);
 
 size_t lnx_kernel_table_bytes(const lnx_plan* p) {
     if (!p) return 0;
-    if (p->tiled) return (size_t)p->d.nb_kernels * p->g.spec * sizeof(float2);
+    // 2048^2 one-channel one-kernel plans hold the table twice: [n_sols][spec] in the generic layout, then in lnx_tiled2k.cuh's
+    if (p->tiled) return (size_t)(th::line2k_plan(p->g, p->d.nb_channels, p->d.nb_kernels) ? 2 : 1) * p->d.nb_kernels * p->g.spec * sizeof(float2);
     return (size_t)p->d.nb_kernels * KTAB_F4 * sizeof(float4);
 }
 
@@ -372,6 +400,12 @@ int lnx_kernels_prepare(const lnx_plan* p, int32_t n_sols, const void* K_fft, vo
                                                             p->d.nb_kernels, p->d.nb_slots, slots_dev, 1.0f / (float)p->g.cells);
         LNX_CUDA(cudaGetLastError());
         LNX_CUDA(cudaFreeAsync(slots_dev, st));
+        if (th::line2k_plan(p->g, p->d.nb_channels, p->d.nb_kernels)) {
+            lnx::t2k::gather_ktab_kernel<<<dim3(2048, 1, n_sols), 256, 0, st>>>(static_cast<const float2*>(K_fft),
+                                                                               static_cast<float2*>(table) + (size_t)n_sols * p->g.spec, p->d.nb_slots,
+                                                                               p->d.slot[0], 1.0f / (float)p->g.cells);
+            LNX_CUDA(cudaGetLastError());
+        }
         return LNX_OK;
     }
     PrepArgs a;
@@ -600,10 +634,22 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
         grid_c(g.n_slabs, 1, (unsigned)worlds);
     // 64^3 worlds with one channel and one kernel (BASELINE config E): thread-per-line passes of lnx_tiled64.cuh
     const bool line64 = th::is_cube64(g) && C == 1 && K == 1 && !(run_flags & LNX_RUN_TILED_GENERIC);
+    // 2048^2 worlds with one channel and one kernel (BASELINE config D): four-step warp-per-line passes of lnx_tiled2k.cuh
+    const bool line2k = th::line2k_plan(g, C, K) && !(run_flags & LNX_RUN_TILED_GENERIC);
+    lnx::t2k::Extra x2k;
+    x2k.tw = th::g_tw2k[p->device];
+    x2k.ktab = static_cast<const float2*>(table) + (size_t)n_sols * g.spec;
     for (int t = 0; t < max_run_iter; ++t) {
         c.t = t;
         d.t = t;
-        if (line64) {
+        if (line2k) {
+            PassDArgs dprev = d;  // statistics of the previous step: finalised by an extra CTA of this step's lead launch
+            dprev.t = t - 1;
+            lnx::t2k::rows_fwd_kernel<<<dim3(1024, 1, (unsigned)worlds), 32, 0, st>>>(a, x2k);
+            lnx::t2k::lead_kernel<<<dim3(1026, 1, (unsigned)worlds), 32, 0, st>>>(b, x2k, dprev);
+            lnx::t2k::rows_inv_kernel<<<dim3(1024, 1, (unsigned)worlds), 32, 0, st>>>(c, x2k);
+            if (t + 1 < max_run_iter) continue;
+        } else if (line64) {
             lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);
             th::launch_lead64(b, (unsigned)worlds, st);
             lnx::t64::plane_inv_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(c);
@@ -612,7 +658,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), st>>>(b);
             pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), st>>>(c);
         }
-        pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
+        pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, st>>>(d);
     }
     LNX_CUDA(cudaGetLastError());
     return LNX_OK;

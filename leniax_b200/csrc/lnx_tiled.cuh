@@ -468,11 +468,13 @@ struct PassDArgs {
     int C, n_sols, n_init, max_iter, t;
     float R, stats_dt;
 };
-__global__ void __launch_bounds__(128) pass_d_kernel(PassDArgs P) {
+constexpr int PASS_D_MAX_WARPS = 16;
+// the work of one CTA (1..16 warps) for world w; also called from the four-step engine's lead kernel (lnx_tiled2k.cuh), where the
+// statistics of step t are finalised by an extra CTA of step t+1's lead launch (nothing before rows_inv needs the carry)
+__device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w) {
     __shared__ float tot[NP_T];
-    __shared__ float red[NP_T][4];
+    __shared__ float red[NP_T][PASS_D_MAX_WARPS];
     const Geom& g = P.g;
-    const int w = blockIdx.x;
     const int sol = w / P.n_init, init = w - sol * P.n_init;
     float acc[NP_T];
 #pragma unroll
@@ -491,7 +493,11 @@ __global__ void __launch_bounds__(128) pass_d_kernel(PassDArgs P) {
         if (lane == 0) red[i][wid] = v;
     }
     __syncthreads();
-    if (threadIdx.x < NP_T) tot[threadIdx.x] = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+    if (threadIdx.x < NP_T) {
+        float v = 0.f;
+        for (int j = 0; j < (int)(blockDim.x >> 5); ++j) v += red[threadIdx.x][j];
+        tot[threadIdx.x] = v;
+    }
     __syncthreads();
     if (threadIdx.x != 0) return;
     WorldCarry S = P.carry[w];
@@ -562,6 +568,9 @@ __global__ void __launch_bounds__(128) pass_d_kernel(PassDArgs P) {
     for (int k = 0; k < ST_COUNT; ++k) P.stats[k * plane + idx] = out[k];
     for (int c = 0; c < C; ++c) P.channel_mass[idx * C + c] = cm[c];
     P.n_alive[w] = S.n_alive;
+}
+__global__ void __launch_bounds__(32 * PASS_D_MAX_WARPS) pass_d_kernel(PassDArgs P) {  // 4..16 warps: see pass_d_threads()
+    pass_d_body(P, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,373 @@
+// Four-step engine for one-channel one-kernel 2048 x 2048 worlds (BASELINE config D): every 2048-point transform is done by
+// ONE WARP as 2048 = 32 x 64 — lane n1 transforms the 64 elements n1 + 32 n2 in its registers (fft_dif<64>), multiplies by the
+// twiddles W^(n1 k2), the warp transposes once through shared memory, lane t transforms the two 32-point lines k2 = t, t + 32
+// (fft_dif<32>).  No radix pass over shared memory, no CTA-wide barrier, every global access a full coalesced line:
+//
+//   rows_fwd   warp per row pair (2p, 2p+1): packed complex transform, untangle, TRANSPOSED half spectrum T[k][row] (16 B per k)
+//   lead       warp per spectral column k = one contiguous 16 KB line of T: transform along the leading axis, multiply by the
+//              kernel table (stored in the warp's register order), inverse transform, in the same layout
+//   rows_inv   warp per row pair: gather the 16-byte pieces of its two rows, retangle, inverse transform, growth / update /
+//              statistics partials of the row pair (= one slab of lnx_tiled.cuh, so pass D is shared)
+//
+// n = n1 + 32 n2, k = k2 + 64 k1:  W_2048^(nk) = W_2048^(n1 k2) W_32^(n1 k1) W_64^(n2 k2).
+// The per-lane phase functions are __host__ __device__: tests/emul/lnx_t64_emul.cu runs them lane by lane on the CPU.
+// Reference: leniax/core.py:52-102, :163-319, leniax/statistics.py:36-126.
+#pragma once
+#include "lnx_tiled64.cuh"
+
+namespace lnx {
+namespace t2k {
+
+using t64::br6;
+using tiled::MAXD;
+using tiled::NP_T;
+using tiled::PassAArgs;
+using tiled::PassBArgs;
+using tiled::PassCArgs;
+using tiled::PassDArgs;
+using tiled::WorldCarry;
+
+constexpr int N = 2048, HALF = 1025;
+constexpr int EXS = 33;                  // row stride (complex) of the 64 x 32 exchange buffer: odd => both views conflict-free
+constexpr int SMEM_C2 = 64 * EXS;        // complex values of shared memory per warp (also holds 2048 complex / 4096 floats)
+constexpr size_t SPEC = (size_t)HALF * N;  // complex values of one transposed half spectrum
+
+LNX_HDC int br5(int x) { return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4); }
+// leading-axis frequency held by lane t in register q (= h * 32 + j) after the second stage
+LNX_HDC int freq_of(int q, int t) { return (t + 32 * (q >> 5)) + 64 * br5(q & 31); }
+
+// v[j] *= W^(lane * k2) (INV: conjugate), k2 = br6(j); tab[i] = (cos, sin)(2 pi i / 2048).  Sixteen exact table values per lane,
+// every twiddle one product of two of them.
+template <bool INV>
+LNX_HD void twiddle64(int lane, float2* v, const float2* __restrict__ tab) {
+    float2 ta[8], tc[8];
+#pragma unroll
+    for (int a = 1; a < 8; ++a) {
+        ta[a] = LNX_T64_LDG(tab + ((lane * a) & (N - 1)));
+        tc[a] = LNX_T64_LDG(tab + ((lane * 8 * a) & (N - 1)));
+    }
+#pragma unroll
+    for (int j = 1; j < 64; ++j) {
+        const int k2 = br6(j), a = k2 & 7, c = k2 >> 3;
+        float2 w;
+        if (c == 0)
+            w = ta[a];
+        else if (a == 0)
+            w = tc[c];
+        else
+            w = make_float2(ta[a].x * tc[c].x - ta[a].y * tc[c].y, ta[a].y * tc[c].x + ta[a].x * tc[c].y);
+        v[j] = INV ? rot_inv(v[j], w.x, w.y) : rot_fwd(v[j], w.x, w.y);
+    }
+}
+
+// ---- forward: v[n2] = x[lane + 32 n2]  ->  u[h * 32 + j] = X[(lane + 32 h) + 64 br5(j)] ----
+LNX_HD void fs_fwd_a(int lane, float2* v, const float2* __restrict__ tab) {
+    fft_dif<64>(v);
+    twiddle64<false>(lane, v, tab);
+}
+LNX_HD void fs_fwd_store(int lane, const float2* v, float2* ex) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) ex[br6(j) * EXS + lane] = v[j];
+}
+LNX_HD void fs_fwd_b(int lane, const float2* ex, float2* u) {
+#pragma unroll
+    for (int q = 0; q < 64; ++q) u[q] = ex[(lane + 32 * (q >> 5)) * EXS + (q & 31)];
+    fft_dif<32>(u);
+    fft_dif<32>(u + 32);
+}
+// ---- inverse (un-normalised): u as above  ->  v[n2] = x[lane + 32 n2] ----
+LNX_HD void fs_inv_a(float2* u) {
+    ifft_dit<32>(u);
+    ifft_dit<32>(u + 32);
+}
+LNX_HD void fs_inv_store(int lane, const float2* u, float2* ex) {
+#pragma unroll
+    for (int q = 0; q < 64; ++q) ex[(lane + 32 * (q >> 5)) * EXS + (q & 31)] = u[q];
+}
+LNX_HD void fs_inv_b(int lane, const float2* ex, float2* v, const float2* __restrict__ tab) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = ex[br6(j) * EXS + lane];
+    twiddle64<true>(lane, v, tab);
+    ifft_dit<64>(v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// rows_fwd phases
+// ---------------------------------------------------------------------------------------------------------------------
+LNX_HD void rf_load(int lane, const float* __restrict__ rows, float2* v) {  // rows: two consecutive rows of 2048 reals
+#pragma unroll
+    for (int n2 = 0; n2 < 64; ++n2) v[n2] = make_float2(LNX_T64_LDG(rows + lane + 32 * n2), LNX_T64_LDG(rows + N + lane + 32 * n2));
+}
+LNX_HD void rf_nat_store(int lane, const float2* u, float2* nat) {  // spectrum of the packed line in natural order
+#pragma unroll
+    for (int q = 0; q < 64; ++q) nat[freq_of(q, lane)] = u[q];
+}
+// untangle the two real rows and write T[k][2p], T[k][2p + 1] (one 16-byte store per k); dst = T + 2p
+LNX_HD void rf_untangle_store(int lane, const float2* nat, float2* __restrict__ dst) {
+#pragma unroll 8
+    for (int i = 0; i <= 32; ++i) {
+        const int k = lane + 32 * i;
+        if (i == 32 && lane != 0) break;  // k = 1024: lane 0 only
+        const float2 zk = nat[k], zc = nat[(N - k) & (N - 1)];
+        const float4 ab = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), 0.5f * (zc.x - zk.x));
+        *reinterpret_cast<float4*>(dst + (size_t)k * N) = ab;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// lead phases: src / dst = line k of T (2048 complex), kt = line k of the kernel table in register order
+// ---------------------------------------------------------------------------------------------------------------------
+LNX_HD void ld_load(int lane, const float2* __restrict__ src, float2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < 64; ++n2) v[n2] = LNX_T64_LDG(src + lane + 32 * n2);
+}
+LNX_HD void ld_mul(int lane, float2* u, const float2* __restrict__ kt) {
+#pragma unroll
+    for (int q = 0; q < 64; ++q) u[q] = cmul(u[q], LNX_T64_LDG(kt + q * 32 + lane));
+}
+LNX_HD void ld_store(int lane, float2* __restrict__ dst, const float2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < 64; ++n2) dst[lane + 32 * n2] = v[n2];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// rows_inv phases
+// ---------------------------------------------------------------------------------------------------------------------
+// gather the spectra of rows 2p, 2p+1 (src = P + 2p, 16 bytes per k) and retangle into the natural-order packed spectrum
+LNX_HD void ri_gather(int lane, const float2* __restrict__ src, float2* nat) {
+#pragma unroll 8
+    for (int i = 0; i <= 32; ++i) {
+        const int k = lane + 32 * i;
+        if (i == 32 && lane != 0) break;
+        const float4 ab = LNX_T64_LDG(reinterpret_cast<const float4*>(src + (size_t)k * N));
+        nat[k] = make_float2(ab.x - ab.w, ab.y + ab.z);
+        if (k != 0 && k != N / 2) nat[N - k] = make_float2(ab.x + ab.w, ab.z - ab.y);
+    }
+}
+LNX_HD void ri_nat_load(int lane, const float2* nat, float2* u) {
+#pragma unroll
+    for (int q = 0; q < 64; ++q) u[q] = nat[freq_of(q, lane)];
+}
+// potentials of the row pair -> shared memory as two rows of 2048 floats [and the trajectory output]
+LNX_HD void ri_pot_store(int lane, const float2* v, float* ps) {
+#pragma unroll
+    for (int n2 = 0; n2 < 64; ++n2) {
+        ps[lane + 32 * n2] = v[n2].x;
+        ps[N + lane + 32 * n2] = v[n2].y;
+    }
+}
+struct CellParams2 {
+    int gf_id, state_fn, mean;
+    GfConst gc;
+    float wk, wsum, dt;
+    int sh0, sh1;
+    int row0;   // first row of the pair
+};
+// coalesced growth / mix / update of the two rows (4096 consecutive cells) + this lane's statistics partials
+template <int GF, int SF>
+LNX_HD void ri_update(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                      float* __restrict__ pot_out, const CellParams2& cp, float* acc) {
+    constexpr int B = 8;
+    float m00 = 0.f, g00 = 0.f, mx0 = 0.f, mx20 = 0.f, gx0 = 0.f, mx1 = 0.f, mx21 = 0.f, gx1 = 0.f, cnt_a = 0.f, cnt_g = 0.f, cnt_p = 0.f;
+    const float inv_wsum = cp.mean ? 1.0f / cp.wsum : 1.0f;
+    const float x0a = (float)(((cp.row0 - cp.sh0) & (N - 1)) - N / 2), x0b = (float)(((cp.row0 + 1 - cp.sh0) & (N - 1)) - N / 2);
+#pragma unroll 1
+    for (int it0 = 0; it0 < 32; it0 += B) {
+        float4 avs[B], pvs[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) avs[b] = *reinterpret_cast<const float4*>(st + (it0 + b) * 128 + lane * 4);
+#pragma unroll
+        for (int b = 0; b < B; ++b) pvs[b] = *reinterpret_cast<const float4*>(ps + (it0 + b) * 128 + lane * 4);
+        const float x0 = it0 < 16 ? x0a : x0b;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int i = (it0 + b) * 128 + lane * 4, n0 = i & (N - 1);
+            const float a4[4] = {avs[b].x, avs[b].y, avs[b].z, avs[b].w};
+            const float p4[4] = {pvs[b].x, pvs[b].y, pvs[b].z, pvs[b].w};
+            float f4[4], n4[4];
+            float sa = 0.f, sg = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                cnt_p += p4[e] > EPS ? 1.f : 0.f;
+                float f;
+                if constexpr (GF >= 0) {
+                    f = (cp.wk * growth<GF, true, GF != GF_POLY_QUAD4>(p4[e], cp.gc)) * inv_wsum;
+                } else {
+                    f = 0.f + cp.wk * growth_dyn<true>(cp.gf_id, p4[e], cp.gc);
+                    if (cp.mean) f = f / cp.wsum;
+                }
+                f4[e] = f;
+                const float a = a4[e];
+                if constexpr (GF >= 0)
+                    n4[e] = state_update<SF, true>(a, f, cp.dt);
+                else
+                    n4[e] = state_update_dyn<true>(cp.state_fn, a, f, cp.dt);
+                const float gp = fmaxf(f, 0.f);
+                const float x1 = (float)(((n0 + e - cp.sh1) & (N - 1)) - N / 2);
+                sa += a;
+                sg += gp;
+                const float ax = a * x1;
+                mx1 += ax;
+                mx21 += ax * x1;
+                gx1 += gp * x1;
+                cnt_a += a > EPS ? 1.f : 0.f;
+                cnt_g += gp > EPS ? 1.f : 0.f;
+            }
+            m00 += sa;
+            g00 += sg;
+            mx0 += sa * x0;
+            mx20 += sa * x0 * x0;
+            gx0 += sg * x0;
+            *reinterpret_cast<float4*>(st + i) = make_float4(n4[0], n4[1], n4[2], n4[3]);
+            if (cells_out) *reinterpret_cast<float4*>(cells_out + i) = avs[b];
+            if (field_out) *reinterpret_cast<float4*>(field_out + i) = make_float4(f4[0], f4[1], f4[2], f4[3]);
+            if (pot_out) *reinterpret_cast<float4*>(pot_out + i) = pvs[b];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) acc[i] = 0.f;
+    acc[0] = cnt_a;
+    acc[1] = g00;
+    acc[2] = cnt_g;
+    acc[3] = cnt_p;
+    acc[4] = mx0;
+    acc[5] = mx1;
+    acc[4 + MAXD] = mx20;
+    acc[5 + MAXD] = mx21;
+    acc[4 + 2 * MAXD] = gx0;
+    acc[5 + 2 * MAXD] = gx1;
+    acc[4 + 3 * MAXD] = m00;
+}
+LNX_HD void ri_update_dispatch(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                               float* __restrict__ pot_out, const CellParams2& cp, float* acc) {
+    if (cp.state_fn == SF_V1 && cp.gf_id == GF_POLY_QUAD4)
+        ri_update<GF_POLY_QUAD4, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc);
+    else if (cp.state_fn == SF_V1 && cp.gf_id == GF_GAUSSIAN)
+        ri_update<GF_GAUSSIAN, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc);
+    else
+        ri_update<-1, -1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc);
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels (one warp per CTA)
+// ---------------------------------------------------------------------------------------------------------------------
+struct Extra {            // what the generic argument structs do not carry
+    const float2* tw;     // (cos, sin)(2 pi i / 2048), i < 2048
+    const float2* ktab;   // [n_sols][1025][2048] kernel table in register order, pre-scaled by 1 / cells
+};
+
+// grid (1024 row pairs, 1, worlds)
+__global__ void __launch_bounds__(32) rows_fwd_kernel(PassAArgs P, Extra X) {
+    __shared__ __align__(16) float2 sm[SMEM_C2];
+    const int lane = threadIdx.x, p = blockIdx.x, w = blockIdx.z;
+    float2 v[64];
+    rf_load(lane, P.state + (size_t)w * N * N + (size_t)(2 * p) * N, v);
+    fs_fwd_a(lane, v, X.tw);
+    fs_fwd_store(lane, v, sm);
+    __syncwarp();
+    fs_fwd_b(lane, sm, v);
+    __syncwarp();
+    rf_nat_store(lane, v, sm);
+    __syncwarp();
+    rf_untangle_store(lane, sm, P.spec + (size_t)w * SPEC + 2 * p);
+}
+
+// grid (1025 columns + 1, 1, worlds).  CTA 1025 of world w finalises the statistics of the PREVIOUS step (pass D; D.t < 0: none):
+// nothing before rows_inv needs the carry it updates, so that latency-bound single-CTA job leaves the critical path.
+__global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArgs D) {
+    __shared__ __align__(16) float2 sm[SMEM_C2];
+    const int lane = threadIdx.x, k = blockIdx.x, w = blockIdx.z;
+    if (k == HALF) {
+        if (D.t >= 0) tiled::pass_d_body(D, w);
+        return;
+    }
+    const int sol = w / P.n_init;
+    const float2* kt = X.ktab + (size_t)sol * SPEC + (size_t)k * N;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)  // the 16 KB table line is needed after the forward transform: have it in L1 by then
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(kt + (j * 32 + lane) * 16));
+    float2 v[64];
+    ld_load(lane, P.spec + (size_t)w * SPEC + (size_t)k * N, v);
+    fs_fwd_a(lane, v, X.tw);
+    fs_fwd_store(lane, v, sm);
+    __syncwarp();
+    fs_fwd_b(lane, sm, v);
+    ld_mul(lane, v, kt);
+    fs_inv_a(v);
+    __syncwarp();
+    fs_inv_store(lane, v, sm);
+    __syncwarp();
+    fs_inv_b(lane, sm, v, X.tw);
+    ld_store(lane, P.pot_spec + (size_t)w * SPEC + (size_t)k * N, v);
+}
+
+// grid (1024 row pairs, 1, worlds)
+__global__ void __launch_bounds__(32) rows_inv_kernel(PassCArgs P, Extra X) {
+    __shared__ __align__(16) float2 sm[SMEM_C2];
+    const int lane = threadIdx.x, p = blockIdx.x, w = blockIdx.z;
+    const int sol = w / P.n_init, init = w - sol * P.n_init;
+    float* st = P.state + (size_t)w * N * N + (size_t)(2 * p) * N;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)  // the state rows are needed after the transform: have them in L1 by then
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(st + (j * 32 + lane) * 32));
+    ri_gather(lane, P.pot_spec + (size_t)w * SPEC + 2 * p, sm);
+    __syncwarp();
+    float2 v[64];
+    ri_nat_load(lane, sm, v);
+    fs_inv_a(v);
+    __syncwarp();
+    fs_inv_store(lane, v, sm);
+    __syncwarp();
+    fs_inv_b(lane, sm, v, X.tw);
+    __syncwarp();
+    ri_pot_store(lane, v, reinterpret_cast<float*>(sm));
+    __syncwarp();
+    const WorldCarry cr = P.carry[w];
+    CellParams2 cp;
+    cp.gf_id = P.gf_id[0];
+    cp.state_fn = P.state_fn;
+    cp.mean = P.mean;
+    cp.gc = gf_prepare(cp.gf_id, P.gf_params[(size_t)sol * 2], P.gf_params[(size_t)sol * 2 + 1]);
+    cp.wk = P.weights[sol];
+    cp.wsum = cp.wk;
+    cp.dt = P.dt[sol];
+    cp.sh0 = cr.shift[0];
+    cp.sh1 = cr.shift[1];
+    cp.row0 = 2 * p;
+    const size_t traj = ((size_t)sol * P.max_iter + P.t) * P.n_init + init;
+    const size_t toff = traj * ((size_t)N * N) + (size_t)(2 * p) * N;
+    float acc[NP_T];
+    ri_update_dispatch(lane, reinterpret_cast<const float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
+                       P.field_out ? P.field_out + toff : nullptr, P.potential_out ? P.potential_out + toff : nullptr, cp, acc);
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) {
+        float x = acc[i];
+        if (i < 5 + 3 * MAXD) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        }
+        acc[i] = x;
+    }
+    if (lane == 0) {
+        float* q = P.partials + ((size_t)w * (N / 2) + p) * NP_T;
+#pragma unroll
+        for (int i = 0; i < NP_T; ++i) q[i] = acc[i];
+    }
+}
+
+// K_fft full complex [n_sols][nb_slots][2048][2048] (reference layout [m][k]) -> tab[sol][k][q * 32 + t] = K[m = freq_of(q, t)][k] * scale
+__global__ void gather_ktab_kernel(const float2* __restrict__ K_fft, float2* __restrict__ tab, int nb_slots, int slot, float scale) {
+    const int sol = blockIdx.z;
+    const float2* src = K_fft + ((size_t)sol * nb_slots + slot) * ((size_t)N * N);
+    float2* dst = tab + (size_t)sol * SPEC;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < SPEC; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i >> 11), r = (int)(i & (N - 1));
+        const float2 x = src[(size_t)freq_of(r >> 5, r & 31) * N + k];
+        dst[i] = make_float2(x.x * scale, x.y * scale);
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace t2k
+}  // namespace lnx

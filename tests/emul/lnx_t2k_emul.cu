@@ -1,0 +1,124 @@
+// CPU emulator of the 2048^2 four-step engine (TEST ONLY — not part of the product library).
+// Runs the exact __host__ __device__ per-lane phase functions of leniax_b200/csrc/lnx_tiled2k.cuh lane by lane, with the
+// kernels' __syncwarp points as loop boundaries.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../../leniax_b200/csrc/lnx_tiled2k.cuh"
+
+using namespace lnx;
+
+namespace e2k {
+using namespace lnx::t2k;
+
+static std::vector<float2> make_tab() {
+    std::vector<float2> tab(N);
+    for (int i = 0; i < N; ++i) {
+        const double a = 2.0 * 3.14159265358979323846 * i / N;
+        tab[i] = make_float2((float)cos(a), (float)sin(a));
+    }
+    return tab;
+}
+// rows_fwd_kernel for row pair p
+static void rows_fwd(const float* state, float2* T, int p, const float2* tab) {
+    std::vector<float2> sm(SMEM_C2), regs(32 * 64);
+    for (int lane = 0; lane < 32; ++lane) {
+        float2* v = regs.data() + lane * 64;
+        rf_load(lane, state + (size_t)(2 * p) * N, v);
+        fs_fwd_a(lane, v, tab);
+        fs_fwd_store(lane, v, sm.data());
+    }
+    for (int lane = 0; lane < 32; ++lane) fs_fwd_b(lane, sm.data(), regs.data() + lane * 64);
+    for (int lane = 0; lane < 32; ++lane) rf_nat_store(lane, regs.data() + lane * 64, sm.data());
+    for (int lane = 0; lane < 32; ++lane) rf_untangle_store(lane, sm.data(), T + 2 * p);
+}
+// lead_kernel for column k; kt == nullptr: forward only, natural-order result to out[m * HALF + k]
+static void lead(const float2* T, const float2* kt, float2* P, float2* fwd_out, int k, const float2* tab) {
+    std::vector<float2> sm(SMEM_C2), regs(32 * 64);
+    for (int lane = 0; lane < 32; ++lane) {
+        float2* v = regs.data() + lane * 64;
+        ld_load(lane, T + (size_t)k * N, v);
+        fs_fwd_a(lane, v, tab);
+        fs_fwd_store(lane, v, sm.data());
+    }
+    for (int lane = 0; lane < 32; ++lane) fs_fwd_b(lane, sm.data(), regs.data() + lane * 64);
+    if (!kt) {
+        for (int lane = 0; lane < 32; ++lane)
+            for (int q = 0; q < 64; ++q) fwd_out[(size_t)freq_of(q, lane) * HALF + k] = regs[lane * 64 + q];
+        return;
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+        float2* v = regs.data() + lane * 64;
+        ld_mul(lane, v, kt + (size_t)k * N);
+        fs_inv_a(v);
+    }
+    for (int lane = 0; lane < 32; ++lane) fs_inv_store(lane, regs.data() + lane * 64, sm.data());
+    for (int lane = 0; lane < 32; ++lane) {
+        float2* v = regs.data() + lane * 64;
+        fs_inv_b(lane, sm.data(), v, tab);
+        ld_store(lane, P + (size_t)k * N, v);
+    }
+}
+}  // namespace e2k
+
+extern "C" {
+
+// world [2048][2048] -> natural-order half spectrum [2048][1025]
+void lnx_t2k_emul_rfft2(const float* world, float2* spec) {
+    using namespace e2k;
+    const std::vector<float2> tab = make_tab();
+    std::vector<float2> T(SPEC);
+    for (int p = 0; p < N / 2; ++p) rows_fwd(world, T.data(), p, tab.data());
+    for (int k = 0; k < HALF; ++k) lead(T.data(), nullptr, nullptr, spec, k, tab.data());
+}
+
+// one Lenia step of one 2048^2 world, one channel / one kernel.  K_half: [2048][1025] complex (natural order, unscaled).
+void lnx_t2k_emul_step(float* state, const float2* K_half, int gf_id, float m, float s, float wk, int mean, int state_fn, float dt,
+                       const int* shift, float* potential, float* field, float* partials) {
+    using namespace e2k;
+    const std::vector<float2> tab = make_tab();
+    std::vector<float2> T(SPEC), Pm(SPEC), kt(SPEC);
+    const float scale = 1.0f / ((float)N * (float)N);
+    for (size_t i = 0; i < SPEC; ++i) {  // gather_ktab_kernel
+        const int k = (int)(i >> 11), r = (int)(i & (N - 1));
+        const float2 x = K_half[(size_t)freq_of(r >> 5, r & 31) * HALF + k];
+        kt[i] = make_float2(x.x * scale, x.y * scale);
+    }
+    for (int p = 0; p < N / 2; ++p) rows_fwd(state, T.data(), p, tab.data());
+    for (int k = 0; k < HALF; ++k) lead(T.data(), kt.data(), Pm.data(), nullptr, k, tab.data());
+    for (int p = 0; p < N / 2; ++p) {  // rows_inv_kernel
+        std::vector<float2> sm(SMEM_C2), regs(32 * 64);
+        for (int lane = 0; lane < 32; ++lane) ri_gather(lane, Pm.data() + 2 * p, sm.data());
+        for (int lane = 0; lane < 32; ++lane) {
+            ri_nat_load(lane, sm.data(), regs.data() + lane * 64);
+            fs_inv_a(regs.data() + lane * 64);
+        }
+        for (int lane = 0; lane < 32; ++lane) fs_inv_store(lane, regs.data() + lane * 64, sm.data());
+        for (int lane = 0; lane < 32; ++lane) fs_inv_b(lane, sm.data(), regs.data() + lane * 64, tab.data());
+        for (int lane = 0; lane < 32; ++lane) ri_pot_store(lane, regs.data() + lane * 64, reinterpret_cast<float*>(sm.data()));
+        CellParams2 cp;
+        cp.gf_id = gf_id;
+        cp.state_fn = state_fn;
+        cp.mean = mean;
+        cp.gc = gf_prepare(gf_id, m, s);
+        cp.wk = wk;
+        cp.wsum = wk;
+        cp.dt = dt;
+        cp.sh0 = shift[0];
+        cp.sh1 = shift[1];
+        cp.row0 = 2 * p;
+        float tot[NP_T];
+        for (int i = 0; i < NP_T; ++i) tot[i] = 0.f;
+        const size_t off = (size_t)(2 * p) * N;
+        for (int lane = 0; lane < 32; ++lane) {
+            float acc[NP_T];
+            ri_update_dispatch(lane, reinterpret_cast<const float*>(sm.data()), state + off, nullptr, field + off, potential + off, cp, acc);
+            for (int i = 0; i < NP_T; ++i) tot[i] += acc[i];
+        }
+        for (int i = 0; i < NP_T; ++i) partials[p * NP_T + i] = tot[i];
+    }
+}
+
+int lnx_t2k_emul_np() { return lnx::t2k::NP_T; }
+
+}  // extern "C"

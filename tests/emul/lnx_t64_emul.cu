@@ -1,6 +1,7 @@
 // CPU emulator of the 64^3 thread-per-line engine (TEST ONLY — not part of the product library).
 // Runs the exact __host__ __device__ per-lane phase functions of leniax_b200/csrc/lnx_tiled64.cuh lane by lane, with the
 // kernels' __syncwarp points as loop boundaries.
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "../../leniax_b200/csrc/lnx_tiled64.cuh"

@@ -324,3 +324,67 @@ def test_t64_step_matches_oracle(emul64, gf_slug, gf_id, sf_slug, sf_id, mean):
     for i, e in enumerate(exp):
         assert abs(tot[i] - e) <= 3e-5 * max(abs(e), scale[i]), (i, tot[i], e)
     assert np.all(tot[len(exp):] == 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2048^2 four-step engine (leniax_b200/csrc/lnx_tiled2k.cuh), emulated lane by lane (tests/emul/lnx_t2k_emul.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+EMUL2K = os.path.join(ROOT, 'tests', 'emul', 'liblnx_t2k_emul.so')
+
+
+@pytest.fixture(scope='module')
+def emul2k():
+    if not os.path.exists(EMUL2K):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(EMUL2K)
+    f, i, v = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
+    lib.lnx_t2k_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v]
+    return lib
+
+
+def test_t2k_rfft2_matches_numpy(emul2k):
+    rng = np.random.default_rng(0)
+    w = rng.random((2048, 2048), dtype=np.float32)
+    spec = np.zeros((2048, 1025), np.complex64)
+    emul2k.lnx_t2k_emul_rfft2(P(w), P(spec))
+    ref = np.fft.rfft2(w.astype(np.float64))
+    assert np.abs(spec - ref).max() < 3e-7 * np.abs(ref).max()
+
+
+def test_t2k_step_matches_oracle(emul2k):
+    """One Lenia step of a 2048^2 world, R = 52 (rows_fwd -> lead -> rows_inv) against the oracle, and the statistics partial
+    sums of the row pairs against direct sums in the rolled frame (statistics.py:64-100)."""
+    S, R = 2048, 52
+    kp = [dict(k_slug='circle_2d', k_params=[1., [1.]], kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1.,
+               c_in=0, c_out=0)]
+    oK, om = lo.get_kernels_and_mapping(kp, [S, S], 1, R)
+    Kh = np.ascontiguousarray(oK[0, 0, 0][:, :S // 2 + 1].astype(np.complex64))
+    rng = np.random.default_rng(2)
+    state = np.zeros((S, S), np.float32)
+    for _ in range(40):
+        y, x = rng.integers(0, S - 200, 2)
+        state[y:y + 200, x:x + 200] = rng.random((200, 200), dtype=np.float32) * 0.35
+    gf, wt = om.get_gf_params(), om.get_kernels_weight_per_channel()
+    ns, of, op = lo.build_update_fn(om)(state[None, None], oK, gf, wt, np.float32(0.1))
+    st, pot, fld = state.copy(), np.zeros_like(state), np.zeros_like(state)
+    NP = emul2k.lnx_t2k_emul_np()
+    part = np.zeros((S // 2, NP), np.float32)
+    shift = np.array([700, 1999], np.int32)
+    emul2k.lnx_t2k_emul_step(P(st), P(Kh), 0, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), 1, 0, 0.1, P(shift), P(pot), P(fld), P(part))
+    assert np.abs(pot - op[0, 0]).max() < 1e-6
+    assert np.abs(fld - of[0, 0]).max() < 5e-5
+    assert np.abs(st - ns[0, 0]).max() < 5e-6
+    a, f = state.astype(np.float64), of[0, 0].astype(np.float64)
+    gp = np.maximum(f, 0)
+    idx = np.indices((S, S))
+    xs = [((idx[d] - shift[d]) % S) - S // 2 for d in range(2)]
+    exp = {0: (a > 1e-7).sum(), 1: gp.sum(), 2: (gp > 1e-7).sum(), 4: (a * xs[0]).sum(), 5: (a * xs[1]).sum(), 7: (a * xs[0] ** 2).sum(),
+           8: (a * xs[1] ** 2).sum(), 10: (gp * xs[0]).sum(), 11: (gp * xs[1]).sum(), 13: a.sum()}
+    tot = part.astype(np.float64).sum(0)
+    for i in range(NP):
+        if i == 3:  # potential > eps: far from the patterns the potential is rounding noise of that size
+            assert abs(tot[3] - (op[0, 0] > 1e-7).sum()) < 1e-3 * S * S
+            continue
+        e = exp.get(i, 0.)
+        assert abs(tot[i] - e) <= 2e-5 * max(abs(e), 1.), (i, tot[i], e)
