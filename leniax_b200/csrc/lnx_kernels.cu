@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/leniax_b200.h"
 #include "lnx_resident_common.cuh"
@@ -156,6 +158,62 @@ static unsigned pass_d_threads(const Geom& g, long long worlds) {
     return t;
 }
 static bool line2k_plan(const Geom& g, int C, int K) { return is_sq2k(g) && C == 1 && K == 1; }
+
+// Graph executables whose last launch may still be running: destroyed by a later call once their event has completed.
+struct RetiredGraph {
+    cudaGraphExec_t exec;
+    cudaGraph_t graph;
+    cudaEvent_t done;
+};
+static std::mutex g_retired_mu;
+static std::vector<RetiredGraph> g_retired;
+static void sweep_retired_graphs() {
+    std::lock_guard<std::mutex> lk(g_retired_mu);
+    for (size_t i = 0; i < g_retired.size();) {
+        if (cudaEventQuery(g_retired[i].done) == cudaSuccess) {
+            cudaGraphExecDestroy(g_retired[i].exec);
+            cudaGraphDestroy(g_retired[i].graph);
+            cudaEventDestroy(g_retired[i].done);
+            g_retired[i] = g_retired.back();
+            g_retired.pop_back();
+        } else {
+            ++i;
+        }
+    }
+    (void)cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
+}
+// the time loop of the four-step engine: rows_fwd, lead (+ pass D of the previous step), rows_inv captured once, replayed per step
+static int run_steps_2k(const PassAArgs& a, const PassBArgs& b, const PassCArgs& c, const PassDArgs& d, const lnx::t2k::Extra& x,
+                        unsigned worlds, int steps, cudaStream_t st) {
+    using namespace lnx::t2k;
+    sweep_retired_graphs();
+    cudaStream_t cap = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t done = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(a, x);
+        lead_kernel<<<dim3(1026, 1, worlds), 32, 0, cap>>>(b, x, d);
+        rows_inv_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(c, x);
+        e = cudaStreamEndCapture(cap, &graph);
+    }
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    for (int t = 0; e == cudaSuccess && t < steps; ++t) e = cudaGraphLaunch(exec, st);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(done, st);
+    if (cap) cudaStreamDestroy(cap);
+    if (e != cudaSuccess) {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (done) cudaEventDestroy(done);
+        return fail(LNX_ERR_CUDA, "four-step engine: graph capture / launch failed: %s", cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lk(g_retired_mu);
+    g_retired.push_back({exec, graph, done});
+    return LNX_OK;
+}
 static bool is_cube64(const Geom& g) { return g.nd == 3 && g.dims[0] == 64 && g.dims[1] == 64 && g.dims[2] == 64; }
 static size_t tw_bytes(int logn) { return ((size_t)1 << (logn - 1)) * sizeof(float2); }  // shared-memory twiddle table of one pass
 static int log_inner(const Geom& g) { return g.logA2 > g.logA1 ? g.logA2 : g.logA1; }
@@ -184,6 +242,8 @@ static int ensure_tiled_init(int dev) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lnx::t2k::rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lnx::t2k::ROWS_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lnx::t2k::rows_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lnx::t2k::ROWS_SMEM);
     if (e != cudaSuccess) {
         fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(e));
         return -1;
@@ -643,12 +703,12 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
         c.t = t;
         d.t = t;
         if (line2k) {
-            PassDArgs dprev = d;  // statistics of the previous step: finalised by an extra CTA of this step's lead launch
-            dprev.t = t - 1;
-            lnx::t2k::rows_fwd_kernel<<<dim3(1024, 1, (unsigned)worlds), 32, 0, st>>>(a, x2k);
-            lnx::t2k::lead_kernel<<<dim3(1026, 1, (unsigned)worlds), 32, 0, st>>>(b, x2k, dprev);
-            lnx::t2k::rows_inv_kernel<<<dim3(1024, 1, (unsigned)worlds), 32, 0, st>>>(c, x2k);
-            if (t + 1 < max_run_iter) continue;
+            // the three launches have step-independent arguments (the step index lives in the carry): replay one captured graph
+            const int rc = th::run_steps_2k(a, b, c, d, x2k, (unsigned)worlds, max_run_iter, st);
+            if (rc != LNX_OK) return rc;
+            d.t = max_run_iter - 1;  // the last step's statistics
+            pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, st>>>(d);
+            break;
         } else if (line64) {
             lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);
             th::launch_lead64(b, (unsigned)worlds, st);

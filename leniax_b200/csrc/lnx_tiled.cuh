@@ -271,6 +271,8 @@ struct WorldCarry {   // per world, device memory
     float should_continue, prev_mass, prev_sign, n_alive;
     int mono, vol;
     float init_cm[MAX_C];
+    int step, pending;   // device-side step counter (graph-replayed loops, lnx_tiled2k.cuh): index of the step whose inverse pass runs
+                         // next; pending = 1: that pass has run and its statistics wait to be finalised
 };
 struct PassCArgs {
     float* state;             // [worlds][C][rows][A2]  updated in place
@@ -471,7 +473,7 @@ struct PassDArgs {
 constexpr int PASS_D_MAX_WARPS = 16;
 // the work of one CTA (1..16 warps) for world w; also called from the four-step engine's lead kernel (lnx_tiled2k.cuh), where the
 // statistics of step t are finalised by an extra CTA of step t+1's lead launch (nothing before rows_inv needs the carry)
-__device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w) {
+__device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w, const int t) {
     __shared__ float tot[NP_T];
     __shared__ float red[NP_T][PASS_D_MAX_WARPS];
     const Geom& g = P.g;
@@ -501,7 +503,7 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w) {
     __syncthreads();
     if (threadIdx.x != 0) return;
     WorldCarry S = P.carry[w];
-    const int nd = g.nd, C = P.C, t = P.t;
+    const int nd = g.nd, C = P.C;
     // reference: R**2 is used for every "volume" normalisation whatever the dimension (statistics.py:70-78)
     const float R2 = P.R * P.R, R = P.R, dt = P.stats_dt;
     float m00 = 0.f, cm[MAX_C];
@@ -562,6 +564,8 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w) {
     S.n_alive += S.should_continue;
     S.prev_mass = mass;
     S.prev_sign = sign;
+    S.step = t + 1;
+    S.pending = 0;
     P.carry[w] = S;
     const size_t plane = (size_t)P.n_sols * P.max_iter * P.n_init;
     const size_t idx = ((size_t)sol * P.max_iter + t) * P.n_init + init;
@@ -570,7 +574,7 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w) {
     P.n_alive[w] = S.n_alive;
 }
 __global__ void __launch_bounds__(32 * PASS_D_MAX_WARPS) pass_d_kernel(PassDArgs P) {  // 4..16 warps: see pass_d_threads()
-    pass_d_body(P, blockIdx.x);
+    pass_d_body(P, blockIdx.x, P.t);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -114,6 +114,41 @@ LNX_HD void rf_untangle_store(int lane, const float2* nat, float2* __restrict__ 
     }
 }
 
+// The same two jobs done by a CTA of ROWS_WARPS warps (one row pair each) together, so that the 16-byte pieces of the transposed
+// layout combine into full 128-byte lines: thread -> (warp buffer w = tid & 7, k = (tid >> 3) + 32 i); the eight pieces of one k are
+// adjacent in T.  nat_all: ROWS_WARPS buffers of NATS complex values (NATS = 2 mod 16: the eight buffers sit in distinct banks).
+constexpr int ROWS_WARPS = 8;
+constexpr int NATS = SMEM_C2 + 2;
+LNX_HD void rf8_untangle_store(int tid, const float2* nat_all, float2* __restrict__ dst) {  // dst = T + first row of the CTA
+    const int w = tid & 7, kq = tid >> 3;
+    const float2* nat = nat_all + w * NATS;
+#pragma unroll 8
+    for (int i = 0; i <= 32; ++i) {
+        const int k = kq + 32 * i;
+        if (i == 32 && kq != 0) break;  // k = 1024
+        const float2 zk = nat[k], zc = nat[(N - k) & (N - 1)];
+        const float4 ab = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), 0.5f * (zc.x - zk.x));
+        *reinterpret_cast<float4*>(dst + (size_t)k * N + 2 * w) = ab;
+    }
+}
+LNX_HD void ri8_gather(int tid, const float2* __restrict__ src, float2* nat_all) {  // src = P + first row of the CTA
+    const int w = tid & 7, kq = tid >> 3;
+    float2* nat = nat_all + w * NATS;
+    float4 ab[33];
+#pragma unroll
+    for (int i = 0; i <= 32; ++i) {
+        const int k = kq + 32 * i;
+        if (i < 32 || kq == 0) ab[i] = LNX_T64_LDG(reinterpret_cast<const float4*>(src + (size_t)k * N + 2 * w));
+    }
+#pragma unroll
+    for (int i = 0; i <= 32; ++i) {
+        const int k = kq + 32 * i;
+        if (i == 32 && kq != 0) break;
+        nat[k] = make_float2(ab[i].x - ab[i].w, ab[i].y + ab[i].z);
+        if (k != 0 && k != N / 2) nat[N - k] = make_float2(ab[i].x + ab[i].w, ab[i].z - ab[i].y);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // lead phases: src / dst = line k of T (2048 complex), kt = line k of the kernel table in register order
 // ---------------------------------------------------------------------------------------------------------------------
@@ -257,10 +292,13 @@ struct Extra {            // what the generic argument structs do not carry
     const float2* ktab;   // [n_sols][1025][2048] kernel table in register order, pre-scaled by 1 / cells
 };
 
-// grid (1024 row pairs, 1, worlds)
-__global__ void __launch_bounds__(32) rows_fwd_kernel(PassAArgs P, Extra X) {
-    __shared__ __align__(16) float2 sm[SMEM_C2];
-    const int lane = threadIdx.x, p = blockIdx.x, w = blockIdx.z;
+// grid (128, 1, worlds), 8 warps: warp j of CTA c owns row pair 8 c + j; dynamic shared memory ROWS_SMEM bytes
+constexpr size_t ROWS_SMEM = (size_t)ROWS_WARPS * NATS * sizeof(float2);
+__global__ void __launch_bounds__(32 * ROWS_WARPS) rows_fwd_kernel(PassAArgs P, Extra X) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* nat_all = reinterpret_cast<float2*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, p = blockIdx.x * ROWS_WARPS + wid, w = blockIdx.z;
+    float2* sm = nat_all + wid * NATS;
     float2 v[64];
     rf_load(lane, P.state + (size_t)w * N * N + (size_t)(2 * p) * N, v);
     fs_fwd_a(lane, v, X.tw);
@@ -269,17 +307,20 @@ __global__ void __launch_bounds__(32) rows_fwd_kernel(PassAArgs P, Extra X) {
     fs_fwd_b(lane, sm, v);
     __syncwarp();
     rf_nat_store(lane, v, sm);
-    __syncwarp();
-    rf_untangle_store(lane, sm, P.spec + (size_t)w * SPEC + 2 * p);
+    __syncthreads();
+    rf8_untangle_store(threadIdx.x, nat_all, P.spec + (size_t)w * SPEC + 2 * ROWS_WARPS * blockIdx.x);
 }
 
-// grid (1025 columns + 1, 1, worlds).  CTA 1025 of world w finalises the statistics of the PREVIOUS step (pass D; D.t < 0: none):
-// nothing before rows_inv needs the carry it updates, so that latency-bound single-CTA job leaves the critical path.
+// grid (1025 columns + 1, 1, worlds).  CTA 1025 of world w finalises the statistics of the PREVIOUS step (pass D) if one is pending:
+// nothing before rows_inv needs the carry it updates, so that latency-bound single-CTA job leaves the critical path.  The step index
+// lives in the world's carry (WorldCarry::step / pending), so the three launches of a step have step-independent arguments and the
+// time loop is ONE captured CUDA graph replayed max_run_iter times (the launches are 10-25 us each: issuing them one by one from the
+// host was the bottleneck).
 __global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArgs D) {
     __shared__ __align__(16) float2 sm[SMEM_C2];
     const int lane = threadIdx.x, k = blockIdx.x, w = blockIdx.z;
     if (k == HALF) {
-        if (D.t >= 0) tiled::pass_d_body(D, w);
+        if (D.carry[w].pending) tiled::pass_d_body(D, w, D.carry[w].step);
         return;
     }
     const int sol = w / P.n_init;
@@ -302,17 +343,19 @@ __global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArg
     ld_store(lane, P.pot_spec + (size_t)w * SPEC + (size_t)k * N, v);
 }
 
-// grid (1024 row pairs, 1, worlds)
-__global__ void __launch_bounds__(32) rows_inv_kernel(PassCArgs P, Extra X) {
-    __shared__ __align__(16) float2 sm[SMEM_C2];
-    const int lane = threadIdx.x, p = blockIdx.x, w = blockIdx.z;
+// grid (128, 1, worlds), 8 warps, dynamic shared memory ROWS_SMEM bytes
+__global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, Extra X) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* nat_all = reinterpret_cast<float2*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, p = blockIdx.x * ROWS_WARPS + wid, w = blockIdx.z;
+    float2* sm = nat_all + wid * NATS;
     const int sol = w / P.n_init, init = w - sol * P.n_init;
     float* st = P.state + (size_t)w * N * N + (size_t)(2 * p) * N;
 #pragma unroll
     for (int j = 0; j < 4; ++j)  // the state rows are needed after the transform: have them in L1 by then
         asm volatile("prefetch.global.L1 [%0];" ::"l"(st + (j * 32 + lane) * 32));
-    ri_gather(lane, P.pot_spec + (size_t)w * SPEC + 2 * p, sm);
-    __syncwarp();
+    ri8_gather(threadIdx.x, P.pot_spec + (size_t)w * SPEC + 2 * ROWS_WARPS * blockIdx.x, nat_all);
+    __syncthreads();
     float2 v[64];
     ri_nat_load(lane, sm, v);
     fs_inv_a(v);
@@ -335,7 +378,7 @@ __global__ void __launch_bounds__(32) rows_inv_kernel(PassCArgs P, Extra X) {
     cp.sh0 = cr.shift[0];
     cp.sh1 = cr.shift[1];
     cp.row0 = 2 * p;
-    const size_t traj = ((size_t)sol * P.max_iter + P.t) * P.n_init + init;
+    const size_t traj = ((size_t)sol * P.max_iter + cr.step) * P.n_init + init;
     const size_t toff = traj * ((size_t)N * N) + (size_t)(2 * p) * N;
     float acc[NP_T];
     ri_update_dispatch(lane, reinterpret_cast<const float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
@@ -353,6 +396,7 @@ __global__ void __launch_bounds__(32) rows_inv_kernel(PassCArgs P, Extra X) {
         float* q = P.partials + ((size_t)w * (N / 2) + p) * NP_T;
 #pragma unroll
         for (int i = 0; i < NP_T; ++i) q[i] = acc[i];
+        if (p == 0) const_cast<WorldCarry*>(P.carry)[w].pending = 1;  // (only pass D, in a later launch, reads it)
     }
 }
 

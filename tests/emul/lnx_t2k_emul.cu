@@ -19,18 +19,22 @@ static std::vector<float2> make_tab() {
     }
     return tab;
 }
-// rows_fwd_kernel for row pair p
-static void rows_fwd(const float* state, float2* T, int p, const float2* tab) {
-    std::vector<float2> sm(SMEM_C2), regs(32 * 64);
-    for (int lane = 0; lane < 32; ++lane) {
-        float2* v = regs.data() + lane * 64;
-        rf_load(lane, state + (size_t)(2 * p) * N, v);
-        fs_fwd_a(lane, v, tab);
-        fs_fwd_store(lane, v, sm.data());
+// rows_fwd_kernel for CTA c (row pairs 8 c .. 8 c + 7)
+static void rows_fwd(const float* state, float2* T, int c, const float2* tab) {
+    std::vector<float2> nat_all(ROWS_WARPS * NATS), regs(32 * 64);
+    for (int wid = 0; wid < ROWS_WARPS; ++wid) {
+        const int p = c * ROWS_WARPS + wid;
+        float2* sm = nat_all.data() + wid * NATS;
+        for (int lane = 0; lane < 32; ++lane) {
+            float2* v = regs.data() + lane * 64;
+            rf_load(lane, state + (size_t)(2 * p) * N, v);
+            fs_fwd_a(lane, v, tab);
+            fs_fwd_store(lane, v, sm);
+        }
+        for (int lane = 0; lane < 32; ++lane) fs_fwd_b(lane, sm, regs.data() + lane * 64);
+        for (int lane = 0; lane < 32; ++lane) rf_nat_store(lane, regs.data() + lane * 64, sm);
     }
-    for (int lane = 0; lane < 32; ++lane) fs_fwd_b(lane, sm.data(), regs.data() + lane * 64);
-    for (int lane = 0; lane < 32; ++lane) rf_nat_store(lane, regs.data() + lane * 64, sm.data());
-    for (int lane = 0; lane < 32; ++lane) rf_untangle_store(lane, sm.data(), T + 2 * p);
+    for (int tid = 0; tid < 32 * ROWS_WARPS; ++tid) rf8_untangle_store(tid, nat_all.data(), T + 2 * ROWS_WARPS * c);
 }
 // lead_kernel for column k; kt == nullptr: forward only, natural-order result to out[m * HALF + k]
 static void lead(const float2* T, const float2* kt, float2* P, float2* fwd_out, int k, const float2* tab) {
@@ -68,7 +72,7 @@ void lnx_t2k_emul_rfft2(const float* world, float2* spec) {
     using namespace e2k;
     const std::vector<float2> tab = make_tab();
     std::vector<float2> T(SPEC);
-    for (int p = 0; p < N / 2; ++p) rows_fwd(world, T.data(), p, tab.data());
+    for (int c = 0; c < N / 2 / ROWS_WARPS; ++c) rows_fwd(world, T.data(), c, tab.data());
     for (int k = 0; k < HALF; ++k) lead(T.data(), nullptr, nullptr, spec, k, tab.data());
 }
 
@@ -84,18 +88,22 @@ void lnx_t2k_emul_step(float* state, const float2* K_half, int gf_id, float m, f
         const float2 x = K_half[(size_t)freq_of(r >> 5, r & 31) * HALF + k];
         kt[i] = make_float2(x.x * scale, x.y * scale);
     }
-    for (int p = 0; p < N / 2; ++p) rows_fwd(state, T.data(), p, tab.data());
+    for (int c = 0; c < N / 2 / ROWS_WARPS; ++c) rows_fwd(state, T.data(), c, tab.data());
     for (int k = 0; k < HALF; ++k) lead(T.data(), kt.data(), Pm.data(), nullptr, k, tab.data());
-    for (int p = 0; p < N / 2; ++p) {  // rows_inv_kernel
-        std::vector<float2> sm(SMEM_C2), regs(32 * 64);
-        for (int lane = 0; lane < 32; ++lane) ri_gather(lane, Pm.data() + 2 * p, sm.data());
+    for (int c = 0; c < N / 2 / ROWS_WARPS; ++c) {  // rows_inv_kernel, CTA c
+      std::vector<float2> nat_all(ROWS_WARPS * NATS);
+      for (int tid = 0; tid < 32 * ROWS_WARPS; ++tid) ri8_gather(tid, Pm.data() + 2 * ROWS_WARPS * c, nat_all.data());
+      for (int wid = 0; wid < ROWS_WARPS; ++wid) {
+        const int p = c * ROWS_WARPS + wid;
+        float2* smp = nat_all.data() + wid * NATS;
+        std::vector<float2> regs(32 * 64);
         for (int lane = 0; lane < 32; ++lane) {
-            ri_nat_load(lane, sm.data(), regs.data() + lane * 64);
+            ri_nat_load(lane, smp, regs.data() + lane * 64);
             fs_inv_a(regs.data() + lane * 64);
         }
-        for (int lane = 0; lane < 32; ++lane) fs_inv_store(lane, regs.data() + lane * 64, sm.data());
-        for (int lane = 0; lane < 32; ++lane) fs_inv_b(lane, sm.data(), regs.data() + lane * 64, tab.data());
-        for (int lane = 0; lane < 32; ++lane) ri_pot_store(lane, regs.data() + lane * 64, reinterpret_cast<float*>(sm.data()));
+        for (int lane = 0; lane < 32; ++lane) fs_inv_store(lane, regs.data() + lane * 64, smp);
+        for (int lane = 0; lane < 32; ++lane) fs_inv_b(lane, smp, regs.data() + lane * 64, tab.data());
+        for (int lane = 0; lane < 32; ++lane) ri_pot_store(lane, regs.data() + lane * 64, reinterpret_cast<float*>(smp));
         CellParams2 cp;
         cp.gf_id = gf_id;
         cp.state_fn = state_fn;
@@ -112,10 +120,11 @@ void lnx_t2k_emul_step(float* state, const float2* K_half, int gf_id, float m, f
         const size_t off = (size_t)(2 * p) * N;
         for (int lane = 0; lane < 32; ++lane) {
             float acc[NP_T];
-            ri_update_dispatch(lane, reinterpret_cast<const float*>(sm.data()), state + off, nullptr, field + off, potential + off, cp, acc);
+            ri_update_dispatch(lane, reinterpret_cast<const float*>(smp), state + off, nullptr, field + off, potential + off, cp, acc);
             for (int i = 0; i < NP_T; ++i) tot[i] += acc[i];
         }
         for (int i = 0; i < NP_T; ++i) partials[p * NP_T + i] = tot[i];
+      }
     }
 }
 
