@@ -704,10 +704,11 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
         d.t = t;
         if (line2k) {
             // the three launches have step-independent arguments (the step index lives in the carry): replay one captured graph
+            d.g.n_slabs = 1024 / lnx::t2k::ROWS_WARPS;  // rows_inv writes one row of partial sums per CTA (eight row pairs)
             const int rc = th::run_steps_2k(a, b, c, d, x2k, (unsigned)worlds, max_run_iter, st);
             if (rc != LNX_OK) return rc;
             d.t = max_run_iter - 1;  // the last step's statistics
-            pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, st>>>(d);
+            pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
             break;
         } else if (line64) {
             lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);

@@ -332,10 +332,21 @@ __global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArg
     ld_load(lane, P.spec + (size_t)w * SPEC + (size_t)k * N, v);
     fs_fwd_a(lane, v, X.tw);
     fs_fwd_store(lane, v, sm);
+    // the two halves of the table line are requested one phase before they are used (all 254 registers are busy otherwise and
+    // the multiply waited for its loads)
+    float2 ka[32], kb[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) ka[q] = __ldg(kt + q * 32 + lane);
     __syncwarp();
     fs_fwd_b(lane, sm, v);
-    ld_mul(lane, v, kt);
-    fs_inv_a(v);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) kb[q] = __ldg(kt + (32 + q) * 32 + lane);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) v[q] = cmul(v[q], ka[q]);
+    ifft_dit<32>(v);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) v[32 + q] = cmul(v[32 + q], kb[q]);
+    ifft_dit<32>(v + 32);
     __syncwarp();
     fs_inv_store(lane, v, sm);
     __syncwarp();
@@ -392,12 +403,21 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
         }
         acc[i] = x;
     }
+    // the eight row pairs of the CTA are summed here, so pass D (one small CTA inside the next lead launch) reads 128 slabs, not 1024
+    __syncthreads();  // every warp is done with its buffer
+    float* red = reinterpret_cast<float*>(nat_all);
     if (lane == 0) {
-        float* q = P.partials + ((size_t)w * (N / 2) + p) * NP_T;
 #pragma unroll
-        for (int i = 0; i < NP_T; ++i) q[i] = acc[i];
-        if (p == 0) const_cast<WorldCarry*>(P.carry)[w].pending = 1;  // (only pass D, in a later launch, reads it)
+        for (int i = 0; i < NP_T; ++i) red[wid * NP_T + i] = acc[i];
     }
+    __syncthreads();
+    if (threadIdx.x < NP_T) {
+        float x = 0.f;
+#pragma unroll
+        for (int j = 0; j < ROWS_WARPS; ++j) x += red[j * NP_T + threadIdx.x];
+        P.partials[((size_t)w * (N / 2 / ROWS_WARPS) + blockIdx.x) * NP_T + threadIdx.x] = x;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) const_cast<WorldCarry*>(P.carry)[w].pending = 1;  // (only pass D, in a later launch, reads it)
 }
 
 // K_fft full complex [n_sols][nb_slots][2048][2048] (reference layout [m][k]) -> tab[sol][k][q * 32 + t] = K[m = freq_of(q, t)][k] * scale
