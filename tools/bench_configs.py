@@ -129,7 +129,8 @@ def config_d(steps):
     gbs = cu * 32 / (ms * 1e-3) / 1e9
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     hbm = peaks.get('hbm_gbs', 6650.0)
-    return {'config': 'D: one 2048x2048 world, 1c1k, R=52, tiled multi-pass engine', 'steps': steps, 'ms': ms, 'cell_updates_per_s': cu / (ms * 1e-3),
+    engine = 'generic tiled passes' if runner.TILED_GENERIC else 'four-step warp-per-line passes (lnx_tiled2k.cuh), CUDA-graph step loop'
+    return {'config': 'D: one 2048x2048 world, 1c1k, R=52, ' + engine, 'steps': steps, 'ms': ms, 'cell_updates_per_s': cu / (ms * 1e-3),
             'roofline': {'bound': 'hbm', 'bytes_per_cell_update': 32, 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
                          'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'},
             'N': float(out[0]['N'][0, 0]), 'note': 'the 48 MiB working set fits the 126 MB L2: algorithmic bytes, not DRAM traffic'}
@@ -163,7 +164,7 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--configs', default='A,C,D,E')
     ap.add_argument('--steps', type=int, default=0)
-    ap.add_argument('--tiled-generic', action='store_true', help='config E through the generic tiled passes (A/B run)')
+    ap.add_argument('--tiled-generic', action='store_true', help='configs D / E through the generic tiled passes (A/B run)')
     a = ap.parse_args()
     runner.TILED_GENERIC = a.tiled_generic
     default_steps = {'A': 1024, 'C': 1024, 'D': 256, 'E': 64}
