@@ -182,7 +182,7 @@ static void sweep_retired_graphs() {
     }
     (void)cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
 }
-// the time loop of the four-step engine: rows_fwd, lead (+ pass D of the previous step), rows_inv captured once, replayed per step
+// the time loop of the four-step engine: lead (+ pass D of the previous step) and the fused rows kernel captured once, replayed per step
 static int run_steps_2k(const PassAArgs& a, const PassBArgs& b, const PassCArgs& c, const PassDArgs& d, const lnx::t2k::Extra& x,
                         unsigned worlds, int steps, cudaStream_t st) {
     using namespace lnx::t2k;
@@ -194,12 +194,16 @@ static int run_steps_2k(const PassAArgs& a, const PassBArgs& b, const PassCArgs&
     cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
-        rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(a, x);
+        // a step = lead + the fused (inverse rows, update, forward rows of the next step) kernel
         lead_kernel<<<dim3(1026, 1, worlds), 32, 0, cap>>>(b, x, d);
-        rows_inv_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(c, x);
+        rows_inv_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(c, x, a.spec);
         e = cudaStreamEndCapture(cap, &graph);
     }
     if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e == cudaSuccess) {  // the first step's forward rows
+        rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, st>>>(a, x);
+        e = cudaGetLastError();
+    }
     for (int t = 0; e == cudaSuccess && t < steps; ++t) e = cudaGraphLaunch(exec, st);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(done, st);
@@ -711,9 +715,10 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
             break;
         } else if (line64) {
-            lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);
+            // a step = lead + the fused (inverse planes, update, forward planes of the next step) kernel
+            if (t == 0) lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);
             th::launch_lead64(b, (unsigned)worlds, st);
-            lnx::t64::plane_inv_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(c);
+            lnx::t64::plane_inv_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(c, a.spec);
         } else {
             pass_a_kernel<<<grid_a, TPB, th::smem_a(g), st>>>(a);
             pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), st>>>(b);

@@ -199,9 +199,10 @@ struct CellParams2 {
     int row0;   // first row of the pair
 };
 // coalesced growth / mix / update of the two rows (4096 consecutive cells) + this lane's statistics partials
+// keep_state: the new cells also replace the potentials in `ps` (the fused step kernel transforms them for the next step)
 template <int GF, int SF>
-LNX_HD void ri_update(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
-                      float* __restrict__ pot_out, const CellParams2& cp, float* acc) {
+LNX_HD void ri_update(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                      float* __restrict__ pot_out, const CellParams2& cp, float* acc, bool keep_state) {
     constexpr int B = 8;
     float m00 = 0.f, g00 = 0.f, mx0 = 0.f, mx20 = 0.f, gx0 = 0.f, mx1 = 0.f, mx21 = 0.f, gx1 = 0.f, cnt_a = 0.f, cnt_g = 0.f, cnt_p = 0.f;
     const float inv_wsum = cp.mean ? 1.0f / cp.wsum : 1.0f;
@@ -254,6 +255,7 @@ LNX_HD void ri_update(int lane, const float* ps, float* __restrict__ st, float* 
             mx20 += sa * x0 * x0;
             gx0 += sg * x0;
             *reinterpret_cast<float4*>(st + i) = make_float4(n4[0], n4[1], n4[2], n4[3]);
+            if (keep_state) *reinterpret_cast<float4*>(ps + i) = make_float4(n4[0], n4[1], n4[2], n4[3]);
             if (cells_out) *reinterpret_cast<float4*>(cells_out + i) = avs[b];
             if (field_out) *reinterpret_cast<float4*>(field_out + i) = make_float4(f4[0], f4[1], f4[2], f4[3]);
             if (pot_out) *reinterpret_cast<float4*>(pot_out + i) = pvs[b];
@@ -273,14 +275,19 @@ LNX_HD void ri_update(int lane, const float* ps, float* __restrict__ st, float* 
     acc[5 + 2 * MAXD] = gx1;
     acc[4 + 3 * MAXD] = m00;
 }
-LNX_HD void ri_update_dispatch(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
-                               float* __restrict__ pot_out, const CellParams2& cp, float* acc) {
+LNX_HD void ri_update_dispatch(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                               float* __restrict__ pot_out, const CellParams2& cp, float* acc, bool keep_state = false) {
     if (cp.state_fn == SF_V1 && cp.gf_id == GF_POLY_QUAD4)
-        ri_update<GF_POLY_QUAD4, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc);
+        ri_update<GF_POLY_QUAD4, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state);
     else if (cp.state_fn == SF_V1 && cp.gf_id == GF_GAUSSIAN)
-        ri_update<GF_GAUSSIAN, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc);
+        ri_update<GF_GAUSSIAN, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state);
     else
-        ri_update<-1, -1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc);
+        ri_update<-1, -1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state);
+}
+// the packed line of the row pair from the two rows of new cells left in shared memory by ri_update(keep_state)
+LNX_HD void rf_load_smem(int lane, const float* ps, float2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < 64; ++n2) v[n2] = make_float2(ps[lane + 32 * n2], ps[N + lane + 32 * n2]);
 }
 
 #ifdef __CUDACC__
@@ -354,8 +361,10 @@ __global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArg
     ld_store(lane, P.pot_spec + (size_t)w * SPEC + (size_t)k * N, v);
 }
 
-// grid (128, 1, worlds), 8 warps, dynamic shared memory ROWS_SMEM bytes
-__global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, Extra X) {
+// grid (128, 1, worlds), 8 warps, dynamic shared memory ROWS_SMEM bytes.  next_spec != nullptr: fused step kernel — the updated row
+// pair is still in the warp's shared memory, so it is transformed for the NEXT step right away (rows_fwd without its launch, its
+// state read and its load latency); the time loop is then lead + this kernel, after one rows_fwd launch for the first step.
+__global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, Extra X, float2* next_spec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* nat_all = reinterpret_cast<float2*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, p = blockIdx.x * ROWS_WARPS + wid, w = blockIdx.z;
@@ -392,8 +401,22 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
     const size_t traj = ((size_t)sol * P.max_iter + cr.step) * P.n_init + init;
     const size_t toff = traj * ((size_t)N * N) + (size_t)(2 * p) * N;
     float acc[NP_T];
-    ri_update_dispatch(lane, reinterpret_cast<const float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
-                       P.field_out ? P.field_out + toff : nullptr, P.potential_out ? P.potential_out + toff : nullptr, cp, acc);
+    const bool fuse = next_spec != nullptr && cr.step + 1 < P.max_iter;
+    ri_update_dispatch(lane, reinterpret_cast<float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
+                       P.field_out ? P.field_out + toff : nullptr, P.potential_out ? P.potential_out + toff : nullptr, cp, acc, fuse);
+    if (fuse) {  // (uniform over the CTA)
+        __syncwarp();
+        rf_load_smem(lane, reinterpret_cast<const float*>(sm), v);
+        fs_fwd_a(lane, v, X.tw);
+        __syncwarp();
+        fs_fwd_store(lane, v, sm);
+        __syncwarp();
+        fs_fwd_b(lane, sm, v);
+        __syncwarp();
+        rf_nat_store(lane, v, sm);
+        __syncthreads();
+        rf8_untangle_store(threadIdx.x, nat_all, next_spec + (size_t)w * SPEC + 2 * ROWS_WARPS * blockIdx.x);
+    }
 #pragma unroll
     for (int i = 0; i < NP_T; ++i) {
         float x = acc[i];

@@ -222,9 +222,11 @@ LNX_HD void inv_pot_store(int lane, const float2* v, float* ps, float* pot_plane
 // GF / SF >= 0: growth and state function fixed at compile time (reciprocal forms of the divisions, like the resident fused
 // kernel); GF < 0: selected per cell from cp (true divisions, like the generic tiled pass C).  Eight row pairs per batch: the
 // sixteen 128-bit loads of a batch are in flight together.
+// keep_state: the new cells also replace the potentials in `ps` (same row placement as fwd_load: the fused kernel transforms them
+// for the next step).
 template <int GF, int SF>
-LNX_HD void inv_update(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
-                       const CellParams& cp, float* acc) {
+LNX_HD void inv_update(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                       const CellParams& cp, float* acc, bool keep_state) {
     constexpr int B = 8;
     const int hi = lane >> 4, n0 = (lane & 15) * 4;
     float colA[4] = {0.f, 0.f, 0.f, 0.f}, colG[4] = {0.f, 0.f, 0.f, 0.f};
@@ -273,6 +275,7 @@ LNX_HD void inv_update(int lane, const float* ps, float* __restrict__ st, float*
             mx21 += rowa * x1 * x1;
             gx1 += rowg * x1;
             *reinterpret_cast<float4*>(st + i) = make_float4(n4[0], n4[1], n4[2], n4[3]);
+            if (keep_state) *reinterpret_cast<float4*>(ps + (it + 32 * hi) * SRS + n0) = make_float4(n4[0], n4[1], n4[2], n4[3]);
             if (cells_out) *reinterpret_cast<float4*>(cells_out + i) = avs[b];
             if (field_out) *reinterpret_cast<float4*>(field_out + i) = make_float4(f4[0], f4[1], f4[2], f4[3]);
         }
@@ -306,14 +309,14 @@ LNX_HD void inv_update(int lane, const float* ps, float* __restrict__ st, float*
     acc[4 + 3 * MAXD] = m00;
 }
 // the common growth functions with the v1 update get compile-time variants, everything else the per-cell selection
-LNX_HD void inv_update_dispatch(int lane, const float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
-                                const CellParams& cp, float* acc) {
+LNX_HD void inv_update_dispatch(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                                const CellParams& cp, float* acc, bool keep_state = false) {
     if (cp.state_fn == SF_V1 && cp.gf_id == GF_POLY_QUAD4)
-        inv_update<GF_POLY_QUAD4, SF_V1>(lane, ps, st, cells_out, field_out, cp, acc);
+        inv_update<GF_POLY_QUAD4, SF_V1>(lane, ps, st, cells_out, field_out, cp, acc, keep_state);
     else if (cp.state_fn == SF_V1 && cp.gf_id == GF_GAUSSIAN)
-        inv_update<GF_GAUSSIAN, SF_V1>(lane, ps, st, cells_out, field_out, cp, acc);
+        inv_update<GF_GAUSSIAN, SF_V1>(lane, ps, st, cells_out, field_out, cp, acc, keep_state);
     else
-        inv_update<-1, -1>(lane, ps, st, cells_out, field_out, cp, acc);
+        inv_update<-1, -1>(lane, ps, st, cells_out, field_out, cp, acc, keep_state);
 }
 
 #ifdef __CUDACC__
@@ -354,8 +357,10 @@ __global__ void __launch_bounds__(LEAD_TPB, MINB) lead_kernel(PassBArgs P) {
     }
 }
 
-// grid (64 planes, 1, worlds), one warp; one channel, one kernel
-__global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P) {
+// grid (64 planes, 1, worlds), one warp; one channel, one kernel.  next_spec != nullptr: fused step kernel — the updated plane is
+// still in shared memory, so it is transformed for the NEXT step right away (plane_fwd without its launch and its state read); the
+// time loop is then lead + this kernel + pass D, after one plane_fwd launch for the first step.
+__global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P, float2* next_spec) {
     __shared__ __align__(16) float sm[SMEM_FLOATS];
     const int lane = threadIdx.x, l = blockIdx.x, w = blockIdx.z;
     const int sol = w / P.n_init, init = w - sol * P.n_init;
@@ -390,8 +395,17 @@ __global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P) {
     inv_pot_store(lane, v, sm, P.potential_out ? P.potential_out + toff : nullptr);
     __syncwarp();
     float acc[NP_T];
+    const bool fuse = next_spec != nullptr && P.t + 1 < P.max_iter;
     inv_update_dispatch(lane, sm, P.state + plane * PLANE_CELLS, P.cells_out ? P.cells_out + toff : nullptr,
-                        P.field_out ? P.field_out + toff : nullptr, cp, acc);
+                        P.field_out ? P.field_out + toff : nullptr, cp, acc, fuse);
+    if (fuse) {
+        __syncwarp();
+        fwd_rows(lane, sm, v);
+        __syncwarp();
+        fwd_rows_store(lane, pl, v);
+        __syncwarp();
+        fwd_cols(lane, pl, next_spec + plane * PLANE_SPEC);
+    }
 #pragma unroll
     for (int i = 0; i < NP_T; ++i) {
         float x = acc[i];

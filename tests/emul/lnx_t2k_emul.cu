@@ -78,7 +78,7 @@ void lnx_t2k_emul_rfft2(const float* world, float2* spec) {
 
 // one Lenia step of one 2048^2 world, one channel / one kernel.  K_half: [2048][1025] complex (natural order, unscaled).
 void lnx_t2k_emul_step(float* state, const float2* K_half, int gf_id, float m, float s, float wk, int mean, int state_fn, float dt,
-                       const int* shift, float* potential, float* field, float* partials) {
+                       const int* shift, float* potential, float* field, float* partials, float2* next_T) {
     using namespace e2k;
     const std::vector<float2> tab = make_tab();
     std::vector<float2> T(SPEC), Pm(SPEC), kt(SPEC);
@@ -120,11 +120,23 @@ void lnx_t2k_emul_step(float* state, const float2* K_half, int gf_id, float m, f
         const size_t off = (size_t)(2 * p) * N;
         for (int lane = 0; lane < 32; ++lane) {
             float acc[NP_T];
-            ri_update_dispatch(lane, reinterpret_cast<const float*>(smp), state + off, nullptr, field + off, potential + off, cp, acc);
+            ri_update_dispatch(lane, reinterpret_cast<float*>(smp), state + off, nullptr, field + off, potential + off, cp, acc, next_T != nullptr);
             for (int i = 0; i < NP_T; ++i) tot[i] += acc[i];
         }
         for (int i = 0; i < NP_T; ++i) partials[p * NP_T + i] = tot[i];
+        if (next_T) {  // fused tail of rows_inv_kernel: forward rows of the next step from the cells left in shared memory
+            for (int lane = 0; lane < 32; ++lane) {
+                float2* v = regs.data() + lane * 64;
+                rf_load_smem(lane, reinterpret_cast<const float*>(smp), v);
+                fs_fwd_a(lane, v, tab.data());
+            }
+            for (int lane = 0; lane < 32; ++lane) fs_fwd_store(lane, regs.data() + lane * 64, smp);
+            for (int lane = 0; lane < 32; ++lane) fs_fwd_b(lane, smp, regs.data() + lane * 64);
+            for (int lane = 0; lane < 32; ++lane) rf_nat_store(lane, regs.data() + lane * 64, smp);
+        }
       }
+      if (next_T)
+          for (int tid = 0; tid < 32 * ROWS_WARPS; ++tid) rf8_untangle_store(tid, nat_all.data(), next_T + 2 * ROWS_WARPS * c);
     }
 }
 

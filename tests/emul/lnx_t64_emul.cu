@@ -35,7 +35,7 @@ void lnx_t64_emul_rfftn(const float* world, float2* spec) {
 // one Lenia step of one world, one channel / one kernel.  ktab: [64][64][33] complex, pre-scaled by 1 / 64^3.
 // state is updated in place; potential / field: [64^3]; partials: [64 planes][NP_T] (lane-summed)
 void lnx_t64_emul_step(float* state, const float2* ktab, int gf_id, float m, float s, float wk, int mean, int state_fn, float dt,
-                       const int* shift, float* potential, float* field, float* partials) {
+                       const int* shift, float* potential, float* field, float* partials, float2* next_spec) {
     std::vector<float2> spec((size_t)N * PLANE_SPEC), pot((size_t)N * PLANE_SPEC);
     for (int l = 0; l < N; ++l) emul_plane_fwd(state + (size_t)l * PLANE_CELLS, spec.data() + (size_t)l * PLANE_SPEC);
     for (int col = 0; col < COLS; ++col) {
@@ -70,8 +70,14 @@ void lnx_t64_emul_step(float* state, const float2* ktab, int gf_id, float m, flo
         for (int i = 0; i < NP_T; ++i) tot[i] = 0.f;
         for (int lane = 0; lane < 32; ++lane) {
             float acc[NP_T];
-            inv_update_dispatch(lane, sm.data(), state + (size_t)l * PLANE_CELLS, nullptr, field + (size_t)l * PLANE_CELLS, cp, acc);
+            inv_update_dispatch(lane, sm.data(), state + (size_t)l * PLANE_CELLS, nullptr, field + (size_t)l * PLANE_CELLS, cp, acc,
+                                next_spec != nullptr);
             for (int i = 0; i < NP_T; ++i) tot[i] += acc[i];
+        }
+        if (next_spec) {  // fused tail of plane_inv_kernel: forward planes of the next step from the cells left in shared memory
+            for (int lane = 0; lane < 32; ++lane) fwd_rows(lane, sm.data(), regs.data() + lane * 64);
+            for (int lane = 0; lane < 32; ++lane) fwd_rows_store(lane, pl, regs.data() + lane * 64);
+            for (int lane = 0; lane < 32; ++lane) fwd_cols(lane, pl, next_spec + (size_t)l * PLANE_SPEC);
         }
         for (int i = 0; i < NP_T; ++i) partials[l * NP_T + i] = tot[i];
     }

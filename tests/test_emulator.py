@@ -270,7 +270,7 @@ def emul64():
         g.build()
     lib = ctypes.CDLL(EMUL64)
     f, i, v = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
-    lib.lnx_t64_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v]
+    lib.lnx_t64_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v, v]
     return lib
 
 
@@ -308,8 +308,11 @@ def test_t64_step_matches_oracle(emul64, gf_slug, gf_id, sf_slug, sf_id, mean):
     NP = emul64.lnx_t64_emul_np()
     part = np.zeros((64, NP), np.float32)
     shift = np.array([5, 60, 17], np.int32)
+    nxt = np.zeros((64, 64, 33), np.complex64)  # fused tail: axes-(1, 2) half spectra of the NEW cells, plane by plane
     emul64.lnx_t64_emul_step(P(st), P(ktab), gf_id, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), mean, sf_id, 0.1, P(shift), P(pot), P(fld),
-                             P(part))
+                             P(part), P(nxt))
+    ref_nxt = np.fft.rfft2(st.astype(np.float64), axes=(1, 2))
+    assert np.abs(nxt - ref_nxt).max() < 2e-7 * np.abs(ref_nxt).max()
     assert np.abs(pot - op[0, 0]).max() < 1e-6
     assert np.abs(fld - of[0, 0]).max() < 2e-5
     assert np.abs(st - ns[0, 0]).max() < 2e-6
@@ -339,7 +342,7 @@ def emul2k():
         g.build()
     lib = ctypes.CDLL(EMUL2K)
     f, i, v = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
-    lib.lnx_t2k_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v]
+    lib.lnx_t2k_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v, v]
     return lib
 
 
@@ -371,7 +374,11 @@ def test_t2k_step_matches_oracle(emul2k):
     NP = emul2k.lnx_t2k_emul_np()
     part = np.zeros((S // 2, NP), np.float32)
     shift = np.array([700, 1999], np.int32)
-    emul2k.lnx_t2k_emul_step(P(st), P(Kh), 0, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), 1, 0, 0.1, P(shift), P(pot), P(fld), P(part))
+    nxt = np.zeros((1025, 2048), np.complex64)  # fused tail: transposed row spectra T[k][row] of the NEW cells
+    emul2k.lnx_t2k_emul_step(P(st), P(Kh), 0, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), 1, 0, 0.1, P(shift), P(pot), P(fld), P(part),
+                             P(nxt))
+    ref_nxt = np.fft.rfft(st.astype(np.float64), axis=1).T
+    assert np.abs(nxt - ref_nxt).max() < 3e-7 * np.abs(ref_nxt).max()
     assert np.abs(pot - op[0, 0]).max() < 1e-6
     assert np.abs(fld - of[0, 0]).max() < 5e-5
     assert np.abs(st - ns[0, 0]).max() < 5e-6
