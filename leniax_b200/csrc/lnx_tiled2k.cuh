@@ -404,6 +404,22 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
     const bool fuse = next_spec != nullptr && cr.step + 1 < P.max_iter;
     ri_update_dispatch(lane, reinterpret_cast<float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
                        P.field_out ? P.field_out + toff : nullptr, P.potential_out ? P.potential_out + toff : nullptr, cp, acc, fuse);
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) {
+        float x = acc[i];
+        if (i < 5 + 3 * MAXD) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        }
+        acc[i] = x;
+    }
+    // the eight row pairs of the CTA are summed here, so pass D (one small CTA inside the next lead launch) reads 128 slabs, not 1024;
+    // the warp's sums are parked in shared memory now: they are not live across the transform below
+    __shared__ float red[ROWS_WARPS * NP_T];
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NP_T; ++i) red[wid * NP_T + i] = acc[i];
+    }
     if (fuse) {  // (uniform over the CTA)
         __syncwarp();
         rf_load_smem(lane, reinterpret_cast<const float*>(sm), v);
@@ -416,22 +432,6 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
         rf_nat_store(lane, v, sm);
         __syncthreads();
         rf8_untangle_store(threadIdx.x, nat_all, next_spec + (size_t)w * SPEC + 2 * ROWS_WARPS * blockIdx.x);
-    }
-#pragma unroll
-    for (int i = 0; i < NP_T; ++i) {
-        float x = acc[i];
-        if (i < 5 + 3 * MAXD) {
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-        }
-        acc[i] = x;
-    }
-    // the eight row pairs of the CTA are summed here, so pass D (one small CTA inside the next lead launch) reads 128 slabs, not 1024
-    __syncthreads();  // every warp is done with its buffer
-    float* red = reinterpret_cast<float*>(nat_all);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NP_T; ++i) red[wid * NP_T + i] = acc[i];
     }
     __syncthreads();
     if (threadIdx.x < NP_T) {

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(LEAD_TPB, MINB) lead_kernel(PassBArgs P) {
 // grid (64 planes, 1, worlds), one warp; one channel, one kernel.  next_spec != nullptr: fused step kernel — the updated plane is
 // still in shared memory, so it is transformed for the NEXT step right away (plane_fwd without its launch and its state read); the
 // time loop is then lead + this kernel + pass D, after one plane_fwd launch for the first step.
-__global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P, float2* next_spec) {
+__global__ void __launch_bounds__(32, 12) plane_inv_kernel(PassCArgs P, float2* next_spec) {  // 12: three warps per scheduler (<= 168 registers)
     __shared__ __align__(16) float sm[SMEM_FLOATS];
     const int lane = threadIdx.x, l = blockIdx.x, w = blockIdx.z;
     const int sol = w / P.n_init, init = w - sol * P.n_init;
@@ -398,14 +398,6 @@ __global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P, float2* next
     const bool fuse = next_spec != nullptr && P.t + 1 < P.max_iter;
     inv_update_dispatch(lane, sm, P.state + plane * PLANE_CELLS, P.cells_out ? P.cells_out + toff : nullptr,
                         P.field_out ? P.field_out + toff : nullptr, cp, acc, fuse);
-    if (fuse) {
-        __syncwarp();
-        fwd_rows(lane, sm, v);
-        __syncwarp();
-        fwd_rows_store(lane, pl, v);
-        __syncwarp();
-        fwd_cols(lane, pl, next_spec + plane * PLANE_SPEC);
-    }
 #pragma unroll
     for (int i = 0; i < NP_T; ++i) {
         float x = acc[i];
@@ -419,6 +411,15 @@ __global__ void __launch_bounds__(32) plane_inv_kernel(PassCArgs P, float2* next
         float* p = P.partials + plane * NP_T;
 #pragma unroll
         for (int i = 0; i < NP_T; ++i) p[i] = acc[i];
+    }
+    // (the partial sums are written first: they are not live across the transform below)
+    if (fuse) {
+        __syncwarp();
+        fwd_rows(lane, sm, v);
+        __syncwarp();
+        fwd_rows_store(lane, pl, v);
+        __syncwarp();
+        fwd_cols(lane, pl, next_spec + plane * PLANE_SPEC);
     }
 }
 #endif  // __CUDACC__
