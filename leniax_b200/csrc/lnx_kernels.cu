@@ -182,10 +182,11 @@ static void sweep_retired_graphs() {
     }
     (void)cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
 }
-// the time loop of the four-step engine: lead (+ pass D of the previous step) and the fused rows kernel captured once, replayed per step
-static int run_steps_2k(const PassAArgs& a, const PassBArgs& b, const PassCArgs& c, const PassDArgs& d, const lnx::t2k::Extra& x,
-                        unsigned worlds, int steps, cudaStream_t st) {
-    using namespace lnx::t2k;
+// One time step whose launches have step-independent arguments (the step index lives in the world's carry), captured once into a
+// CUDA graph and replayed `steps` times on `st`: the passes of small / single worlds take 10-30 us each and issuing them one by one
+// cost the host 14-20 us per launch (the loop was launch-bound).
+template <class EnqueueStep>
+static int replay_steps(EnqueueStep enqueue_step, int steps, cudaStream_t st) {
     sweep_retired_graphs();
     cudaStream_t cap = nullptr;
     cudaGraph_t graph = nullptr;
@@ -194,16 +195,10 @@ static int run_steps_2k(const PassAArgs& a, const PassBArgs& b, const PassCArgs&
     cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
-        // a step = lead + the fused (inverse rows, update, forward rows of the next step) kernel
-        lead_kernel<<<dim3(1026, 1, worlds), 32, 0, cap>>>(b, x, d);
-        rows_inv_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(c, x, a.spec);
+        enqueue_step(cap);
         e = cudaStreamEndCapture(cap, &graph);
     }
     if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
-    if (e == cudaSuccess) {  // the first step's forward rows
-        rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, worlds), 32 * ROWS_WARPS, ROWS_SMEM, st>>>(a, x);
-        e = cudaGetLastError();
-    }
     for (int t = 0; e == cudaSuccess && t < steps; ++t) e = cudaGraphLaunch(exec, st);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(done, st);
@@ -212,7 +207,7 @@ static int run_steps_2k(const PassAArgs& a, const PassBArgs& b, const PassCArgs&
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
         if (done) cudaEventDestroy(done);
-        return fail(LNX_ERR_CUDA, "four-step engine: graph capture / launch failed: %s", cudaGetErrorString(e));
+        return fail(LNX_ERR_CUDA, "tiled engine: graph capture / launch failed: %s", cudaGetErrorString(e));
     }
     std::lock_guard<std::mutex> lk(g_retired_mu);
     g_retired.push_back({exec, graph, done});
@@ -707,12 +702,20 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
         c.t = t;
         d.t = t;
         if (line2k) {
-            // the three launches have step-independent arguments (the step index lives in the carry): replay one captured graph
-            d.g.n_slabs = 1024 / lnx::t2k::ROWS_WARPS;  // rows_inv writes one row of partial sums per CTA (eight row pairs)
-            const int rc = th::run_steps_2k(a, b, c, d, x2k, (unsigned)worlds, max_run_iter, st);
+            // a step = lead (+ pass D of the previous step) + the fused (inverse rows, update, forward rows of the next step) kernel
+            using namespace lnx::t2k;
+            d.g.n_slabs = 1024 / ROWS_WARPS;  // rows_inv writes one row of partial sums per CTA (eight row pairs)
+            const unsigned nw = (unsigned)worlds;
+            rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, nw), 32 * ROWS_WARPS, ROWS_SMEM, st>>>(a, x2k);  // the first step's forward rows
+            const int rc = th::replay_steps(
+                [&](cudaStream_t cap) {
+                    lnx::t2k::lead_kernel<<<dim3(1026, 1, nw), 32, 0, cap>>>(b, x2k, d);
+                    rows_inv_kernel<<<dim3(1024 / ROWS_WARPS, 1, nw), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(c, x2k, a.spec);
+                },
+                max_run_iter, st);
             if (rc != LNX_OK) return rc;
             d.t = max_run_iter - 1;  // the last step's statistics
-            pass_d_kernel<<<(unsigned)worlds, 128, 0, st>>>(d);
+            pass_d_kernel<<<nw, 128, 0, st>>>(d);
             break;
         } else if (line64) {
             // a step = lead + the fused (inverse planes, update, forward planes of the next step) kernel
@@ -720,9 +723,19 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             th::launch_lead64(b, (unsigned)worlds, st);
             lnx::t64::plane_inv_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(c, a.spec);
         } else {
-            pass_a_kernel<<<grid_a, TPB, th::smem_a(g), st>>>(a);
-            pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), st>>>(b);
-            pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), st>>>(c);
+            // generic passes: four launches with step-independent arguments (t < 0: the step index is read from the carry), replayed
+            c.t = -1;
+            d.t = -1;
+            const int rc = th::replay_steps(
+                [&](cudaStream_t cap) {
+                    pass_a_kernel<<<grid_a, TPB, th::smem_a(g), cap>>>(a);
+                    pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), cap>>>(b);
+                    pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), cap>>>(c);
+                    pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, cap>>>(d);
+                },
+                max_run_iter, st);
+            if (rc != LNX_OK) return rc;
+            break;
         }
         pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, st>>>(d);
     }

@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
     const size_t row0 = (size_t)slab * R;
     const bool plane = g.nd == 3;
     const int slab_cells = R * A2;
-    const size_t traj = ((size_t)sol * P.max_iter + P.t) * P.n_init + init;  // world-step slot of the trajectory outputs
+    const int t = P.t >= 0 ? P.t : P.carry[w].step;  // t < 0: graph-replayed loop, the step index lives in the world's carry
+    const size_t traj = ((size_t)sol * P.max_iter + t) * P.n_init + init;  // world-step slot of the trajectory outputs
     for (int i = threadIdx.x; i < P.C * slab_cells; i += blockDim.x) field[i] = 0.f;
     float acc[NP_T];
 #pragma unroll
@@ -574,7 +575,7 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w, con
     P.n_alive[w] = S.n_alive;
 }
 __global__ void __launch_bounds__(32 * PASS_D_MAX_WARPS) pass_d_kernel(PassDArgs P) {  // 4..16 warps: see pass_d_threads()
-    pass_d_body(P, blockIdx.x, P.t);
+    pass_d_body(P, blockIdx.x, P.t >= 0 ? P.t : P.carry[blockIdx.x].step);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
