@@ -65,8 +65,8 @@ typedef enum {
                                         4 warps per scheduler) instead of the default 256-thread one (A/B runs, tests) */
 #define LNX_RUN_FUSED_SMEM 0x400u    /* fused single-channel path: use the older kernel that keeps the state in shared memory
                                         (one world per SM + statistics warp) instead of the TMEM kernel; kept for A/B runs */
-#define LNX_RUN_TILED_GENERIC 0x800u /* 64^3 one-channel one-kernel worlds: use the generic tiled passes instead of the
-                                        thread-per-line kernels (A/B runs, cross-check in the tests) */
+#define LNX_RUN_TILED_GENERIC 0x800u /* 64^3 and 2048^2 one-channel one-kernel worlds: use the generic tiled passes instead of
+                                        the thread-per-line / four-step kernels (A/B runs, cross-check in the tests) */
 #define LNX_RUN_ASSUME_FINITE 0x100u /* caller checked that no growth s == 0 and no weight row sums to 0: NaN cannot
                                         appear, the fused kernel may use min/max clamps that do not propagate NaN */
 

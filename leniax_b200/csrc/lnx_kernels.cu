@@ -133,22 +133,11 @@ static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
     g->tc = tc;
     return true;
 }
-// experiment switch: resident CTAs per SM the lead kernel is compiled for (6: no spills, 166 registers; 8: 128 registers)
+// lead kernel of the 64^3 engine: 6 CTAs of 64 threads per SM (166 registers, no spills; 8 CTAs / 128 registers measured slower)
 static void launch_lead64(const PassBArgs& b, unsigned images, cudaStream_t st) {
-    static int minb = -1;
-    if (minb < 0) {
-        const char* e = getenv("LNX_T64_LEAD_MINB");
-        minb = e ? atoi(e) : 6;
-    }
     const dim3 grid(lnx::t64::COLS / lnx::t64::LEAD_TPB, b.C, images);
-    if (minb == 8)
-        lnx::t64::lead_kernel<8><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
-    else if (minb == 10)
-        lnx::t64::lead_kernel<10><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
-    else
-        lnx::t64::lead_kernel<6><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
+    lnx::t64::lead_kernel<6><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
 }
-static bool line2k_plan(const Geom& g, int C, int K);
 static bool is_sq2k(const Geom& g) { return g.nd == 2 && g.dims[0] == 2048 && g.dims[1] == 2048; }
 // one thread per slab of partial sums while there are few worlds (a single 2048^2 world has 1024 slabs); 128 threads otherwise
 static unsigned pass_d_threads(const Geom& g, long long worlds) {

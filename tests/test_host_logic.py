@@ -171,3 +171,16 @@ def test_zoom_nearest_is_scipy_order0_zoom():
             ref = scipy.ndimage.zoom(a, sc, order=0)
             got = utils.zoom_nearest(torch.from_numpy(a), sc).numpy()
             assert ref.shape == got.shape and np.array_equal(ref, got), (shape, sc)
+
+
+def test_vectorised_heuristic_counter_matches_the_recurrence():
+    """runner.run replays the reference loop's counters (statistics.py:287-306, 317-333) over all steps at once."""
+    from leniax_b200.runner import _heuristic_counter
+    rng = np.random.default_rng(0)
+    for p in (0.02, 0.5, 0.98, 1.0, 0.0):
+        keep = rng.random(700) < p
+        c, ref = 0, []
+        for k in keep:
+            c = c * int(k) + 1
+            ref.append(c)
+        assert _heuristic_counter(keep).tolist() == ref
