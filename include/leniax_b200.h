@@ -143,7 +143,10 @@ size_t lnx_workspace_bytes(const lnx_plan* plan);
  *                                                                out, each may be NULL (run_scan keeps them,
  *                                                                run_scan_mem_optimized does not)
  *   workspace     lnx_workspace_bytes() bytes of device scratch (contents undefined afterwards)
- */
+ *
+ * Asynchronous: all work is enqueued on `stream`.  Worlds that are not 128 x 128 run as a loop of passes per step; for
+ * max_run_iter >= 8 that loop is one CUDA graph (captured on a private stream, thread-local capture mode) launched
+ * max_run_iter times into `stream`; the graph is released by a later call once its last launch has completed. */
 /* Scratch needed by lnx_run_scan for n_sols x n_init worlds (the tiled engine keeps per-world spectra in the workspace). */
 size_t lnx_workspace_bytes_for(const lnx_plan* plan, int32_t n_sols, int32_t n_init);
 

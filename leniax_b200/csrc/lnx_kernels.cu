@@ -174,8 +174,14 @@ static void sweep_retired_graphs() {
 // One time step whose launches have step-independent arguments (the step index lives in the world's carry), captured once into a
 // CUDA graph and replayed `steps` times on `st`: the passes of small / single worlds take 10-30 us each and issuing them one by one
 // cost the host 14-20 us per launch (the loop was launch-bound).
+constexpr int GRAPH_MIN_STEPS = 8;  // shorter loops (lnx_update = one step) are launched directly: building a graph costs ~0.3 ms
 template <class EnqueueStep>
 static int replay_steps(EnqueueStep enqueue_step, int steps, cudaStream_t st) {
+    if (steps < GRAPH_MIN_STEPS) {
+        for (int t = 0; t < steps; ++t) enqueue_step(st);
+        const cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? LNX_OK : fail(LNX_ERR_CUDA, "tiled engine: launch failed: %s", cudaGetErrorString(e));
+    }
     sweep_retired_graphs();
     cudaStream_t cap = nullptr;
     cudaGraph_t graph = nullptr;
