@@ -184,3 +184,39 @@ def test_vectorised_heuristic_counter_matches_the_recurrence():
             c = c * int(k) + 1
             ref.append(c)
         assert _heuristic_counter(keep).tolist() == ref
+
+
+def test_header_compiles_as_plain_c_and_a_c_program_binds_the_library(tmp_path):
+    """include/leniax_b200.h is the contract a cgo / JNI / ctypes binding is written against: it must be valid C (no C++, no
+    CUDA or torch types) and a plain C program linked against the shared library must reach the entry points.  No compute call
+    is made: a plan for an unsupported world shape has to come back as LNX_ERR_UNSUPPORTED with a message."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not on PATH')
+    libdir = os.path.join(ROOT, 'leniax_b200')
+    src = tmp_path / 'bind.c'
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "leniax_b200.h"
+int main(void) {
+    lnx_desc d;
+    lnx_plan* plan = NULL;
+    memset(&d, 0, sizeof d);
+    d.nb_dims = 2; d.dims[0] = 100; d.dims[1] = 100;
+    d.nb_channels = 1; d.nb_kernels = 1; d.nb_slots = 1; d.R = 13.f; d.stats_dt = .1f;
+    d.gf_id[0] = LNX_GF_POLY_QUAD4; d.state_fn = LNX_STATE_V1;
+    int rc = lnx_plan_create(&d, &plan);
+    printf("%d %d %d %zu %s\n", lnx_version(), rc, plan == NULL, sizeof(lnx_desc), lnx_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / 'bind'
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                    '-L', libdir, '-lleniax_b200', f'-Wl,-rpath,{libdir}'], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(' ', 4)
+    assert int(out[0]) == 100 and int(out[1]) == _lib.LNX_ERR_UNSUPPORTED and int(out[2]) == 1
+    assert int(out[3]) == ctypes.sizeof(_lib.LnxDesc)  # the ctypes mirror and the C struct agree on the layout
+    assert 'power of two' in out[4]
