@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Secondary measurements: the BASELINE configs other than the headline one (A, C, D, E).  One JSON line per config.
+"""Secondary measurements: the BASELINE configs other than the headline one (A, the search form of B, C, D, E).  One JSON line per config.
 
-    python tools/bench_configs.py [--configs A,C,D,E] [--steps N]
+    python tools/bench_configs.py [--configs A,B,C,D,E] [--steps N]
 
 These are parity-test configurations first (tests/test_gpu_parity.py); this script only times them (CUDA events around
 the whole run_scan* call, inputs resident in HBM) and relates the result to the roofline SURVEY.md §8d assigns.
@@ -73,6 +73,28 @@ def config_a(steps):
             'cell_updates_per_s': cu / (ms * 1e-3), 'N': int(out[3]['N']),
             'stats_only_ms': ms2, 'stats_only_cell_updates_per_s': cu / (ms2 * 1e-3),
             'note': 'one world occupies one SM (one CTA per world): latency, not throughput, configuration'}
+
+
+def config_b(steps):
+    """BASELINE configs[1] as search_for_init_mem_optimized runs it: one solution x 4096 perlin
+    initialisations, all statistics, with and without the early-stop extension.  Most perlin soups die early, so the
+    early-stop time is what a search pays; the headline bench (bench.py) uses all-surviving worlds instead."""
+    n_init = 4096
+    K, mapping, ufn, sfn = orbium_parts()
+    _, noise = initializations.perlin(initializations.RngKey(1), n_init, [128, 128], 13, [.15, .015], device=DEV)
+    cells = noise.reshape(1, n_init, 1, 128, 128)
+    args = (cells, K[None], mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None], torch.full((1, ), 10., device=DEV))
+    ms, out = timed(lambda: runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn))
+    ms_early, out_e = timed(lambda: runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn, early_stop=True))
+    n_full, n_early = out[0]['N'], out_e[0]['N']
+    cu = n_init * 128 * 128 * steps
+    tfl = cu * 110 / (ms * 1e-3) / 1e12
+    return {'config': 'B (search form): 1 solution x 4096 perlin inits, Orbium physics 1c1k 128x128, all statistics', 'steps': steps, 'ms': ms,
+            'cell_updates_per_s': cu / (ms * 1e-3), 'early_stop_ms': ms_early,
+            'early_stop_note': 'extension (early_stop=True): a world stops once its stop criteria fired and 128 rows exist; N is unchanged',
+            'N_identical_with_early_stop': bool(torch.equal(n_full, n_early)), 'mean_N': float(n_full.mean()), 'max_N': float(n_full.max()),
+            'survivors': int((n_full >= steps).sum()),
+            'roofline': {'bound': 'fp32', 'flop_per_cell_update': 110, 'achieved_tflops': tfl, 'peak_tflops': fp32_peak(), 'frac': tfl / fp32_peak()}}
 
 
 def config_c(steps):
@@ -167,7 +189,7 @@ if __name__ == '__main__':
     ap.add_argument('--tiled-generic', action='store_true', help='configs D / E through the generic tiled passes (A/B run)')
     a = ap.parse_args()
     runner.TILED_GENERIC = a.tiled_generic
-    default_steps = {'A': 1024, 'C': 1024, 'D': 256, 'E': 64}
-    fns = {'A': config_a, 'C': config_c, 'D': config_d, 'E': config_e}
+    default_steps = {'A': 1024, 'B': 1024, 'C': 1024, 'D': 256, 'E': 64}
+    fns = {'A': config_a, 'B': config_b, 'C': config_c, 'D': config_d, 'E': config_e}
     for c in a.configs.split(','):
         print(json.dumps(fns[c](a.steps or default_steps[c])), flush=True)
