@@ -24,7 +24,11 @@ FP32_PEAK = None
 
 
 def timed(fn, reps=3):
-    fn()
+    # two untimed calls with the previous result still alive, exactly like the timed loop below: torch's caching allocator then
+    # owns both generations of output / workspace blocks and no cudaMalloc (an implicit device synchronisation, 5-40 ms measured on
+    # the 10 ms call of config D, tools/time_config_d_calls.py) falls inside the timed region
+    out = fn()
+    out = fn()  # noqa: F841
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -146,7 +150,7 @@ def config_d(steps):
         world[y:y + big.shape[0], x:x + big.shape[1]] = np.maximum(world[y:y + big.shape[0], x:x + big.shape[1]], big)
     cells = torch.from_numpy(world).to(DEV)[None, None, None]
     gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
-    ms, out = timed(lambda: runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn), reps=2)
+    ms, out = timed(lambda: runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn), reps=5)
     cu = size * size * steps
     gbs = cu * 32 / (ms * 1e-3) / 1e9
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
