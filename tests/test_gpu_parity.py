@@ -1004,3 +1004,52 @@ def test_fused_tmem_kernel_for_every_growth_function(golden_dir, gf_slug, params
     assert bad < (2e-3 if discontinuous else 1e-9), (gf_slug, bad)
     np.testing.assert_allclose(stats['mass'][0].cpu().numpy(), ost['mass'], atol=5e-3 if discontinuous else 2e-5)
     np.testing.assert_allclose(stats['growth'][0].cpu().numpy(), ost['growth'], atol=2e-2 if discontinuous else 5e-5)
+
+
+def test_full_size_full_length_search_batch(golden_dir):
+    """BASELINE configs[1] at its real size and length: 1 solution x 4096 perlin initialisations x 1024 steps, all statistics, as
+    search_for_init_mem_optimized runs it (leniax/helpers.py:140-186).  Size-independent properties:
+    (i) two runs are bit-identical; (ii) the early-stop extension leaves N and the summary block that update_individuals reads
+    (qd.py:168-186: N and the means over rows [ns-128, ns)) bit-identical; (iii) any slice of the batch run alone gives the same N
+    and the same rows; (iv) N against the oracle on the worlds that stop within the first 40 steps (fate decided before rounding
+    noise matters), each with a bounded oracle run."""
+    from leniax_b200 import initializations, qd
+    def same(a, b):  # bit-identical, NaN == NaN
+        return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+    steps, n = 1024, 4096
+    cfg, ocfg = _setup(golden_dir, 'orbium-test')
+    _, K, mapping, ufn, sfn = _engine_parts(cfg)
+    gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
+    T = torch.tensor([10.], device=DEV)
+    _, soups = initializations.perlin(initializations.RngKey(1), n, [128, 128], 13, [.15, .015], device=DEV)
+    cells0 = soups.reshape(1, n, 1, 128, 128).contiguous()
+    s1, f1 = runner.run_scan_mem_optimized(None, cells0, K[None], gf, w, T, steps, 13, ufn, sfn)
+    s2, f2 = runner.run_scan_mem_optimized(None, cells0, K[None], gf, w, T, steps, 13, ufn, sfn)
+    for k in s1:
+        assert same(s1[k], s2[k]), k
+    assert same(f1, f2)
+    fast, _ = runner.run_scan_mem_optimized(None, cells0, K[None], gf, w, T, steps, 13, ufn, sfn, early_stop=True)
+    assert same(fast['N'], s1['N'])
+    b_full, keys = qd.summarize_stats(s1)
+    b_fast, _ = qd.summarize_stats(fast)
+    assert same(b_full, b_fast)
+    N = s1['N'][0]
+    assert float(N.min()) >= 1 and float(N.max()) == steps and 0 < int((N == steps).sum()) < n  # a search: most soups die, a few survive
+    sl = slice(2049, 2049 + 517)  # odd offset and length: not aligned with any wave / CTA pairing
+    s3, f3 = runner.run_scan_mem_optimized(None, cells0[:, sl].contiguous(), K[None], gf, w, T, steps, 13, ufn, sfn)
+    assert same(s3['N'], s1['N'][:, sl])
+    for k in ('mass', 'mass_angle_speed', 'inertia'):
+        assert same(s3[k], s1[k][:, :, sl]), k
+    assert same(f3, f1[:, sl])
+    # (iv) oracle on early-decided worlds
+    Nh = N.cpu().numpy()
+    early = np.nonzero(Nh <= 40)[0][:32]
+    assert len(early) >= 8
+    worlds = cells0[0, early].cpu().numpy()
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(ocfg['kernels_params']), [128, 128], 1, 13)
+    ostats, _ = lo.run_scan(worlds, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), 64,
+                            lo.build_update_fn(om), lo.build_compute_stats_fn(ocfg['world_params'], ocfg['render_params']), False)
+    same = float((ostats['N'] == Nh[early]).mean())
+    print('early-decided worlds checked against the oracle: %d, identical N: %.1f %%' % (len(early), 100 * same))
+    assert same >= 0.99
