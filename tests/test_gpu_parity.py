@@ -1053,3 +1053,71 @@ def test_full_size_full_length_search_batch(golden_dir):
     same = float((ostats['N'] == Nh[early]).mean())
     print('early-decided worlds checked against the oracle: %d, identical N: %.1f %%' % (len(early), 100 * same))
     assert same >= 0.99
+
+
+def test_full_size_qd_generation_3c6k():
+    """BASELINE configs[2] at its real size: one CMA-ME generation's evaluations of conf/config_qd_cmame_3c6k.yaml physics (3 channels,
+    6 kernels in sorted-by-c_in order, per-solution growth parameters / weights), 16 solutions x 128 perlin initialisations x 1024
+    steps.  Properties: bit-identical reruns; the early-stop extension leaves N and the summary block update_individuals reads
+    (leniax/qd.py:168-186) bit-identical; a sub-range of the solutions run alone gives the same rows (what the multi-GPU sharding
+    relies on); N against the oracle on early-decided worlds of three solutions."""
+    from leniax_b200 import initializations, qd
+
+    def same(a, b):
+        return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+    pairs = [(0, 0), (0, 1), (1, 1), (1, 2), (2, 2), (2, 0)]
+    bs = {(0, 0): [1.], (1, 1): [.5, 1.], (2, 2): [1., .5]}
+    base = [dict(k_slug='circle_2d', k_params=[1., bs.get(p, [1.])], kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4',
+                 gf_params=[.17, .015], h=1., c_in=p[0], c_out=p[1]) for p in pairs]
+    rng = np.random.default_rng(2)
+    n_sols, n_init, steps = 16, 128, 1024
+    kps, Ks, gfs, ws, cells = [], [], [], [], []
+    key = initializations.RngKey(2)
+    for s in range(n_sols):
+        kp = copy.deepcopy(base)
+        for k in kp:  # genotype ranges of lenia.py:131-143, rounded to 8 decimals (lenia.py:66)
+            g = rng.random(3)
+            k['gf_params'] = [round(.1 + .4 * g[0], 8), round(.005 + .095 * g[1], 8)]
+            k['h'] = round(.05 + .95 * g[2], 8)
+        K, mapping = kernels.get_kernels_and_mapping(copy.deepcopy(kp), [128, 128], 3, 13, device=DEV)
+        kps.append(kp)
+        Ks.append(K)
+        gfs.append(mapping.get_gf_params(DEV))
+        ws.append(mapping.get_kernels_weight_per_channel(DEV))
+        key, noise = initializations.perlin(key, 3 * n_init, [128, 128], 13, kp[0]['gf_params'], device=DEV)
+        cells.append(noise.reshape(n_init, 3, 128, 128))
+    ufn = helpers.build_update_fn(Ks[0].shape, mapping)
+    wp, rp = {'R': 13, 'T': 10}, {'world_size': [128, 128]}
+    sfn = statistics.build_compute_stats_fn(wp, rp)
+    args = (torch.stack(cells), torch.stack(Ks), torch.stack(gfs), torch.stack(ws), torch.full((n_sols, ), 10., device=DEV))
+    s1, f1 = runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn)
+    s2, f2 = runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn)
+    assert s1['mass'].shape == (n_sols, steps, n_init) and s1['channel_mass'].shape == (n_sols, steps, n_init, 3) and s1['N'].shape == (n_sols, n_init)
+    for k in s1:
+        assert same(s1[k], s2[k]), k
+    assert same(f1, f2)
+    fast, _ = runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn, early_stop=True)
+    assert torch.equal(fast['N'], s1['N'])
+    assert same(qd.summarize_stats(s1)[0], qd.summarize_stats(fast)[0])
+    sl = slice(5, 12)
+    s3, f3 = runner.run_scan_mem_optimized(None, *[a[sl].contiguous() for a in args], steps, 13, ufn, sfn)
+    assert torch.equal(s3['N'], s1['N'][sl])
+    for k in ('mass', 'channel_mass', 'mass_speed', 'inertia'):
+        assert same(s3[k], s1[k][sl]), k
+    assert same(f3, f1[sl])
+    # oracle: worlds of solutions 0, 7, 15 whose fate is decided within 30 steps
+    N = s1['N'].cpu().numpy()
+    checked = agree = 0
+    for s in (0, 7, 15):
+        early = np.nonzero(N[s] <= 30)[0][:6]
+        if len(early) == 0:
+            continue
+        oK, om = lo.get_kernels_and_mapping(copy.deepcopy(kps[s]), [128, 128], 3, 13)
+        ostats, _ = lo.run_scan(args[0][s, early].cpu().numpy(), oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), 48,
+                                lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp), False)
+        checked += len(early)
+        agree += int((ostats['N'] == N[s, early]).sum())
+        np.testing.assert_allclose(s1['mass'][s, :8][:, early].cpu().numpy(), ostats['mass'][:8], rtol=2e-5, atol=2e-5)
+    print('3c6k early-decided worlds checked against the oracle: %d, identical N: %d' % (checked, agree))
+    assert checked >= 6 and agree >= checked - (checked // 50)
