@@ -1121,3 +1121,59 @@ def test_full_size_qd_generation_3c6k():
         np.testing.assert_allclose(s1['mass'][s, :8][:, early].cpu().numpy(), ostats['mass'][:8], rtol=2e-5, atol=2e-5)
     print('3c6k early-decided worlds checked against the oracle: %d, identical N: %d' % (checked, agree))
     assert checked >= 6 and agree >= checked - (checked // 50)
+
+
+def test_full_size_3d_batch():
+    """BASELINE configs[4] at its real size: 256 worlds 64^3, 1 channel / 1 kernel (spherical shell R = 13), uniform random initial
+    states (initializations.py:26-28), 64 steps through the thread-per-line engine.  Properties: bit-identical reruns; an odd slice of
+    the batch run alone gives the same rows; axis-permutation symmetry (the kernel is spherical: a world with its axes permuted has the
+    same mass / volume statistics up to summation order, and the same N); state, potential and N of two worlds of the batch against the
+    oracle over the first 4 steps."""
+    def same(a, b):
+        return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+    D, R, steps, n = 64, 13, 64, 256
+    kern = kernels.sphere_nd(R, [1., [1.]], 'poly_quad', [4], device=DEV)
+    kp = [dict(k_slug='raw', k_params=kern, kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1., c_in=0, c_out=0)]
+    K, mapping = kernels.get_kernels_and_mapping(kp, [D, D, D], 1, R, device=DEV)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    maxv = torch.linspace(0.15, 0.45, n)[:, None, None, None, None]
+    worlds = torch.rand((n, 1, D, D, D), generator=g) * maxv
+    worlds[n // 2:] = worlds[:n // 2].permute(0, 1, 4, 2, 3)  # second half: the first half with its axes rotated
+    cells = worlds.to(DEV)[None].contiguous()
+    ufn = helpers.build_update_fn(K.shape, mapping)
+    wp, rp = {'R': R, 'T': 10}, {'world_size': [D, D, D]}
+    sfn = statistics.build_compute_stats_fn(wp, rp)
+    gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
+    T = torch.tensor([10.], device=DEV)
+    s1, f1 = runner.run_scan_mem_optimized(None, cells, K[None], gf, w, T, steps, R, ufn, sfn)
+    s2, f2 = runner.run_scan_mem_optimized(None, cells, K[None], gf, w, T, steps, R, ufn, sfn)
+    assert s1['mass'].shape == (1, steps, n) and f1.shape == (1, n, 1, D, D, D)
+    for k in s1:
+        assert same(s1[k], s2[k]), k
+    assert same(f1, f2)
+    sl = slice(37, 37 + 51)
+    s3, f3 = runner.run_scan_mem_optimized(None, cells[:, sl].contiguous(), K[None], gf, w, T, steps, R, ufn, sfn)
+    assert torch.equal(s3['N'], s1['N'][:, sl])
+    for k in ('mass', 'growth', 'inertia'):
+        assert same(s3[k], s1[k][:, :, sl]), k
+    assert same(f3, f1[:, sl])
+    h = n // 2
+    first = 6  # before rounding differences between the two transform / summation orders are amplified (growth slope ~ 1 / s = 67)
+    for k in ('mass', 'mass_volume', 'growth'):
+        a, b = s1[k][0, :first, :h].cpu().numpy(), s1[k][0, :first, h:].cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-4, err_msg=k)
+    assert float((s1['N'][0, :h] == s1['N'][0, h:]).float().mean()) >= 0.99
+    assert len(s1['N'].unique()) >= 2  # the batch mixes worlds that stop at different steps
+    # oracle on worlds 3 and 200
+    pick = [3, 200]
+    okp = [dict(kp[0], k_params=kern.cpu().numpy())]
+    oK, om = lo.get_kernels_and_mapping(okp, [D, D, D], 1, R)
+    sub = worlds[pick].numpy()
+    c, f, p, st = runner.run_scan(None, torch.from_numpy(sub).to(DEV), K, gf[0], w[0], 10., 4, R, ufn, sfn)
+    oc, of, op, ostats = lo.run_scan(sub, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), 4,
+                                     lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp))
+    assert np.abs(p.cpu().numpy() - op).max() < 3e-6
+    assert np.abs(c.cpu().numpy() - oc).max() < 1e-5
+    np.testing.assert_allclose(s1['mass'][0, :4][:, pick].cpu().numpy(), ostats['mass'], rtol=2e-5, atol=1e-5)
+    np.testing.assert_array_equal(st['mass'].cpu().numpy(), s1['mass'][0, :4][:, pick].cpu().numpy())
