@@ -38,8 +38,6 @@ def parse_args():
     ap.add_argument('--sim-steps', type=int, default=SIM_STEPS)
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--fused-r16', action='store_true', help='A/B: time the 512-thread (R16) fused kernel instead of the default TMEM kernel')
-    ap.add_argument('--fused-smem', action='store_true', help='A/B: time the shared-memory-state fused kernel (one world per SM) instead of the default TMEM kernel')
     return ap.parse_args()
 
 
@@ -200,9 +198,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = leniax_b200.load_library()
-    runner.FUSED_VARIANT = 'r16' if args.fused_r16 else ('smem' if args.fused_smem else 'tmem')
-    variant_flag = _lib.LNX_RUN_FUSED_R16 if args.fused_r16 else (_lib.LNX_RUN_FUSED_SMEM if args.fused_smem else 0)
-    kernel_name = {'r16': 'lnx_world128_r16', 'smem': 'lnx_world128_fused', 'tmem': 'lnx_world128_tm'}[runner.FUSED_VARIANT]
+    variant_flag = 0
+    kernel_name = 'lnx_world128_tm'
 
     n_worlds, sim_steps = args.worlds, args.sim_steps
     cfg, worlds_np = make_worlds_numpy(n_worlds, seed=1 + rank)

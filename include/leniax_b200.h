@@ -61,10 +61,8 @@ typedef enum {
                                  the stop are left untouched); default off = bit-for-bit [max_run_iter] rows like
                                  runner.py:207-213 */
 #define LNX_RUN_NO_STATS 2u   /* reserved */
-#define LNX_RUN_FUSED_R16 0x200u     /* fused single-channel path: use the 512-thread kernel (one real row quarter per thread,
-                                        4 warps per scheduler) instead of the default 256-thread one (A/B runs, tests) */
-#define LNX_RUN_FUSED_SMEM 0x400u    /* fused single-channel path: use the older kernel that keeps the state in shared memory
-                                        (one world per SM + statistics warp) instead of the TMEM kernel; kept for A/B runs */
+#define LNX_RUN_GENERIC_OLD 0x400u   /* several channels / kernels: use the older lnx_world128_generic kernel (everything in an L2
+                                        scratch, statistics warp) instead of lnx_world128_gen_tm; cross-check in the tests */
 #define LNX_RUN_TILED_GENERIC 0x800u /* 64^3 and 2048^2 one-channel one-kernel worlds: use the generic tiled passes instead of
                                         the thread-per-line / four-step kernels (A/B runs, cross-check in the tests) */
 #define LNX_RUN_ASSUME_FINITE 0x100u /* caller checked that no growth s == 0 and no weight row sums to 0: NaN cannot

@@ -13,8 +13,7 @@ LNX_NB_STATS = 11
 
 LNX_RUN_EARLY_STOP = 1
 LNX_RUN_ASSUME_FINITE = 0x100
-LNX_RUN_FUSED_R16 = 0x200
-LNX_RUN_FUSED_SMEM = 0x400
+LNX_RUN_GENERIC_OLD = 0x400
 LNX_RUN_TILED_GENERIC = 0x800
 LNX_PLAN_FORCE_TILED = 1
 

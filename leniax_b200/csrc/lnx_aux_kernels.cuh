@@ -1,0 +1,107 @@
+// Small stand-alone kernels of the resident path: kernel-spectrum table builder, plain rfft2 (used to build K without cuFFT),
+// FP32 peak probe.  Included by exactly one translation unit (lnx_tu_generic.cu).
+#pragma once
+#include "lnx_resident_common.cuh"
+
+namespace lnx {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel-spectrum table builder: K_fft [n_sols][nb_slots][128][128] complex64 -> per-thread multipliers
+// ---------------------------------------------------------------------------------------------------------------------
+struct PrepArgs {
+    const float2* K_fft;
+    float4* table;
+    int K, nb_slots;
+    int slot[MAX_K];
+};
+__global__ void __launch_bounds__(NT) lnx_prepare_kernel(PrepArgs P) {
+    const int sol = blockIdx.x / P.K, k = blockIdx.x % P.K, tid = threadIdx.x;
+    const float2* Kf = P.K_fft + ((size_t)sol * P.nb_slots + P.slot[k]) * (WS * WS);
+    float4* tab = P.table + ((size_t)sol * P.K + k) * KTAB_F4;
+    const float scale = 1.0f / (2.0f * WS * WS);
+    const int col = t_col(tid);
+    for (int i = 0; i < 16; ++i) {
+        float2 v[2];
+        for (int e = 0; e < 2; ++e) {
+            const int m = p3_slot_m(tid, 2 * i + e);
+            v[e] = col == 0 ? make_float2(0.f, 0.f) : Kf[m * WS + col];
+        }
+        tab[i * NT + tid] = make_float4(v[0].x * scale, v[0].y * scale, v[1].x * scale, v[1].y * scale);
+    }
+    if (tid < KPQ_LANES) {
+        for (int s = 0; s < 32; ++s) {
+            const int m = p3_slot_m(tid, s);
+            const float2 k0 = Kf[m * WS], k64 = Kf[m * WS + 64];
+            const float h = 0.5f * scale;
+            tab[KT_F4 + s * KPQ_LANES + tid] = make_float4((k0.x + k64.x) * h, (k0.y + k64.y) * h, (k0.x - k64.x) * h, (k0.y - k64.y) * h);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// plain 2-D FFT of real 128x128 images -> full complex spectrum (used to build K = fftn(fftshift(kernel)) like
+// leniax/kernels.py:145-149 without cuFFT).  One CTA per image, phases P1..P3a of the resident pipeline.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool B0, int S>
+__device__ __forceinline__ void rfft2_col0(const float2* v, float2* out, int tid) {
+    if constexpr (S < 32) {
+        const int m = p3_slot_m(tid, S);
+        const float2 g = v[S], gp = v[col0_partner(B0, S)];
+        // v = 2 (F0 + i F64):  F0 = (G + conj G')/4, F64 = -i (G - conj G')/4
+        out[m * WS] = make_float2((g.x + gp.x) * 0.25f, (g.y - gp.y) * 0.25f);
+        out[m * WS + 64] = make_float2((g.y + gp.y) * 0.25f, (gp.x - g.x) * 0.25f);
+        rfft2_col0<B0, S + 1>(v, out, tid);
+    }
+}
+__global__ void __launch_bounds__(NT) lnx_rfft2_kernel(const float* __restrict__ images, float2* __restrict__ spectra) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float2* W = reinterpret_cast<float2*>(smem);
+    const int tid = threadIdx.x, l = t_sub(tid) & 3;
+    const float* img = images + (size_t)blockIdx.x * (WS * WS);
+    float2* out = spectra + (size_t)blockIdx.x * (WS * WS);
+    float4* twtab = reinterpret_cast<float4*>(smem + 65536);
+    Regs R;
+    init_twiddle_table(tid, twtab, c_tw128);
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) R.v[j] = make_float2(img[cell_row(tid, 0) * WS + 4 * j + l], img[cell_row(tid, 1) * WS + 4 * j + l]);
+    phase1(tid, R, W);
+    __syncthreads();
+    phase2_load(tid, R, W);
+    __syncthreads();
+    phase2_compute_store(tid, R, W, twtab);
+    __syncthreads();
+    phase3_load_fft(tid, R, W);
+    const int col = t_col(tid);
+    if (col != 0) {
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const int m = p3_slot_m(tid, s);
+            const float2 v = make_float2(R.v[s].x * 0.5f, R.v[s].y * 0.5f);
+            out[m * WS + col] = v;
+            out[((WS - m) & (WS - 1)) * WS + (WS - col)] = make_float2(v.x, -v.y);
+        }
+    } else if (tid == 0) {
+        rfft2_col0<true, 0>(R.v, out, tid);
+    } else {
+        rfft2_col0<false, 0>(R.v, out, tid);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FP32 FMA-throughput probe: the roofline denominator for the resident kernels (MEASURED_PEAKS.json has no FP32 entry)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) lnx_fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456f) out[0] = r;  // never true in practice; keeps the loop alive
+}
+
+}  // namespace lnx

@@ -15,7 +15,6 @@ struct GenericConsts {
     float dt;
 };
 constexpr int GENERIC_SMEM = 65536 + NPART_MAX * NT * 4 + CTRL_BYTES + SCRATCH_BYTES + TW_BYTES + (int)sizeof(GenericConsts);
-constexpr int PLANE_F4 = 16 * NT;  // float4 per thread-private image
 
 __global__ void __launch_bounds__(NTHREADS, 1) lnx_world128_generic(const RunArgs P) {
     extern __shared__ __align__(1024) unsigned char smem[];

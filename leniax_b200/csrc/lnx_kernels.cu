@@ -1,12 +1,8 @@
-// leniax_b200: C ABI (include/leniax_b200.h) and host-side launch code.  The device code lives in the headers:
-//   lnx_kernel_tm.cuh          lnx_world128_tm      fused 1-channel 1-kernel scan, state + multipliers in tensor memory (default)
-//   lnx_kernel_generic.cuh     lnx_world128_gen_tm  any C <= 4 / K <= 32, growth and state functions, optional trajectory
-//                              lnx_world128_generic older variant, C <= 8
-//   lnx_kernel_fused_smem.cuh  lnx_world128_fused / _r16   the earlier fused kernels (A/B runs, cross-checks)
-//   lnx_tiled.cuh              multi-pass engine for worlds that are not 128x128 (2-D / 3-D, powers of two)
-//   lnx_conv.cuh               direct-convolution potential (fft=False)
-//   lnx_world128.cuh, lnx_step.cuh, lnx_fft.cuh, lnx_stats_batch.cuh, lnx_tmem.cuh   the phases they are made of
-// There is no CPU fallback anywhere in this file.
+// leniax_b200: C ABI (include/leniax_b200.h) and host-side launch code.  The resident 128x128 kernels compile in their own
+// translation units (lnx_tu_tm.cu, lnx_tu_generic.cu; interfaces in lnx_internal.h); this one holds the device code of
+//   lnx_tiled.cuh / lnx_tiled64.cuh / lnx_tiled2k.cuh   multi-pass engines for worlds that are not 128x128
+//   lnx_conv.cuh                                        direct-convolution potential (fft=False)
+// There is no CPU fallback anywhere in this library.
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -15,11 +11,8 @@
 #include <new>
 #include <vector>
 
-#include "../../include/leniax_b200.h"
+#include "lnx_internal.h"
 #include "lnx_resident_common.cuh"
-#include "lnx_kernel_tm.cuh"
-#include "lnx_kernel_fused_smem.cuh"
-#include "lnx_kernel_generic.cuh"
 #include "lnx_tiled.cuh"
 #include "lnx_tiled64.cuh"
 #include "lnx_tiled2k.cuh"
@@ -60,18 +53,14 @@ __global__ void __launch_bounds__(128) lnx_summarize_kernel(SummArgs P) {
 using namespace lnx;
 
 static thread_local char g_err[512] = "";
-static int fail(int code, const char* fmt, ...) {
+int lnx_fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
-#define LNX_CUDA(call)                                                                              \
-    do {                                                                                            \
-        cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess) return fail(LNX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
+#define fail lnx_fail
 
 struct lnx_plan {
     lnx_desc d;
@@ -287,30 +276,11 @@ static Workspace carve(const Geom& g, int C, int K, long long worlds, unsigned c
 }
 }  // namespace th
 
-// the TMEM fused kernel is instantiated for every growth function (state function v1): one-channel one-kernel worlds of any
-// registered growth function take the fast path
-static bool tm_kernel_exists(int gf, int sf) { return sf == SF_V1 || (sf == SF_V2 && gf == GF_GAUSSIAN_TARGET); }
-static const void* tm_kernel_for(int gf, int sf, bool np) {
-    if (sf == SF_V2)  // the asymptotic update of conf/config_qd_cmame_v2.yaml and species/2d/1c-1k-v2 (gaussian_target growth)
-        return np ? reinterpret_cast<const void*>(&lnx_world128_tm<GF_GAUSSIAN_TARGET, SF_V2, true>)
-                  : reinterpret_cast<const void*>(&lnx_world128_tm<GF_GAUSSIAN_TARGET, SF_V2, false>);
-#define LNX_TM_CASE(G) \
-    case G: return np ? reinterpret_cast<const void*>(&lnx_world128_tm<G, SF_V1, true>) : reinterpret_cast<const void*>(&lnx_world128_tm<G, SF_V1, false>);
-    switch (gf) {
-        LNX_TM_CASE(GF_POLY_QUAD4)
-        LNX_TM_CASE(GF_GAUSSIAN)
-        LNX_TM_CASE(GF_GAUSSIAN_TARGET)
-        LNX_TM_CASE(GF_STEP)
-        LNX_TM_CASE(GF_STAIRCASE)
-        LNX_TM_CASE(GF_TRIANGLE)
-        default: break;
-    }
-    return np ? reinterpret_cast<const void*>(&lnx_world128_tm<GF_IDENTITY, SF_V1, true>)
-              : reinterpret_cast<const void*>(&lnx_world128_tm<GF_IDENTITY, SF_V1, false>);
-#undef LNX_TM_CASE
-}
+using lnx::host::tm_kernel_exists;
 
-// one-time per-device setup: architecture check (no fallback), twiddle constants, dynamic shared memory opt-in
+// one-time per-device setup: architecture check (no fallback), twiddle constants, dynamic shared memory opt-in.  Guarded by a
+// mutex: plans may be created from several host threads (the header promises concurrent calls are safe).
+static std::mutex g_init_mu;
 static int ensure_device_init(int* dev_out, int* sms_out) {
     static bool done[64] = {false};
     static int sms[64] = {0};
@@ -321,28 +291,17 @@ static int ensure_device_init(int* dev_out, int* sms_out) {
         return fail(LNX_ERR_NO_DEVICE, "no CUDA device: %s (leniax_b200 has no CPU fallback)", cudaGetErrorString(e));
     }
     if (dev < 0 || dev >= 64) return fail(LNX_ERR_INVALID, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_init_mu);
     if (!done[dev]) {
         cudaDeviceProp prop;
         LNX_CUDA(cudaGetDeviceProperties(&prop, dev));
         if (prop.major != 10)
             return fail(LNX_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", dev, prop.major,
                         prop.minor);
-        float2 tw[128];
-        for (int k = 0; k < 128; ++k) tw[k] = make_float2(Tw128::c[k], Tw128::s[k]);
-        LNX_CUDA(cudaMemcpyToSymbol(c_tw128, tw, sizeof(tw)));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_fused<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
-        for (int gf = 0; gf <= GF_COUNT; ++gf)  // (the extra round sets up the v2 instantiation)
-            for (int np = 0; np < 2; ++np) {
-                const void* fn = gf < GF_COUNT ? tm_kernel_for(gf, SF_V1, np != 0) : tm_kernel_for(GF_GAUSSIAN_TARGET, SF_V2, np != 0);
-                LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM));
-                LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            }
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, GENERIC_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_gen_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_r16<GF_POLY_QUAD4, SF_V1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, R16_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_world128_r16<GF_POLY_QUAD4, SF_V1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, R16_SMEM));
-        LNX_CUDA(cudaFuncSetAttribute(lnx_rfft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + TW_BYTES));
+        int rc = lnx::host::tm_setup_device();
+        if (rc != LNX_OK) return rc;
+        rc = lnx::host::generic_setup_device();
+        if (rc != LNX_OK) return rc;
         sms[dev] = prop.multiProcessorCount;
         done[dev] = true;
     }
@@ -462,15 +421,7 @@ int lnx_kernels_prepare(const lnx_plan* p, int32_t n_sols, const void* K_fft, vo
         }
         return LNX_OK;
     }
-    PrepArgs a;
-    a.K_fft = static_cast<const float2*>(K_fft);
-    a.table = static_cast<float4*>(table);
-    a.K = p->d.nb_kernels;
-    a.nb_slots = p->d.nb_slots;
-    for (int k = 0; k < a.K; ++k) a.slot[k] = p->d.slot[k];
-    lnx_prepare_kernel<<<n_sols * a.K, NT, 0, static_cast<cudaStream_t>(stream)>>>(a);
-    LNX_CUDA(cudaGetLastError());
-    return LNX_OK;
+    return lnx::host::prepare_launch(p->d, n_sols, K_fft, table, static_cast<cudaStream_t>(stream));
 }
 
 int lnx_rfft2(const lnx_plan* p, int32_t n_images, const float* images, void* spectra, void* stream) {
@@ -478,9 +429,7 @@ int lnx_rfft2(const lnx_plan* p, int32_t n_images, const float* images, void* sp
     if (!images || !spectra || n_images < 1) return fail(LNX_ERR_INVALID, "lnx_rfft2: bad argument");
     const int rc = ensure_device_init(nullptr, nullptr);
     if (rc != LNX_OK) return rc;
-    lnx_rfft2_kernel<<<n_images, NT, 65536 + TW_BYTES, static_cast<cudaStream_t>(stream)>>>(images, static_cast<float2*>(spectra));
-    LNX_CUDA(cudaGetLastError());
-    return LNX_OK;
+    return lnx::host::rfft2_launch(n_images, images, spectra, static_cast<cudaStream_t>(stream));
 }
 
 int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const float* images, void* spectra, void* stream) {
@@ -594,9 +543,11 @@ int lnx_measure_fp32_peak(int32_t iters, double* tflops, double* ms, void* strea
     LNX_CUDA(cudaEventCreate(&e0));
     LNX_CUDA(cudaEventCreate(&e1));
     const int grid = sms * 4, block = 512;
-    lnx_fp32_peak_kernel<<<grid, block, 0, st>>>(d_out, iters / 8 + 1, 0.999f, 0.001f);  // warm-up
+    int prc = lnx::host::fp32_peak_launch(grid, block, d_out, iters / 8 + 1, st);  // warm-up
+    if (prc != LNX_OK) return prc;
     LNX_CUDA(cudaEventRecord(e0, st));
-    lnx_fp32_peak_kernel<<<grid, block, 0, st>>>(d_out, iters, 0.999f, 0.001f);
+    prc = lnx::host::fp32_peak_launch(grid, block, d_out, iters, st);
+    if (prc != LNX_OK) return prc;
     LNX_CUDA(cudaEventRecord(e1, st));
     LNX_CUDA(cudaEventSynchronize(e1));
     float t = 0.f;
@@ -790,12 +741,10 @@ int lnx_update_conv(const lnx_desc* d, int32_t n_worlds, int32_t kh, int32_t kw,
     return LNX_OK;
 }
 
-static bool use_fused(const lnx_plan* p, bool trajectory, uint32_t run_flags = 0) {
+static bool use_fused(const lnx_plan* p, bool trajectory) {
     const lnx_desc& d = p->d;
     if (d.nb_channels != 1 || d.nb_kernels != 1 || trajectory) return false;
-    // the two earlier fused kernels (A/B flags) only exist for poly_quad4 / v1; the default TMEM kernel for every growth function
-    // with v1 and for gaussian_target with v2
-    if (run_flags & (LNX_RUN_FUSED_R16 | LNX_RUN_FUSED_SMEM)) return d.gf_id[0] == GF_POLY_QUAD4 && d.state_fn == SF_V1;
+    // the TMEM kernel exists for every growth function with v1 and for gaussian_target with v2
     return tm_kernel_exists(d.gf_id[0], d.state_fn);
 }
 
@@ -818,7 +767,7 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
         return run_scan_tiled(p, n_sols, n_init, max_run_iter, cells0, table, gf_params, weights, dt, stats, channel_mass, n_alive, final_cells,
                               cells_out, field_out, potential_out, workspace, workspace_bytes, stream, run_flags);
     const bool trajectory = cells_out || field_out || potential_out;
-    const bool fused = use_fused(p, trajectory, run_flags);
+    const bool fused = use_fused(p, trajectory);
     if (!workspace || workspace_bytes < (fused ? (size_t)256 : lnx_workspace_bytes(p)))
         return fail(LNX_ERR_INVALID, "lnx_run_scan: workspace too small (%zu < %zu)", workspace_bytes, lnx_workspace_bytes(p));
 
@@ -859,31 +808,11 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
     if (fused) {
         // NaN can only be born from s == 0 or a zero weight (0 * inf); the fast variant assumes neither.  The host
         // cannot see device-side parameters without a sync, so the NaN-propagating variant is the default and the
-        // caller opts into the fast one with flag bit 8 (set by the Python layer after checking the parameters).
-        const bool t32 = (run_flags & LNX_RUN_FUSED_R16) == 0;
-        if (!(run_flags & (LNX_RUN_FUSED_R16 | LNX_RUN_FUSED_SMEM))) {  // default: TMEM-resident state, two worlds per SM
-            const int grid2 = (int)(n_worlds < 2 * p->sm_count ? n_worlds : 2 * p->sm_count);
-            void* kargs[] = {&a};
-            LNX_CUDA(cudaLaunchKernel(tm_kernel_for(p->d.gf_id[0], p->d.state_fn, !(run_flags & LNX_RUN_ASSUME_FINITE)), dim3(grid2), dim3(NT), kargs,
-                                      TM_SMEM, st));
-        } else if (t32) {
-            if (run_flags & LNX_RUN_ASSUME_FINITE)
-                lnx_world128_fused<GF_POLY_QUAD4, SF_V1, false><<<grid, NTHREADS, FUSED_SMEM, st>>>(a);
-            else
-                lnx_world128_fused<GF_POLY_QUAD4, SF_V1, true><<<grid, NTHREADS, FUSED_SMEM, st>>>(a);
-        } else {
-            if (run_flags & LNX_RUN_ASSUME_FINITE)
-                lnx_world128_r16<GF_POLY_QUAD4, SF_V1, false><<<grid, R16_THREADS, R16_SMEM, st>>>(a);
-            else
-                lnx_world128_r16<GF_POLY_QUAD4, SF_V1, true><<<grid, R16_THREADS, R16_SMEM, st>>>(a);
-        }
-    } else if (a.C <= G2_MAX_C && !(run_flags & LNX_RUN_FUSED_SMEM)) {
-        lnx_world128_gen_tm<<<grid, NT, G2_SMEM, st>>>(a);
-    } else {
-        lnx_world128_generic<<<grid, NTHREADS, GENERIC_SMEM, st>>>(a);
+        // caller opts into the fast one with LNX_RUN_ASSUME_FINITE (set by the Python layer after checking the parameters).
+        const int grid2 = (int)(n_worlds < 2 * p->sm_count ? n_worlds : 2 * p->sm_count);  // TMEM-resident state, two worlds per SM
+        return lnx::host::tm_launch(p->d.gf_id[0], p->d.state_fn, !(run_flags & LNX_RUN_ASSUME_FINITE), grid2, a, st);
     }
-    LNX_CUDA(cudaGetLastError());
-    return LNX_OK;
+    return lnx::host::generic_launch(lnx::host::gen_tm_supports(a.C) && !(run_flags & LNX_RUN_GENERIC_OLD), grid, a, st);
 }
 
 int lnx_summarize_stats(const float* const* planes, const float* n_alive, int32_t n_sols, int32_t T, int32_t n_init, int32_t window,

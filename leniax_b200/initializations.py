@@ -87,21 +87,29 @@ def random_uniform(rng_key: RngKey, nb_init: int, world_size: List[int], R: floa
     return rng_key, make_array_compressible(cells)
 
 
+def perlin_from_angles(angles: torch.Tensor, world_size: List[int], R: float, gf_params: List) -> torch.Tensor:
+    """initializations.py:56-75 after the random draw: ``angles [nb_init, res0, res1]`` -> states ``[nb_init, 1, H, W]``."""
+    nb_init = angles.shape[0]
+    kernel_radius = math.ceil(R)
+    res = [world_size[0] // (kernel_radius * 3), world_size[1] // (kernel_radius * 2)]
+    lo = gf_params[0]
+    hi = min(1, 3 * lo)
+    scaling = torch.tensor([lo + i / nb_init * (hi - lo) for i in range(nb_init)], dtype=torch.float32, device=angles.device)[:, None, None]
+    cells = generate_perlin_noise_2d(angles, tuple(world_size), tuple(res), nb_init)
+    cells = cells - cells.amin(dim=(1, 2), keepdim=True)
+    cells = cells / cells.amax(dim=(1, 2), keepdim=True)
+    cells = cells * scaling
+    return make_array_compressible(cells[:, None])
+
+
 def perlin(rng_key: RngKey, nb_init: int, world_size: List[int], R: float, gf_params: List, device=None):
     """initializations.py:35-77."""
     device = _device(device)
     kernel_radius = math.ceil(R)
     res = [world_size[0] // (kernel_radius * 3), world_size[1] // (kernel_radius * 2)]
-    lo = gf_params[0]
-    hi = min(1, 3 * lo)
-    scaling = torch.tensor([lo + i / nb_init * (hi - lo) for i in range(nb_init)], dtype=torch.float32, device=device)[:, None, None]
     rng_key, subkey = rng_key.split()
     angles = 2 * math.pi * torch.rand([nb_init] + res, generator=subkey.generator(device), device=device)
-    cells = generate_perlin_noise_2d(angles, tuple(world_size), tuple(res), nb_init)
-    cells = cells - cells.amin(dim=(1, 2), keepdim=True)
-    cells = cells / cells.amax(dim=(1, 2), keepdim=True)
-    cells = cells * scaling
-    return rng_key, make_array_compressible(cells[:, None])
+    return rng_key, perlin_from_angles(angles, world_size, R, gf_params)
 
 
 def cropped_perlin(rng_key: RngKey, nb_init: int, world_size: List[int], R: float, gf_params: List, device=None):

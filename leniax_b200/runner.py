@@ -35,11 +35,7 @@ def _finite_params(gf_params: torch.Tensor, weights: torch.Tensor, average: bool
     return ok and bool(torch.isfinite(weights).all().item())
 
 
-# fused single-channel kernel variant: 'tmem' (default: state + kernel multipliers in tensor memory, two worlds per SM),
-# 'smem' (state in shared memory, one world per SM + statistics warp), 'r16' (512 threads, one real row quarter each).
-# The last two are kept for A/B runs and as cross-checks in the tests.
-FUSED_VARIANT = 'tmem'
-FUSED_R16 = False  # older spelling of FUSED_VARIANT = 'r16'
+GENERIC_OLD = False  # tests: several channels / kernels through the older lnx_world128_generic kernel (cross-check)
 TILED_GENERIC = False  # tests / A-B runs: 64^3 one-channel one-kernel worlds through the generic tiled passes instead of lnx_tiled64.cuh
 FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the tiled multi-pass engine as a cross-check
 
@@ -77,12 +73,8 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     flags = 0
     if early_stop:
         flags |= _lib.LNX_RUN_EARLY_STOP
-    if FUSED_R16 or FUSED_VARIANT == 'r16':
-        flags |= _lib.LNX_RUN_FUSED_R16
-    elif FUSED_VARIANT == 'smem':
-        flags |= _lib.LNX_RUN_FUSED_SMEM
-    elif FUSED_VARIANT != 'tmem':
-        raise ValueError(f'unknown FUSED_VARIANT {FUSED_VARIANT!r}')
+    if GENERIC_OLD:
+        flags |= _lib.LNX_RUN_GENERIC_OLD
     if TILED_GENERIC:
         flags |= _lib.LNX_RUN_TILED_GENERIC
     if _finite_params(gf_params, weights, update_fn.get_field_fn.average):

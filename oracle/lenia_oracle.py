@@ -12,7 +12,9 @@ golden last-frame fixtures of the reference's own test-suite
 ``tests/test_oracle_golden.py``) and the known-answer tests of
 ``tests/test_core.py:55-103,159-185``, ``tests/test_statistics.py:14-50`` and
 ``tests/test_kernels.py:12-20``.  **Unpinned** (no reference fixture exists):
-the numeric values of the 12 statistics and of ``stats['N']`` on real runs.
+the numeric values of the 12 statistics and of ``stats['N']`` on real runs, and
+the perlin / uniform initial states (``perlin.py``, ``initializations.py``:
+restated from the angles / uniform draw onwards, no reference test fixes one).
 
 Third-party arithmetic that is not in /root/reference: the reference lowers
 ``jnp.fft.fftn`` / reductions through JAX/XLA (pinned env jax 0.2.26 / jaxlib
@@ -648,6 +650,85 @@ def behaviours_of(stats: Dict[str, np.ndarray], fitness_coef: float = 1.):
         ns = max(int(fitness[i]), 128)
         behaviours.append({k: stats[k][i, ns - 128:ns, best[i]].mean(axis=0) for k in stats if k != 'N'})
     return fitness, best, behaviours
+
+
+# ---------------------------------------------------------------------------
+# initial states            leniax/perlin.py, leniax/initializations.py, leniax/loader.py:16-30
+# ---------------------------------------------------------------------------
+def make_array_compressible(cells: np.ndarray) -> np.ndarray:  # loader.py:16-30
+    max_val = NB_CHARS**2 - 1
+    cells_int32 = np.round(np.asarray(cells, np.float32) * np.float32(max_val)).astype(np.int32)  # jnp.round = half to even, like np.round
+    return (cells_int32 / max_val).astype(np.float32)
+
+
+def perlin_interpolant(t):  # perlin.py:12-13
+    return t * t * t * (t * (t * 6 - 15) + 10)
+
+
+def generate_perlin_noise_2d(angles: np.ndarray, shape: Sequence[int], res: Sequence[int], nb_noise: int = 1) -> np.ndarray:
+    """perlin.py:16-71, statement by statement (including the ``diff``-based corner slicing of lines 51-55: the repeated
+    gradient image is ``d`` cells larger than ``shape`` on each axis and the four corner gradients are the four ways of
+    cropping it).  ``angles [nb_noise, res0, res1]`` float32 -> ``[nb_noise, *shape]`` float32."""
+    angles = np.asarray(angles, np.float32)
+    gradients = np.stack([np.cos(angles), np.sin(angles)], axis=-1).astype(np.float32)  # :46
+    gradients = np.pad(gradients, [(0, 0), (0, 1), (0, 1), (0, 0)], mode='wrap')  # :47
+    d = (shape[0] // res[0], shape[1] // res[1])  # :48
+    gradients = gradients.repeat(d[0], 1).repeat(d[1], 2)  # :49
+    diff = [gradients.shape[1] - shape[0], gradients.shape[2] - shape[1]]  # :51
+    g00 = gradients[:, :-diff[0], :-diff[1]]  # :52-55
+    g10 = gradients[:, diff[0]:, :-diff[1]]
+    g01 = gradients[:, :-diff[0], diff[1]:]
+    g11 = gradients[:, diff[0]:, diff[1]:]
+    delta = (res[0] / shape[0], res[1] / shape[1])  # :58
+    # jnp.mgrid[0:res0:delta0, 0:res1:delta1] (:59) = start + arange(n) * step with n = ceil(res / delta), computed in
+    # float32 under jax's default x64-off mode
+    n0, n1 = int(math.ceil(res[0] / delta[0])), int(math.ceil(res[1] / delta[1]))
+    g0 = (np.arange(n0, dtype=np.float32) * np.float32(delta[0])) % np.float32(1)
+    g1 = (np.arange(n1, dtype=np.float32) * np.float32(delta[1])) % np.float32(1)
+    grid = np.stack(np.meshgrid(g0, g1, indexing='ij'), axis=-1)[np.newaxis].repeat(nb_noise, 0)  # :59-61
+    one = np.float32(1)
+    n00 = np.sum(np.stack([grid[..., 0], grid[..., 1]], axis=-1) * g00, 3, dtype=np.float32)  # :62-65
+    n10 = np.sum(np.stack([grid[..., 0] - one, grid[..., 1]], axis=-1) * g10, 3, dtype=np.float32)
+    n01 = np.sum(np.stack([grid[..., 0], grid[..., 1] - one], axis=-1) * g01, 3, dtype=np.float32)
+    n11 = np.sum(np.stack([grid[..., 0] - one, grid[..., 1] - one], axis=-1) * g11, 3, dtype=np.float32)
+    t = perlin_interpolant(grid)  # :68
+    n0_ = n00 * (one - t[..., 0]) + t[..., 0] * n10  # :69-70
+    n1_ = n01 * (one - t[..., 0]) + t[..., 0] * n11
+    return (np.float32(np.sqrt(2)) * ((one - t[..., 1]) * n0_ + t[..., 1] * n1_)).astype(np.float32)  # :72
+
+
+def perlin_from_angles(angles: np.ndarray, world_size: Sequence[int], R: float, gf_params: Sequence[float]) -> np.ndarray:
+    """initializations.py:35-77 after the random draw (:63-65): ``angles [nb_init, res0, res1]`` in [0, 2 pi) ->
+    ``[nb_init, 1, H, W]`` initial states.  (``jax.random`` itself is third-party and unpinned: SURVEY §8c.)"""
+    nb_init = angles.shape[0]
+    kernel_radius = math.ceil(R)
+    res = [world_size[0] // (kernel_radius * 3), world_size[1] // (kernel_radius * 2)]  # :56
+    assert list(angles.shape[1:]) == res, (angles.shape, res)
+    lo = gf_params[0]
+    hi = min(1, 3 * lo)  # :57-58
+    scaling = np.array([lo + i / nb_init * (hi - lo) for i in range(nb_init)], dtype=np.float32)[:, None, None]  # :59-61
+    cells = generate_perlin_noise_2d(angles, tuple(world_size), tuple(res), nb_init)
+    cells = cells - cells.min(axis=(1, 2), keepdims=True)  # :70-72
+    cells = cells / cells.max(axis=(1, 2), keepdims=True)
+    cells = cells * scaling
+    return make_array_compressible(cells[:, np.newaxis])  # :73-75
+
+
+def cropped_perlin_from_angles(angles, world_size, R, gf_params):  # initializations.py:80-116
+    init_cells = perlin_from_angles(angles, world_size, R, gf_params)
+    size = math.ceil(R) * 2
+    pad_left = (128 - size) // 2
+    pad_right = pad_left + 1 if pad_left * 2 + size != 128 else pad_left
+    init_cells = np.pad(init_cells[:, :, 24:24 + size, 24:24 + size], ((0, 0), (0, 0), (pad_left, pad_right), (pad_left, pad_right)))
+    return make_array_compressible(init_cells)
+
+
+def random_uniform_from_unit(u: np.ndarray) -> np.ndarray:
+    """initializations.py:10-32 after the random draw: ``u [nb_init, *world]`` uniform in [0, 1) -> states.
+    ``jax.random.uniform(minval=0, maxval=m)`` is ``u * (m - 0) + 0`` clipped below at 0."""
+    nb_init = u.shape[0]
+    maxvals = np.linspace(0.4, 1., nb_init, dtype=np.float32).reshape((nb_init, ) + (1, ) * (u.ndim - 1))
+    return make_array_compressible(np.asarray(u, np.float32) * maxvals)
 
 
 # ---------------------------------------------------------------------------

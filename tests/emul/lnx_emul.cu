@@ -259,145 +259,3 @@ int lnx_emul_run_fused(const float* cells0, const float* Kt, const float* Kpq, i
 }
 
 }  // extern "C"
-
-// ---- R16 variant (lnx_w128r.cuh) ----
-#include "../../leniax_b200/csrc/lnx_step_r16.cuh"
-extern "C" {
-void lnx_emul_rfft32_fwd(const float* x, float* y /* 16 complex */) { lnx::r16::rfft32_fwd(x, reinterpret_cast<float2*>(y)); }
-void lnx_emul_rfft32_inv(const float* y /* 16 complex */, float* x) { lnx::r16::rfft32_inv(reinterpret_cast<const float2*>(y), x); }
-}
-
-namespace R16 = lnx::r16;
-namespace {
-void r16_phases(std::vector<float>& xs /* [512][32] state in / potential out */, std::vector<float2>& W, const float4* twtab, const float* Kt,
-                const float* Kpq) {
-    std::vector<R16::P2State> s2(R16::NT);
-    std::vector<R16::P4State> s4(R16::NT);
-    std::vector<R16::Regs> regs(R16::NT);
-    std::vector<float2> scratch(256);
-    for (int u = 0; u < R16::NT; ++u) R16::phase1(u, &xs[u * 32], W.data());
-    for (int u = 0; u < R16::NT; ++u) R16::phase2_compute(u, s2[u], W.data(), twtab);
-    for (int u = 0; u < R16::NT; ++u) R16::phase2_store(u, s2[u], W.data());
-    for (int u = 0; u < R16::NT; ++u) R16::phase3_load_fft(u, regs[u], W.data());
-    for (int u = 0; u < 32; ++u) R16::phase3_col0_stash(u, regs[u], scratch.data());
-    for (int u = 0; u < 32; ++u) R16::phase3_col0_compute(u, scratch.data(), reinterpret_cast<const float4*>(Kpq));
-    for (int u = 0; u < R16::NT; ++u) {
-        R16::phase3_multiply(u, regs[u], reinterpret_cast<const float4*>(Kt));
-        if (u < 32) R16::phase3_col0_fetch(u, regs[u], scratch.data());
-        R16::phase3_ifft_store(u, regs[u], W.data());
-    }
-    for (int u = 0; u < R16::NT; ++u) R16::phase4_load_ifft(u, s4[u], W.data(), twtab);
-    for (int u = 0; u < R16::NT; ++u) R16::phase4_finish_store(u, s4[u], s4[u ^ 1].cA + 4, s4[u ^ 1].cB + 4, W.data(), twtab);
-    for (int u = 0; u < R16::NT; ++u) R16::phase5(u, &xs[u * 32], W.data());
-}
-}  // namespace
-
-extern "C" {
-int lnx_emul_r16_e1_addr(int i, int k1, int l) { return R16::e1_addr(i, k1, l); }
-int lnx_emul_r16_e2_addr(int col, int m2, int swz) { return R16::e2_addr(col, m2, swz); }
-int lnx_emul_r16_e2_swz(int col) { return R16::e2_swz(col); }
-int lnx_emul_r16_k1_of(int a, int h) { return R16::k1_of(a, h); }
-
-void lnx_emul_r16_build_kt(const float* Kfull, float* Kt /* float4[8][512] */, float* Kpq /* float4[16][8] */) {
-    const float scale = 1.0f / (2.0f * 128.0f * 128.0f);
-    for (int u = 0; u < R16::NT; ++u)
-        for (int pos = 0; pos < 16; ++pos) {
-            const int m = R16::p3_slot_m(u, pos), col = R16::t_col(u);
-            float* dst = Kt + ((pos >> 1) * R16::NT + u) * 4 + (pos & 1) * 2;
-            if (col == 0) {
-                dst[0] = dst[1] = 0.f;
-                const float* k0 = Kfull + (m * 128 + 0) * 2;
-                const float* k64 = Kfull + (m * 128 + 64) * 2;
-                float* pq = Kpq + (pos * 8 + u) * 4;
-                pq[0] = (k0[0] + k64[0]) * 0.5f * scale;
-                pq[1] = (k0[1] + k64[1]) * 0.5f * scale;
-                pq[2] = (k0[0] - k64[0]) * 0.5f * scale;
-                pq[3] = (k0[1] - k64[1]) * 0.5f * scale;
-            } else {
-                dst[0] = Kfull[(m * 128 + col) * 2] * scale;
-                dst[1] = Kfull[(m * 128 + col) * 2 + 1] * scale;
-            }
-        }
-}
-
-void lnx_emul_r16_potential(const float* state, const float* Kt, const float* Kpq, float* potential) {
-    std::vector<float> xs(R16::NT * 32);
-    std::vector<float2> W(16 * R16::REGION);
-    std::vector<float4> twtab(R16::TW_TABLE_F4);
-    float2 tw[128];
-    make_tw(tw);
-    for (int u = 0; u < R16::NT; ++u) R16::init_twiddle_table(u, twtab.data(), tw);
-    for (int u = 0; u < R16::NT; ++u)
-        for (int j = 0; j < 32; ++j) xs[u * 32 + j] = state[R16::cell_row(u) * 128 + 4 * j + R16::t_l(u)];
-    r16_phases(xs, W, twtab.data(), Kt, Kpq);
-    for (int u = 0; u < R16::NT; ++u)
-        for (int j = 0; j < 32; ++j) potential[R16::cell_row(u) * 128 + 4 * j + R16::t_l(u)] = xs[u * 32 + j];
-}
-}
-
-// full fused run with the R16 variant (poly_quad4 / v1), same outputs as lnx_emul_run_fused
-namespace {
-template <bool NP>
-void r16_run(const float* cells0, const float* Kt, const float* Kpq, float m, float s, float w, int mean, float T, float R, float stats_dt,
-             int n_steps, float* stats, float* cm, float* N_out, float* final_cells) {
-    using namespace lnx;
-    std::vector<float> xs(R16::NT * 32);
-    std::vector<float2> W(16 * R16::REGION);
-    std::vector<float4> twtab(R16::TW_TABLE_F4), A4(8 * R16::NT);
-    std::vector<float> part((PT_FIXED + 1) * R16::NT);
-    float2 tw[128];
-    make_tw(tw);
-    for (int u = 0; u < R16::NT; ++u) R16::init_twiddle_table(u, twtab.data(), tw);
-    for (int u = 0; u < R16::NT; ++u)
-        for (int i4 = 0; i4 < 8; ++i4) {
-            float e[4];
-            for (int k = 0; k < 4; ++k) e[k] = cells0[R16::cell_row(u) * 128 + 4 * (4 * i4 + k) + R16::t_l(u)];
-            A4[i4 * R16::NT + u] = make_float4(e[0], e[1], e[2], e[3]);
-        }
-    const FusedConsts K = fused_consts(GF_POLY_QUAD4, m, s, w, mean, 1.0f / T);
-    StatsCarry S;
-    S.reset();
-    for (int step = 0; step < n_steps; ++step) {
-        const int sh0 = S.shift[0], sh1 = S.shift[1];
-        for (int u = 0; u < R16::NT; ++u)
-            for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 c = A4[i4 * R16::NT + u];
-                xs[u * 32 + 4 * i4 + 0] = c.x;
-                xs[u * 32 + 4 * i4 + 1] = c.y;
-                xs[u * 32 + 4 * i4 + 2] = c.z;
-                xs[u * 32 + 4 * i4 + 3] = c.w;
-            }
-        r16_phases(xs, W, twtab.data(), Kt, Kpq);
-        for (int u = 0; u < R16::NT; ++u) R16::cells_fused<GF_POLY_QUAD4, SF_V1, NP>(u, &xs[u * 32], A4.data(), K, sh0, sh1, part.data());
-        float totals[PT_FIXED + 1];
-        for (int k = 0; k <= PT_FIXED; ++k) {  // statistics warp order: 16 values per lane, then the xor-shuffle tree
-            float lane[32];
-            for (int ln = 0; ln < 32; ++ln) {
-                float a = 0.f;
-                for (int i = 0; i < 16; ++i) a += part[k * R16::NT + ln + 32 * i];
-                lane[ln] = a;
-            }
-            for (int off = 16; off >= 1; off >>= 1)
-                for (int ln = 0; ln < 32; ++ln)
-                    if ((ln & off) == 0) lane[ln] = lane[ln] + lane[ln ^ off];
-            totals[k] = lane[0];
-        }
-        float row[ST_COUNT + MAX_C];
-        stats_finalize(totals, 1, step, 1.0f / (R * R), 1.0f / R, 1.0f / stats_dt, S, row);
-        for (int k = 0; k < ST_COUNT; ++k) stats[k * n_steps + step] = row[k];
-        cm[step] = row[ST_COUNT];
-    }
-    *N_out = S.n_alive;
-    for (int u = 0; u < R16::NT; ++u)
-        for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 c = A4[i4 * R16::NT + u];
-            const float e[4] = {c.x, c.y, c.z, c.w};
-            for (int k = 0; k < 4; ++k) final_cells[R16::cell_row(u) * 128 + 4 * (4 * i4 + k) + R16::t_l(u)] = e[k];
-        }
-}
-}  // namespace
-extern "C" int lnx_emul_r16_run_fused(const float* cells0, const float* Kt, const float* Kpq, float m, float s, float w, int mean, float T,
-                                      float R, float stats_dt, int n_steps, float* stats, float* cm, float* N_out, float* final_cells) {
-    r16_run<true>(cells0, Kt, Kpq, m, s, w, mean, T, R, stats_dt, n_steps, stats, cm, N_out, final_cells);
-    return 0;
-}

@@ -183,80 +183,6 @@ def test_exchange_layouts_are_bijections(emul):
     cols = sorted(emul.lnx_emul_col_of(a, c) for a in range(16) for c in range(4))
     assert cols == list(range(64))
 
-
-# ---------------------------------------------------------------------------------------------------------------------
-# R16 variant (leniax_b200/csrc/lnx_w128r.cuh): 512 threads, one real row quarter per thread
-# ---------------------------------------------------------------------------------------------------------------------
-def _r16_tables(emul, Kfull):
-    Kt, Kpq = np.zeros((8, 512, 4), np.float32), np.zeros((16, 8, 4), np.float32)
-    emul.lnx_emul_r16_build_kt(P(np.ascontiguousarray(Kfull.astype(np.complex64))), P(Kt), P(Kpq))
-    return Kt, Kpq
-
-
-def test_r16_real_fft32(emul):
-    rng = np.random.default_rng(2)
-    x = rng.random(32).astype(np.float32)
-    y = np.zeros(32, np.float32)
-    emul.lnx_emul_rfft32_fwd(P(x), P(y))
-    Y = np.fft.rfft(x.astype(np.float64))
-    assert np.abs((y[2::2] + 1j * y[3::2]) - 2 * Y[1:16]).max() < 5e-6
-    assert abs(y[0] - 2 * Y[0].real) < 5e-6 and abs(y[1] - 2 * Y[16].real) < 5e-6
-    yin = np.zeros(32, np.float32)
-    yin[0], yin[1], yin[2::2], yin[3::2] = Y[0].real, Y[16].real, Y[1:16].real, Y[1:16].imag
-    xo = np.zeros(32, np.float32)
-    emul.lnx_emul_rfft32_inv(P(yin), P(xo))
-    assert np.abs(xo - 32 * x).max() < 2e-5
-
-
-def test_r16_potential_and_full_run(emul, golden_dir):
-    cfg = lo.load_yaml_config(os.path.join(golden_dir, 'orbium-test.yaml'))
-    cells, K, _ = lo.init(cfg)
-    rng = np.random.default_rng(0)
-    state = rng.random((128, 128), dtype=np.float32)
-    pot = np.zeros((128, 128), np.float32)
-    Kt, Kpq = _r16_tables(emul, K[0, 0, 0])
-    emul.lnx_emul_r16_potential(P(state), P(Kt), P(Kpq), P(pot))
-    assert np.abs(pot - lo.get_potential_fft(state[None, None], K)[0, 0]).max() < 1e-6
-    kern = rng.random((128, 128)).astype(np.float32)
-    kern /= kern.sum()
-    ref = np.real(np.fft.ifft2(np.fft.fft2(state.astype(np.float64)) * np.fft.fft2(kern.astype(np.float64))))
-    Kt2, Kpq2 = _r16_tables(emul, np.fft.fft2(kern))
-    emul.lnx_emul_r16_potential(P(state), P(Kt2), P(Kpq2), P(pot))
-    assert np.abs(pot - ref).max() < 5e-7
-    # 128 steps with statistics + the reference's golden last frame (127 updates)
-    n, f = 128, ctypes.c_float
-    stats, cm, N, fin = np.zeros((11, n), np.float32), np.zeros(n, np.float32), np.zeros(1, np.float32), np.zeros((128, 128), np.float32)
-    c0 = np.ascontiguousarray(cells[0, 0])
-    emul.lnx_emul_r16_run_fused(P(c0), P(Kt), P(Kpq), f(.15), f(.015), f(1.), 1, f(10.), f(13.), f(.1), n, P(stats), P(cm), P(N), P(fin))
-    ostats = lo.init_and_run(cfg, with_jit=True)[3]
-    tol = dict(zip(KEYS, [2e-6, 3e-7, 2e-6, 5e-6, 3e-7, 1e-5, 5e-5, 0.05, 2e-5, 5e-6, 0.05]))
-    for i, k in enumerate(KEYS):
-        assert np.abs(stats[i] - ostats[k][:, 0]).max() <= tol[k], k
-    assert float(N[0]) == 128.
-    stats2, cm2 = np.zeros((11, 127), np.float32), np.zeros(127, np.float32)
-    emul.lnx_emul_r16_run_fused(P(c0), P(Kt), P(Kpq), f(.15), f(.015), f(1.), 1, f(10.), f(13.), f(.1), 127, P(stats2), P(cm2), P(N), P(fin))
-    gold = np.load(os.path.join(golden_dir, 'orbium-test_last_frame.npy'))
-    np.testing.assert_array_almost_equal(gold[0], fin, decimal=4)
-
-
-def test_r16_layouts_conflict_free_and_bijective(emul):
-    e1, e2, swz, k1_of = emul.lnx_emul_r16_e1_addr, emul.lnx_emul_r16_e2_addr, emul.lnx_emul_r16_e2_swz, emul.lnx_emul_r16_k1_of
-    lanes = range(32)
-    for k1 in range(16):  # P1'/P5': 64-bit, lanes (i, l)
-        assert _conflict_degree([e1((ln >> 2) & 7, k1, ln & 3) * 8 for ln in lanes], 8) == 1
-    for i, p in itertools.product(range(8), range(2)):  # P2' loads: 128-bit, lanes (a, h) (pairs broadcast)
-        assert _conflict_degree([e1(i, (ln >> 1) & 15, 2 * p) * 8 for ln in lanes], 16) == 1
-    for j, p in itertools.product(range(4), range(2)):  # P4' stores: row 4h + j
-        assert _conflict_degree([e1(4 * (ln & 1) + j, (ln >> 1) & 15, 2 * p) * 8 for ln in lanes], 16) == 1
-    for which, uu in itertools.product(range(2), range(4)):  # P2' stores / P4' loads of E2'
-        cols = [k1_of((ln >> 1) & 15, ln & 1) + 32 * which for ln in lanes]
-        assert _conflict_degree([e2(c, 2 * uu, swz(c)) * 8 for c in cols], 16) == 1
-    for w in range(16):  # P3': 64-bit, lanes (col, m2)
-        assert _conflict_degree([e2((w * 32 + ln) >> 3, (w * 32 + ln) & 7, swz((w * 32 + ln) >> 3)) * 8 for ln in lanes], 8) == 1
-    assert sorted(e1(i, k, l) for i in range(8) for k in range(16) for l in range(4)) == list(range(512))
-    assert sorted(e2(c, m, swz(c)) for c in range(64) for m in range(8)) == list(range(512))
-
-
 # ---------------------------------------------------------------------------------------------------------------------
 # 64^3 thread-per-line engine (leniax_b200/csrc/lnx_tiled64.cuh), emulated lane by lane (tests/emul/lnx_t64_emul.cu)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -143,20 +143,14 @@ def _orbium_batch(golden_dir, n, seed=0):
     return cfg, ocfg, np.stack(worlds), K, mapping, ufn, sfn
 
 
-@pytest.mark.parametrize('variant', ['tmem', 'smem', 'r16'])
-def test_fused_batch_matches_oracle_and_generic(golden_dir, variant):
-    """run_scan_mem_optimized (fused persistent kernels: the default TMEM kernel, the shared-memory kernel and the 512-thread
-    R16 variant) vs the oracle and vs the generic kernel on the same worlds."""
+def test_fused_batch_matches_oracle_and_generic(golden_dir):
+    """run_scan_mem_optimized (fused persistent TMEM kernel) vs the oracle and vs the generic kernel on the same worlds."""
     steps, n = 160, 12
-    runner.FUSED_VARIANT = variant
     cfg, ocfg, worlds, K, mapping, ufn, sfn = _orbium_batch(golden_dir, n)
     gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
     T = torch.tensor([10.], device=DEV)
     cells0 = torch.from_numpy(worlds).to(DEV)[None]  # [1, n, 1, 128, 128]
-    try:
-        mstats, final = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
-    finally:
-        runner.FUSED_VARIANT = 'tmem'
+    mstats, final = runner.run_scan_mem_optimized(None, cells0, K[None], gf[None], w[None], T, steps, 13, ufn, sfn)
     assert mstats['mass'].shape == (1, steps, n) and mstats['channel_mass'].shape == (1, steps, n, 1)
     assert mstats['N'].shape == (1, n) and final.shape == cells0.shape
     # generic kernel (trajectory requested)
@@ -774,11 +768,11 @@ def test_generic_kernels_early_stop_and_old_vs_new(golden_dir):
         ns = max(int(N[i]), 128)
         for k in ('mass', 'mass_speed', 'inertia', 'channel_mass'):
             np.testing.assert_array_equal(full[k][0, :ns, i].cpu().numpy(), fast[k][0, :ns, i].cpu().numpy())
-    runner.FUSED_VARIANT = 'smem'  # also selects the older generic kernel (per-CTA global scratch, statistics warp)
+    runner.GENERIC_OLD = True  # the older generic kernel (per-CTA global scratch, statistics warp)
     try:
         old, fold = runner.run_scan_mem_optimized(None, *args)
     finally:
-        runner.FUSED_VARIANT = 'tmem'
+        runner.GENERIC_OLD = False
     np.testing.assert_array_equal(old['N'].cpu().numpy(), full['N'].cpu().numpy())
     early = slice(0, 40)  # before rounding differences between the two kernels are amplified
     np.testing.assert_allclose(old['mass'][0, early].cpu().numpy(), full['mass'][0, early].cpu().numpy(), atol=2e-5)

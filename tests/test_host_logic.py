@@ -220,3 +220,27 @@ int main(void) {
     assert int(out[0]) == 100 and int(out[1]) == _lib.LNX_ERR_UNSUPPORTED and int(out[2]) == 1
     assert int(out[3]) == ctypes.sizeof(_lib.LnxDesc)  # the ctypes mirror and the C struct agree on the layout
     assert 'power of two' in out[4]
+
+
+def test_parallel_early_exit_oracle_equals_run_scan(golden_dir):
+    """oracle/parallel.py (used by the GPU integer-parity tests): dropping a world from the oracle's batch once its stop criteria
+    fired and 128 rows exist gives the same N and the same rows [ns-128, ns) as lo.run_scan; also through the process pool."""
+    from oracle import parallel as opar
+    cfg = lo.load_yaml_config(os.path.join(golden_dir, 'orbium-test.yaml'))
+    rng = np.random.default_rng(0)
+    ang = (2 * np.pi * rng.random((7, 3, 4))).astype(np.float32)
+    worlds = lo.perlin_from_angles(ang, [128, 128], 13, [.15, .015])
+    c, K, m = lo.init(copy.deepcopy(cfg))
+    worlds = np.concatenate([worlds, c])
+    steps = 150
+    keys = ('mass_density', 'mass_speed')
+    ref, _ = lo.run_scan(worlds, K, m.get_gf_params(), m.get_kernels_weight_per_channel(), np.float32(10.), steps, lo.build_update_fn(m),
+                         lo.build_compute_stats_fn(cfg['world_params'], cfg['render_params']), False)
+    for procs in (1, 2):
+        r = opar.parallel_scan(cfg['kernels_params'], cfg['world_params'], cfg['render_params'], worlds, steps, keys, chunk=4, procs=procs)
+        assert r['N'].tolist() == ref['N'].tolist()
+        assert (r['steps'] <= steps).all() and r['steps'].min() < steps  # some worlds really left early
+        for k in keys:
+            for i in range(len(worlds)):
+                ns = max(int(ref['N'][i]), 128)
+                assert abs(ref[k][ns - 128:ns, i].mean(dtype=np.float64) - r[k][i]) < 1e-6, (k, i)
