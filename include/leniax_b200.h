@@ -184,6 +184,57 @@ int lnx_update_conv(const lnx_desc* desc, int32_t n_worlds, int32_t kh, int32_t 
                     const float* gf_params, const float* weights, float dt, float* state_out, float* field_out, float* potential_out,
                     void* stream);
 
+/* ---- set-up either side of the scan, batched over all individuals of a QD generation ---- */
+
+/* kernel shapes: leniax/kernels.py:312-317 (register; `raw` needs no rasterisation), kernel functions: leniax/kernel_functions.py:253-261 */
+typedef enum { LNX_KSHAPE_EMPTY = 0, LNX_KSHAPE_CIRCLE_2D = 1, LNX_KSHAPE_ELLIPSE_2D = 2, LNX_KSHAPE_ORIENTED_ELLIPSE_2D = 3 } lnx_kernel_shape;
+typedef enum {
+    LNX_KF_POLY_QUAD = 0, LNX_KF_GAUSS_BUMP = 1, LNX_KF_STEP = 2, LNX_KF_GAUSS = 3, LNX_KF_THRESHOLD = 4, LNX_KF_STAIRCASE = 5,
+    LNX_KF_TRIANGLE = 6
+} lnx_kernel_fn;
+#define LNX_MAX_RINGS 8
+typedef struct lnx_kernel_spec {
+    int32_t shape;               /* lnx_kernel_shape; EMPTY = a padded slot of the reference's K tensor (all zeros, kernels.py:122-143) */
+    int32_t kf;                  /* lnx_kernel_fn (kf_slug) */
+    int32_t nb_b;                /* number of rings = len(k_params[1]) */
+    float r;                     /* k_params[0]: relative radius, the kernel covers ceil(r R) pixels either side */
+    float bs[LNX_MAX_RINGS];     /* k_params[1]: ring heights */
+    float kf_params[2];          /* q, or (m, s) for staircase / triangle */
+    float a, b;                  /* ellipses: k_params[2], k_params[3] */
+    float cos_theta, sin_theta;  /* ellipses: cos / sin of k_params[4] * pi */
+} lnx_kernel_spec;
+
+/* Rasterise n kernels in one launch: replaces kernels.circle_2d / ellipse_2d / oriented_ellipse_2d (leniax/kernels.py:176-309) and the
+ * kernel functions (leniax/kernel_functions.py:7-250), fp32 in the reference's operation order.  specs: HOST array; out: device float32
+ * [n][side][side], side even and >= 2 ceil(r R) for every kernel; a kernel of radius k px sits at offset side / 2 - k, i.e. centre-padding
+ * `out` into the world places it exactly where the reference's own centre padding does (leniax/utils.py:231-263). */
+int lnx_rasterize_kernels(int32_t n, const lnx_kernel_spec* specs, float R, int32_t side, float* out, void* stream);
+
+/* K = fftn(fftshift(centre-padded kernel)) (leniax/kernels.py:145-149) for n kernels in 2 (2-D) or 3 (3-D) launches: an exact separable
+ * DFT over the small support (fp64 accumulation and twiddles, one rounding to complex64).  spatial: device float32 [n][support...],
+ * K_out: device complex64 [n][dims...].  Any world size (no power-of-two restriction); no cuFFT. */
+int lnx_kernel_spectrum(int32_t nb_dims, const int32_t* dims, int32_t n, const int32_t* support, const float* spatial, void* K_out, void* stream);
+
+/* n uniform numbers in [0, 1) from a counter-based generator (SplitMix64 of seed + index): stands in for jax.random.uniform
+ * (initializations.py:24-28, 63-65; bit-parity with threefry is not provided, no reference test pins a random draw). */
+int lnx_random_uniform(uint64_t seed, int64_t n, float* out, void* stream);
+
+/* initializations.random_uniform (leniax/initializations.py:24-30): out[w][i] = make_array_compressible(u * maxvals[w]). */
+int lnx_init_uniform(uint64_t seed, int32_t n_worlds, int64_t cells_per_world, const float* maxvals, float* out, void* stream);
+
+/* initializations.perlin after the random draw (leniax/initializations.py:66-75) with perlin.generate_perlin_noise_2d
+ * (leniax/perlin.py:16-71) and loader.make_array_compressible (leniax/loader.py:16-30), one CTA per world:
+ * angles [n][res0][res1] (device) -> out [n][H][W] = quantise((noise - min) / max * scaling[w]).  noise_out != NULL: write the plain
+ * noise there instead (scaling / out may then be NULL). */
+int lnx_init_perlin(int32_t n_worlds, int32_t H, int32_t W, int32_t res0, int32_t res1, const float* angles, const float* scaling, float* out,
+                    float* noise_out, void* stream);
+
+/* The perlin initial states of a whole QD generation in ONE launch (replaces the per-individual calls of leniax/qd.py:121-125): world
+ * (s, i) of individual s draws its angles 2 pi u(seeds[s], i res0 res1 + j) itself - the numbers lnx_random_uniform(seeds[s]) gives - and
+ * proceeds as lnx_init_perlin.  seeds: HOST array [n_seeds]; scaling: device [n_seeds * nb_init]; out: device [n_seeds * nb_init][H][W]. */
+int lnx_init_perlin_seeded(int32_t n_seeds, const uint64_t* seeds, int32_t nb_init, int32_t H, int32_t W, int32_t res0, int32_t res1,
+                           const float* scaling, float* out, void* stream);
+
 /* Name of the CUDA kernel lnx_run_scan would launch for this plan/arguments ("fused" or "generic"), for tests. */
 const char* lnx_run_scan_variant(const lnx_plan* plan, int32_t with_trajectory);
 

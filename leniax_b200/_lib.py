@@ -5,11 +5,12 @@ implementation: a missing library or a missing GPU raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_size_t, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
 
 LNX_MAX_CHANNELS = 8
 LNX_MAX_KERNELS = 32
 LNX_NB_STATS = 11
+LNX_MAX_RINGS = 8
 
 LNX_RUN_EARLY_STOP = 1
 LNX_RUN_ASSUME_FINITE = 0x100
@@ -46,6 +47,24 @@ class LnxDesc(Structure):
     ]
 
 
+class LnxKernelSpec(Structure):
+    _fields_ = [
+        ('shape', c_int32),
+        ('kf', c_int32),
+        ('nb_b', c_int32),
+        ('r', c_float),
+        ('bs', c_float * LNX_MAX_RINGS),
+        ('kf_params', c_float * 2),
+        ('a', c_float),
+        ('b', c_float),
+        ('cos_theta', c_float),
+        ('sin_theta', c_float),
+    ]
+
+
+KSHAPE_IDS = {'circle_2d': 1, 'ellipse_2d': 2, 'oriented_ellipse_2d': 3}
+KF_IDS = {'poly_quad': 0, 'gauss_bump': 1, 'step': 2, 'gauss': 3, 'threshold': 4, 'staircase': 5, 'triangle': 6}
+
 EXPORTS = {
     'lnx_version': (ctypes.c_int, []),
     'lnx_last_error': (c_char_p, []),
@@ -64,6 +83,12 @@ EXPORTS = {
     'lnx_run_scan_variant': (c_char_p, [c_void_p, c_int32]),
     'lnx_summarize_stats': (ctypes.c_int, [POINTER(c_void_p), c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'lnx_update': (ctypes.c_int, [c_void_p, c_int32] + [c_void_p] * 9),
+    'lnx_rasterize_kernels': (ctypes.c_int, [c_int32, POINTER(LnxKernelSpec), c_float, c_int32, c_void_p, c_void_p]),
+    'lnx_kernel_spectrum': (ctypes.c_int, [c_int32, POINTER(c_int32), c_int32, POINTER(c_int32), c_void_p, c_void_p, c_void_p]),
+    'lnx_random_uniform': (ctypes.c_int, [c_uint64, c_int64, c_void_p, c_void_p]),
+    'lnx_init_uniform': (ctypes.c_int, [c_uint64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
+    'lnx_init_perlin': (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'lnx_init_perlin_seeded': (ctypes.c_int, [c_int32, POINTER(c_uint64), c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     'lnx_update_conv': (ctypes.c_int, [POINTER(LnxDesc), c_int32, c_int32, c_int32] + [c_void_p] * 4 + [c_float] + [c_void_p] * 4),
 }
 

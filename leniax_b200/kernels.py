@@ -1,8 +1,9 @@
 """Kernel rasterisation, packing and spectrum (reference: leniax/kernels.py:10-317).
 
 ``get_kernels_and_mapping`` keeps the reference signature and returns ``(K, KernelMapping)`` with the same shapes:
-``K`` is ``complex64 [1, C, max_k_per_channel, H, W]`` for ``fft=True``.  The spectrum is computed on the GPU with the
-engine's own butterflies (``lnx_rfft2``), not cuFFT; rasterisation uses torch elementwise ops on the same device.
+``K`` is ``complex64 [1, C, max_k_per_channel, H, W]`` for ``fft=True``.  On the GPU the kernels of ALL individuals of a
+generation are rasterised by one launch (``lnx_rasterize_kernels``) and transformed by an exact small-support DFT
+(``lnx_kernel_spectrum``; never cuFFT); the torch rasterisers below serve host-side callers (``fft=False`` on the CPU).
 """
 import ctypes
 import math
@@ -156,47 +157,166 @@ def sphere_nd(R, k_params: List, kf_slug: str, kf_params, device=None, nb_dims: 
     return (kernel / kernel.sum())[None]
 
 
-def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_channels: int, R: float, fft: bool = True,
-                            device=None) -> Tuple[torch.Tensor, KernelMapping]:
-    """Construct the kernel array and the associated mapping (leniax/kernels.py:66-158).
-
-    Like the reference it sorts ``kernels_params`` **in place** by ``c_in`` (kernels.py:90).
-    """
-    device = _default_device(device)
-    world_size = list(world_size)
+def _fill_mapping(kernels_params: List, nb_channels: int) -> KernelMapping:
+    """kernels.py:90-143: sort IN PLACE by ``c_in``, record the computation graph, mark the padded kernel slots."""
     mapping = KernelMapping(nb_channels, len(kernels_params))
     kernels_params.sort(key=lambda d: d['c_in'])
-    # K only depends on the kernel shapes (not on growth parameters or weights): in a QD generation every individual usually
-    # shares them (conf/config_qd_cmame*.yaml mutate gf_params and h), so the rasterisation + FFT is done once and reused.
-    cache_key = _kernel_cache_key(kernels_params, world_size, nb_channels, R, fft, device)
-    cached = _K_CACHE.get(cache_key) if cache_key is not None else None
-    padded = []
     for idx, p in enumerate(kernels_params):
-        if cached is None:
-            k = register[p['k_slug']](R, p['k_params'], p['kf_slug'], p['kf_params'], device=device)
-            pads: List[int] = []
-            for ws, ks in reversed(list(zip(world_size, k.shape[1:]))):  # F.pad wants the last dim first
-                lo = (ws - ks) // 2
-                pads += [lo, lo if (ws - ks) % 2 == 0 else lo + 1]
-            padded.append(torch.nn.functional.pad(k, pads))
         mapping.cin_kernels[p['c_in']].append(idx)
         mapping.cin_gfs[p['c_in']].append(p['gf_slug'])
         mapping.cin_gf_params[p['c_in']].append(p['gf_params'])
         mapping.cin_kfs[p['c_in']].append(p['kf_slug'])
         mapping.cin_k_params[p['c_in']].append(p['k_params'])
         mapping.kernels_weight_per_channel[p['c_out']][idx] = p['h']
-
     max_k = max(len(lst) for lst in mapping.cin_kernels)
     true_channels: List[bool] = []
     for lst in mapping.cin_kernels:  # kernels.py:122-143
         true_channels += [True] * len(lst) + [False] * (max_k - len(lst))
     mapping.true_channels = None if all(true_channels) else true_channels
-    if cached is not None:
-        return cached.clone(), mapping
+    return mapping
 
-    kernels = torch.cat(padded)  # [nb_kernels, *dims]
-    if not fft:
-        kernels = crop_zero(kernels)
+
+def _spec_of(p: Dict, R: float) -> Tuple[Optional[_lib.LnxKernelSpec], int]:
+    """Parametric kernel -> (descriptor for ``lnx_rasterize_kernels``, radius in pixels); ``raw`` kernels -> ``(None, 0)``."""
+    slug = p['k_slug']
+    if slug == 'raw':
+        return None, 0
+    if slug not in _lib.KSHAPE_IDS:
+        raise NotImplementedError(f"kernel shape '{slug}' is not one of {sorted(register)}")
+    if p['kf_slug'] not in _lib.KF_IDS:
+        raise NotImplementedError(f"kernel function '{p['kf_slug']}' is not one of {sorted(_lib.KF_IDS)}")
+    kp = p['k_params']
+    bs = [float(b) for b in (kp[1].tolist() if hasattr(kp[1], 'tolist') else kp[1])]
+    if len(bs) > _lib.LNX_MAX_RINGS:
+        raise ValueError(f'at most {_lib.LNX_MAX_RINGS} rings per kernel are supported, got {len(bs)}')
+    spec = _lib.LnxKernelSpec()
+    spec.shape, spec.kf, spec.nb_b, spec.r = _lib.KSHAPE_IDS[slug], _lib.KF_IDS[p['kf_slug']], len(bs), float(kp[0])
+    for i, b in enumerate(bs):
+        spec.bs[i] = b
+    kfp = [float(v) for v in (p['kf_params'].tolist() if hasattr(p['kf_params'], 'tolist') else p['kf_params'])]
+    for i, v in enumerate(kfp[:2]):
+        spec.kf_params[i] = v
+    if slug != 'circle_2d':
+        theta = float(kp[4]) * math.pi
+        spec.a, spec.b, spec.cos_theta, spec.sin_theta = float(kp[2]), float(kp[3]), math.cos(theta), math.sin(theta)
+    return spec, math.ceil(float(kp[0]) * R)
+
+
+def _spatial_kernels_cuda(all_params: List[Dict], R: float, device) -> List[torch.Tensor]:
+    """Spatial kernels ``[*support]`` of a flat list of kernel descriptions, all parametric ones rasterised by ONE launch."""
+    specs = [_spec_of(p, R) for p in all_params]
+    side = 2 * max([k for _, k in specs] + [1])
+    n_par = sum(1 for sp, _ in specs if sp is not None)
+    out: List[Optional[torch.Tensor]] = [None] * len(all_params)
+    if n_par:
+        arr = (_lib.LnxKernelSpec * n_par)(*[sp for sp, _ in specs if sp is not None])
+        buf = torch.empty((n_par, side, side), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.load_library().lnx_rasterize_kernels(n_par, arr, float(R), side, buf.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        j = 0
+        for i, (sp, _) in enumerate(specs):
+            if sp is not None:
+                out[i] = buf[j]
+                j += 1
+    for i, p in enumerate(all_params):
+        if out[i] is None:
+            out[i] = raw(R, p['k_params'], p['kf_slug'], p['kf_params'], device=device)[0]
+    return out  # type: ignore
+
+
+def kernel_spectrum(spatial: torch.Tensor, world_size: List[int]) -> torch.Tensor:
+    """``fftn(fftshift(centre-pad(kernel)))`` (kernels.py:145-149, utils.py:231-263) of ``spatial [n, *support]`` -> complex64
+    ``[n, *world_size]``: exact separable DFT over the support (``lnx_kernel_spectrum``; fp64 inside, no cuFFT)."""
+    if not spatial.is_cuda:
+        raise _lib.LeniaxB200Error('the kernel spectrum is computed on the GPU by lnx_kernel_spectrum; no CPU fallback exists')
+    nd = len(world_size)
+    spatial = spatial.contiguous().float()
+    n = spatial.shape[0]
+    K = torch.empty((n, ) + tuple(world_size), dtype=torch.complex64, device=spatial.device)
+    dims = (ctypes.c_int32 * 3)(*(list(world_size) + [1] * (3 - nd)))
+    support = (ctypes.c_int32 * 3)(*(list(spatial.shape[1:]) + [1] * (3 - nd)))
+    with torch.cuda.device(spatial.device):
+        _lib.check(_lib.load_library().lnx_kernel_spectrum(nd, dims, n, support, spatial.data_ptr(), K.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream))
+    return K
+
+
+def _spectra_of(spatials: List[torch.Tensor], world_size: List[int]) -> torch.Tensor:
+    """Spectra of a list of spatial kernels (grouped by support so that every group is one batched call) -> ``[n, *world_size]``."""
+    out = torch.empty((len(spatials), ) + tuple(world_size), dtype=torch.complex64, device=spatials[0].device)
+    groups: Dict[Tuple[int, ...], List[int]] = {}
+    for i, k in enumerate(spatials):
+        groups.setdefault(tuple(k.shape), []).append(i)
+    for shape, idxs in groups.items():
+        if any(s > w for s, w in zip(shape, world_size)):
+            raise ValueError(f'kernel of size {shape} does not fit the world {tuple(world_size)}')
+        out[torch.tensor(idxs, device=out.device)] = kernel_spectrum(torch.stack([spatials[i] for i in idxs]), world_size)
+    return out
+
+
+def get_kernels_and_mapping_batch(all_kernels_params: List[List], world_size: List[int], nb_channels: int, R: float, device=None
+                                  ) -> Tuple[torch.Tensor, List[KernelMapping]]:
+    """``get_kernels_and_mapping(fft=True)`` for every individual of a QD generation at once (replaces the per-individual loop of
+    leniax/qd.py:113-131): ONE rasterisation launch and ONE spectrum call (2-3 launches) for all kernels of all individuals.
+    Returns ``K [n_sols, 1, C, max_k, *world_size]`` complex64 and the mappings.  Every ``kernels_params`` is sorted in place."""
+    device = _default_device(device)
+    world_size = list(world_size)
+    mappings = [_fill_mapping(kp, nb_channels) for kp in all_kernels_params]
+    max_k = max(len(lst) for lst in mappings[0].cin_kernels)
+    layout = [list(m.cin_kernels) for m in mappings]
+    if any(lay != layout[0] for lay in layout):
+        raise ValueError('get_kernels_and_mapping_batch: all individuals must share the same (c_in -> kernels) layout')
+    flat = [p for kp in all_kernels_params for p in kp]
+    spectra = _spectra_of(_spatial_kernels_cuda(flat, R, device), world_size)
+    n_sols, nk = len(all_kernels_params), len(all_kernels_params[0])
+    spectra = spectra.reshape((n_sols, nk) + tuple(world_size))
+    K = torch.zeros((n_sols, nb_channels, max_k) + tuple(world_size), dtype=torch.complex64, device=device)
+    for c, lst in enumerate(mappings[0].cin_kernels):
+        for j, idx in enumerate(lst):
+            K[:, c, j] = spectra[:, idx]
+    return K[:, None], mappings
+
+
+def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_channels: int, R: float, fft: bool = True,
+                            device=None) -> Tuple[torch.Tensor, KernelMapping]:
+    """Construct the kernel array and the associated mapping (leniax/kernels.py:66-158).
+
+    Like the reference it sorts ``kernels_params`` **in place** by ``c_in`` (kernels.py:90).  On a CUDA device the kernels are
+    rasterised by ``lnx_rasterize_kernels`` and, for ``fft=True``, transformed by ``lnx_kernel_spectrum``; the torch
+    rasterisers of this module serve host-side callers of the direct-convolution path (``fft=False`` on the CPU).
+    """
+    device = _default_device(device)
+    world_size = list(world_size)
+    if fft and device.type == 'cuda':
+        # K only depends on the kernel shapes (not on growth parameters or weights): callers that loop over individuals which
+        # share them (conf/config_qd_cmame*.yaml mutate gf_params and h) get the cached spectrum back.
+        mapping = _fill_mapping(kernels_params, nb_channels)
+        cache_key = _kernel_cache_key(kernels_params, world_size, nb_channels, R, fft, device)
+        cached = _K_CACHE.get(cache_key) if cache_key is not None else None
+        if cached is not None:
+            return cached.clone(), mapping
+        K = get_kernels_and_mapping_batch([kernels_params], world_size, nb_channels, R, device)[0][0]
+        if cache_key is not None and _K_CACHE_MAX > 0:
+            if len(_K_CACHE) >= _K_CACHE_MAX:
+                _K_CACHE.pop(next(iter(_K_CACHE)))
+            _K_CACHE[cache_key] = K.clone()
+        return K, mapping
+    if fft:
+        raise _lib.LeniaxB200Error('the kernel spectrum is computed on the GPU (lnx_kernel_spectrum); no CPU fallback exists')
+    mapping = _fill_mapping(kernels_params, nb_channels)
+    max_k = max(len(lst) for lst in mapping.cin_kernels)
+    if device.type == 'cuda':
+        ks = [k[None] for k in _spatial_kernels_cuda(kernels_params, R, device)]
+    else:
+        ks = [register[p['k_slug']](R, p['k_params'], p['kf_slug'], p['kf_params'], device=device) for p in kernels_params]
+    padded = []
+    for k in ks:
+        pads: List[int] = []
+        for ws, ksz in reversed(list(zip(world_size, k.shape[1:]))):  # F.pad wants the last dim first
+            lo = (ws - ksz) // 2
+            pads += [lo, lo if (ws - ksz) % 2 == 0 else lo + 1]
+        padded.append(torch.nn.functional.pad(k, pads))
+    kernels = crop_zero(torch.cat(padded))  # [nb_kernels, kh, kw]
     kshape = tuple(kernels.shape[1:])
     per_channel = []
     for lst in mapping.cin_kernels:
@@ -205,39 +325,34 @@ def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_chan
         if missing:
             kc = torch.cat([kc, kernels.new_zeros((missing, ) + kshape)])
         per_channel.append(kc)
-
-    if fft:
-        nd = len(world_size)
-        dims = tuple(range(-nd, 0))
-        K = torch.stack(per_channel)[None]  # [1, C, max_k, *dims]
-        K = torch.roll(K, shifts=[s // 2 for s in K.shape[-nd:]], dims=dims)  # fftshift (kernels.py:147)
-        K = rfftn_full(K, nd)  # kernels.py:148
-    else:
-        K = torch.cat(per_channel)[:, None]  # [C*max_k, 1, kh, kw]
-    if cache_key is not None and _K_CACHE_MAX > 0:
-        if len(_K_CACHE) >= _K_CACHE_MAX:
-            _K_CACHE.pop(next(iter(_K_CACHE)))
-        _K_CACHE[cache_key] = K.clone()
-    return K, mapping
+    return torch.cat(per_channel)[:, None], mapping  # [C*max_k, 1, kh, kw]
 
 
 _K_CACHE: Dict[Tuple, torch.Tensor] = {}
 _K_CACHE_MAX = 64
+_UNCACHEABLE = object()
 
 
 def _freeze(x):
+    """Hashable image of a kernel parameter; ``_UNCACHEABLE`` for arrays (``k_slug: raw``) at any nesting level."""
+    import numbers
     if isinstance(x, (list, tuple)):
-        return tuple(_freeze(v) for v in x)
-    if isinstance(x, (int, float, str, bool)) or x is None:
+        items = tuple(_freeze(v) for v in x)
+        return _UNCACHEABLE if any(v is _UNCACHEABLE for v in items) else items
+    if isinstance(x, (str, bool)) or x is None:
         return x
-    return None  # tensors / arrays (k_slug 'raw'): not cached
+    if isinstance(x, numbers.Real):  # Python and NumPy scalars
+        return float(x)
+    if hasattr(x, 'ndim') and x.ndim == 0 and hasattr(x, 'item'):  # 0-d arrays / tensors
+        return float(x.item())
+    return _UNCACHEABLE
 
 
 def _kernel_cache_key(kernels_params: List, world_size: List[int], nb_channels: int, R: float, fft: bool, device) -> Optional[Tuple]:
     parts = []
     for p in kernels_params:
         kp, kfp = _freeze(p['k_params']), _freeze(p['kf_params'])
-        if kp is None or kfp is None or (isinstance(kp, tuple) and any(v is None for v in kp)):
+        if kp is _UNCACHEABLE or kfp is _UNCACHEABLE:
             return None
         parts.append((p['k_slug'], kp, p['kf_slug'], kfp, int(p['c_in'])))
     return (tuple(parts), tuple(world_size), int(nb_channels), float(R), bool(fft), str(torch.device(device)))

@@ -244,3 +244,22 @@ def test_parallel_early_exit_oracle_equals_run_scan(golden_dir):
             for i in range(len(worlds)):
                 ns = max(int(ref['N'][i]), 128)
                 assert abs(ref[k][ns - 128:ns, i].mean(dtype=np.float64) - r[k][i]) < 1e-6, (k, i)
+
+
+def test_kernel_cache_key_distinguishes_numpy_and_tensor_scalars():
+    """np.float32 / 0-d tensor parameters used to freeze to None, so different kernels shared one cache entry."""
+    import torch
+    from leniax_b200 import kernels
+
+    def key(kf_params, bs):
+        kp = [dict(k_slug='circle_2d', k_params=[1., bs], kf_slug='poly_quad', kf_params=kf_params, c_in=0)]
+        return kernels._kernel_cache_key(kp, [128, 128], 1, 13., True, 'cpu')
+
+    assert key([np.float32(4)], [1.]) != key([np.float32(1)], [1.])
+    assert key([4], [np.float32(1), np.float32(.5)]) != key([4], [np.float32(.2), np.float32(1)])
+    assert key([torch.tensor(4.)], [1.]) != key([torch.tensor(2.)], [1.])
+    assert key([np.float32(4)], [1.]) == key([4.0], [1.0])  # same values, same key
+    raw = [dict(k_slug='raw', k_params=np.ones((1, 3, 3), np.float32), kf_slug='poly_quad', kf_params=[4], c_in=0)]
+    assert kernels._kernel_cache_key(raw, [128, 128], 1, 13., True, 'cpu') is None  # arrays are not cached
+    nested = [dict(k_slug='circle_2d', k_params=[1., [1., np.ones(2)]], kf_slug='poly_quad', kf_params=[4], c_in=0)]
+    assert kernels._kernel_cache_key(nested, [128, 128], 1, 13., True, 'cpu') is None  # ... at any nesting level

@@ -82,6 +82,14 @@ def test_shard_ranges_cover_everything():
     pieces = [p for r in range(4) for p in lnx_dist.local_pieces(3, 10, r, 4)]
     covered = sorted((s, i) for s, a, b in pieces for i in range(a, b))
     assert covered == [(s, i) for s in range(3) for i in range(10)]
+    # rectangles = launches: BASELINE configs[2] (16 solutions x 128 inits over 8 ranks) and configs[1] (1 x 4096) are one launch per rank
+    assert lnx_dist.local_rectangles(16, 128, 3, 8) == [(6, 8, 0, 128)]
+    assert lnx_dist.local_rectangles(1, 4096, 7, 8) == [(0, 1, 3584, 4096)]
+    for n_sols, n_init, world in [(3, 10, 4), (5, 7, 3), (16, 128, 8), (2, 3, 8)]:
+        rects = [r for rk in range(world) for r in lnx_dist.local_rectangles(n_sols, n_init, rk, world)]
+        assert all(len(lnx_dist.local_rectangles(n_sols, n_init, rk, world)) <= 3 for rk in range(world))
+        cov = sorted((s, i) for s0, s1, a, b in rects for s in range(s0, s1) for i in range(a, b))
+        assert cov == [(s, i) for s in range(n_sols) for i in range(n_init)]
 
 
 # ---- 2-rank gloo run: each rank simulates its slice with a CPU stand-in (oracle), one all_gather, same result ----
@@ -107,8 +115,15 @@ def _worker(rank, world, port, golden_dir, out_dir):
         upd = lo.build_update_fn(mapping)
         sfn = lo.build_compute_stats_fn(cfg['world_params'], cfg['render_params'])
         summary, keys, _ = lnx_dist.run_scan_mem_optimized_sharded(None, *args, steps, 13, upd, sfn, local_run=_oracle_local_run)
-        torch.save({'summary': summary, 'keys': keys, 'pieces': lnx_dist.local_pieces(n_sols, n_init, rank, world)},
-                   os.path.join(out_dir, f'rank{rank}.pt'))
+        # the same batch with every rank holding only its own part: one solution each / a ragged split of the initialisations
+        s0, s1 = lnx_dist.shard_range(n_sols, rank, world)
+        by_sols, _, _ = lnx_dist.run_scan_mem_optimized_sharded(None, *[a[s0:s1] for a in args], steps, 13, upd, sfn,
+                                                                local_run=_oracle_local_run, sharded_inputs='sols')
+        i0, i1 = lnx_dist.shard_range(n_init, rank, world)  # 3 inits over 2 ranks: 2 + 1
+        by_inits, _, _ = lnx_dist.run_scan_mem_optimized_sharded(None, args[0][:, i0:i1], *args[1:], steps, 13, upd, sfn,
+                                                                 local_run=_oracle_local_run, sharded_inputs='inits')
+        torch.save({'summary': summary, 'keys': keys, 'pieces': lnx_dist.local_pieces(n_sols, n_init, rank, world), 'by_sols': by_sols,
+                    'by_inits': by_inits}, os.path.join(out_dir, f'rank{rank}.pt'))
         if rank == 0:
             full, _ = _oracle_local_run(None, *args, steps, 13, upd, sfn)
             torch.save(qd.summarize_stats(full)[0], os.path.join(out_dir, 'single.pt'))
@@ -126,3 +141,5 @@ def test_two_rank_gloo_sharding_matches_single_process(golden_dir, tmp_path):
     assert torch.equal(r0['summary'], r1['summary'])  # every rank holds the gathered block
     assert torch.equal(r0['summary'], single)  # and it equals the unsharded computation bit for bit
     assert r0['pieces'] != r1['pieces'] and len(r0['keys']) == 11
+    for k in ('by_sols', 'by_inits'):  # pre-sharded inputs: same gathered block on both ranks, equal to the unsharded one
+        assert torch.equal(r0[k], r1[k]) and torch.equal(r0[k], single), k
