@@ -28,6 +28,8 @@ extern "C" {
 #define LNX_MAX_CHANNELS 8
 #define LNX_MAX_KERNELS 32
 #define LNX_NB_STATS 11 /* scalar statistics per world-step, order = lnx_stat_key */
+#define LNX_COUT_ANY (-1)
+#define LNX_COUT_NONE (-2)
 
 typedef enum {
     LNX_OK = 0,
@@ -63,6 +65,10 @@ typedef enum {
 #define LNX_RUN_NO_STATS 2u   /* reserved */
 #define LNX_RUN_GENERIC_OLD 0x400u   /* several channels / kernels: use the older lnx_world128_generic kernel (everything in an L2
                                         scratch, statistics warp) instead of lnx_world128_gen_tm; cross-check in the tests */
+#define LNX_RUN_GENERIC_1CTA 0x1000u  /* several channels / kernels: one world per SM (lnx_world128_gen_tm) even when the two-worlds-per-SM
+                                        kernel applies; A/B runs and cross-check in the tests */
+#define LNX_RUN_WEIGHTS_MATCH_COUT 0x2000u /* caller checked that `weights` is zero outside the (c_out[k], k) entries the plan declares:
+                                        required by lnx_world128_gen2, which reads one weight per kernel */
 #define LNX_RUN_TILED_GENERIC 0x800u /* 64^3 and 2048^2 one-channel one-kernel worlds: use the generic tiled passes instead of
                                         the thread-per-line / four-step kernels (A/B runs, cross-check in the tests) */
 #define LNX_RUN_ASSUME_FINITE 0x100u /* caller checked that no growth s == 0 and no weight row sums to 0: NaN cannot
@@ -81,6 +87,9 @@ typedef struct {
     int32_t slot[LNX_MAX_KERNELS];       /* tc_indices: slot of kernel k inside [C * max_k] (helpers.py:449-456) */
     int32_t c_in[LNX_MAX_KERNELS];       /* input channel of kernel k ( = slot / max_k, kernels.py:122-143) */
     int32_t gf_id[LNX_MAX_KERNELS];      /* lnx_growth_fn of kernel k (mapping.cin_gfs flattened) */
+    int32_t c_out[LNX_MAX_KERNELS];      /* the ONE channel whose weight row is non-zero in column k (kernels.py:110-111: W[c_out][k] = h),
+                                            LNX_COUT_NONE when the column is all zero; LNX_COUT_ANY in every entry = not declared: the
+                                            weights tensor is used as given (slower kernel for several channels) */
     int32_t state_fn;                    /* lnx_state_fn (world_params.get_state_fn_slug) */
     int32_t weighted_average;            /* 1: core.weighted_mean, 0: core.weighted_sum (core.py:202-242) */
     float R;                             /* world_params.R used by the statistics (statistics.py:23) */
@@ -235,7 +244,7 @@ int lnx_init_perlin(int32_t n_worlds, int32_t H, int32_t W, int32_t res0, int32_
 int lnx_init_perlin_seeded(int32_t n_seeds, const uint64_t* seeds, int32_t nb_init, int32_t H, int32_t W, int32_t res0, int32_t res1,
                            const float* scaling, float* out, void* stream);
 
-/* Name of the CUDA kernel lnx_run_scan would launch for this plan/arguments ("fused" or "generic"), for tests. */
+/* Name of the CUDA kernel family lnx_run_scan would launch for this plan/arguments ("fused", "generic2", "generic", "tiled"), for tests. */
 const char* lnx_run_scan_variant(const lnx_plan* plan, int32_t with_trajectory);
 
 #ifdef __cplusplus

@@ -11,11 +11,14 @@ LNX_MAX_CHANNELS = 8
 LNX_MAX_KERNELS = 32
 LNX_NB_STATS = 11
 LNX_MAX_RINGS = 8
+LNX_COUT_ANY, LNX_COUT_NONE = -1, -2
 
 LNX_RUN_EARLY_STOP = 1
 LNX_RUN_ASSUME_FINITE = 0x100
 LNX_RUN_GENERIC_OLD = 0x400
 LNX_RUN_TILED_GENERIC = 0x800
+LNX_RUN_GENERIC_1CTA = 0x1000
+LNX_RUN_WEIGHTS_MATCH_COUT = 0x2000
 LNX_PLAN_FORCE_TILED = 1
 
 LNX_OK, LNX_ERR_INVALID, LNX_ERR_UNSUPPORTED, LNX_ERR_CUDA, LNX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -39,6 +42,7 @@ class LnxDesc(Structure):
         ('slot', c_int32 * LNX_MAX_KERNELS),
         ('c_in', c_int32 * LNX_MAX_KERNELS),
         ('gf_id', c_int32 * LNX_MAX_KERNELS),
+        ('c_out', c_int32 * LNX_MAX_KERNELS),
         ('state_fn', c_int32),
         ('weighted_average', c_int32),
         ('R', c_float),

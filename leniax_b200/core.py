@@ -145,7 +145,7 @@ def update_conv(state: torch.Tensor, K, gf_params, kernels_weight_per_channel, d
     d.dims[0], d.dims[1] = int(world_size[0]), int(world_size[1])
     d.nb_channels, d.nb_kernels, d.nb_slots = C, len(slots), ufn.get_potential_fn.nb_slots
     for k in range(len(slots)):
-        d.slot[k], d.c_in[k], d.gf_id[k] = int(slots[k]), int(c_in[k]), int(gf_ids[k])
+        d.slot[k], d.c_in[k], d.gf_id[k], d.c_out[k] = int(slots[k]), int(c_in[k]), int(gf_ids[k]), _lib.LNX_COUT_ANY
     d.state_fn = engine.STATE_FN_IDS[ufn.get_state_fn.slug]
     d.weighted_average = 1 if ufn.get_field_fn.average else 0
     d.R, d.stats_dt = 1.0, 1.0

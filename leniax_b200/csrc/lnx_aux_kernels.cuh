@@ -15,18 +15,26 @@ struct PrepArgs {
     int slot[MAX_K];
 };
 __global__ void __launch_bounds__(NT) lnx_prepare_kernel(PrepArgs P) {
+    __shared__ float red[2][NT];
     const int sol = blockIdx.x / P.K, k = blockIdx.x % P.K, tid = threadIdx.x;
     const float2* Kf = P.K_fft + ((size_t)sol * P.nb_slots + P.slot[k]) * (WS * WS);
     float4* tab = P.table + ((size_t)sol * P.K + k) * KTAB_F4;
     const float scale = 1.0f / (2.0f * WS * WS);
     const int col = t_col(tid);
+    float max_re = 0.f, max_im = 0.f;
     for (int i = 0; i < 16; ++i) {
         float2 v[2];
         for (int e = 0; e < 2; ++e) {
             const int m = p3_slot_m(tid, 2 * i + e);
             v[e] = col == 0 ? make_float2(0.f, 0.f) : Kf[m * WS + col];
+            max_re = fmaxf(max_re, fabsf(v[e].x));
+            max_im = fmaxf(max_im, fabsf(v[e].y));
         }
         tab[i * NT + tid] = make_float4(v[0].x * scale, v[0].y * scale, v[1].x * scale, v[1].y * scale);
+        if (i & 1) {  // real parts of slots 4j .. 4j+3, j = i / 2 (lnx_world128_gen2 stages these when the spectrum is real)
+            const float4 lo = tab[(i - 1) * NT + tid];
+            tab[KTAB_REAL_F4 + (i >> 1) * NT + tid] = make_float4(lo.x, lo.z, v[0].x * scale, v[1].x * scale);
+        }
     }
     if (tid < KPQ_LANES) {
         for (int s = 0; s < 32; ++s) {
@@ -36,6 +44,19 @@ __global__ void __launch_bounds__(NT) lnx_prepare_kernel(PrepArgs P) {
             tab[KT_F4 + s * KPQ_LANES + tid] = make_float4((k0.x + k64.x) * h, (k0.y + k64.y) * h, (k0.x - k64.x) * h, (k0.y - k64.y) * h);
         }
     }
+    // "real spectrum": every imaginary part below a quarter of an fp32 ulp of the largest multiplier (the packed column is always
+    // multiplied in its general complex form, so only the plain columns matter)
+    red[0][tid] = max_re;
+    red[1][tid] = max_im;
+    __syncthreads();
+    for (int s = NT / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            red[0][tid] = fmaxf(red[0][tid], red[0][tid + s]);
+            red[1][tid] = fmaxf(red[1][tid], red[1][tid + s]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) tab[KTAB_FLAG_F4] = make_float4(__int_as_float(red[1][0] <= red[0][0] * 1.4901161e-8f ? 1 : 0), red[0][0], red[1][0], 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -4,6 +4,8 @@
 //   lnx_tu_tm.cu       lnx_world128_tm      fused 1-channel 1-kernel scan, state + multipliers in tensor memory (default)
 //   lnx_tu_generic.cu  lnx_world128_gen_tm / lnx_world128_generic (several channels / kernels), kernel-table builder, rfft2,
 //                      FP32 probe
+//   lnx_tu_gen2.cu     lnx_world128_gen2    several channels / kernels, two worlds per SM (default when the kernel graph allows)
+//   lnx_tu_setup.cu    kernel rasterisation, exact kernel spectrum, random numbers, initial states
 // Every kernel family compiles in its own translation unit so that the library builds in parallel.
 #pragma once
 #include <cstdarg>
@@ -40,6 +42,12 @@ int generic_launch(bool gen_tm, int grid, const RunArgs& a, cudaStream_t st);
 int prepare_launch(const lnx_desc& d, int n_sols, const void* K_fft, void* table, cudaStream_t st);
 int rfft2_launch(int n_images, const float* images, void* spectra, cudaStream_t st);
 int fp32_peak_launch(int grid, int block, float* out, int iters, cudaStream_t st);
+
+// ---- lnx_tu_gen2.cu ----
+int gen2_setup_device();
+bool gen2_plan(const lnx_desc& d, RunArgs& a);  // fills the schedule fields of `a`; false: this kernel graph runs in gen_tm instead
+size_t gen2_scratch_planes(int C);              // 64 KB planes of L2 scratch per CTA
+int gen2_launch(int grid, const RunArgs& a, cudaStream_t st);
 
 }  // namespace host
 }  // namespace lnx

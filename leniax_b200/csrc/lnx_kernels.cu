@@ -197,6 +197,18 @@ static int replay_steps(EnqueueStep enqueue_step, int steps, cudaStream_t st) {
     g_retired.push_back({exec, graph, done});
     return LNX_OK;
 }
+// worlds per launch of the 64^3 line engine.  Default: all of them.  LNX_T64_BATCH=n runs every n worlds through ALL their steps
+// before the next n start (so that a batch stays L2-resident: 3.2 MB per world); measured SLOWER on B200 (256 worlds x 64 steps:
+// 30.2 ms unbatched, 42 / 46 / 55 ms at 64 / 39 / 13 worlds per batch, profiles/r2_e_batch_sweep.txt): a wave of the plane kernel
+// takes 43-47 us per step whether its planes come from L2 or HBM - the per-warp dependency chain, not the memory level, sets the
+// pace - so smaller launches only lower the number of warps in flight.  Kept for A/B runs.
+static int t64_batch(long long worlds) {
+    static const int forced = [] {
+        const char* e = getenv("LNX_T64_BATCH");
+        return e ? atoi(e) : 0;
+    }();
+    return forced > 0 ? forced : (int)worlds;
+}
 static bool is_cube64(const Geom& g) { return g.nd == 3 && g.dims[0] == 64 && g.dims[1] == 64 && g.dims[2] == 64; }
 static size_t tw_bytes(int logn) { return ((size_t)1 << (logn - 1)) * sizeof(float2); }  // shared-memory twiddle table of one pass
 static int log_inner(const Geom& g) { return g.logA2 > g.logA1 ? g.logA2 : g.logA1; }
@@ -302,6 +314,8 @@ static int ensure_device_init(int* dev_out, int* sms_out) {
         if (rc != LNX_OK) return rc;
         rc = lnx::host::generic_setup_device();
         if (rc != LNX_OK) return rc;
+        rc = lnx::host::gen2_setup_device();
+        if (rc != LNX_OK) return rc;
         sms[dev] = prop.multiProcessorCount;
         done[dev] = true;
     }
@@ -351,6 +365,7 @@ int lnx_plan_create(const lnx_desc* d, lnx_plan** out) {
         if (d->c_in[k] < 0 || d->c_in[k] >= d->nb_channels) return fail(LNX_ERR_INVALID, "c_in[%d] out of range", k);
         if (d->slot[k] < 0 || d->slot[k] >= d->nb_slots) return fail(LNX_ERR_INVALID, "slot[%d] out of range", k);
         if (d->gf_id[k] < 0 || d->gf_id[k] >= GF_COUNT) return fail(LNX_ERR_INVALID, "gf_id[%d]: unknown growth function", k);
+        if (d->c_out[k] < LNX_COUT_NONE || d->c_out[k] >= d->nb_channels) return fail(LNX_ERR_INVALID, "c_out[%d] out of range", k);
     }
     if (d->state_fn < 0 || d->state_fn >= SF_COUNT) return fail(LNX_ERR_INVALID, "unknown state function %d", d->state_fn);
     if (!(d->R > 0.f) || !(d->stats_dt > 0.f)) return fail(LNX_ERR_INVALID, "R and stats_dt must be positive");
@@ -397,8 +412,10 @@ size_t lnx_workspace_bytes_for(const lnx_plan* p, int32_t n_sols, int32_t n_init
 size_t lnx_workspace_bytes(const lnx_plan* p) {
     if (!p) return 0;
     if (p->tiled) return th::carve(p->g, p->d.nb_channels, p->d.nb_kernels, 1, nullptr).bytes;
-    // 256 B header (world queue counter) + per-CTA scratch of the generic kernel: [3][C] thread-private images
-    return 256 + (size_t)p->sm_count * 3 * p->d.nb_channels * PLANE_F4 * sizeof(float4);
+    // 256 B header (world queue counter) + per-CTA scratch of the multi-channel kernels: [3][C] thread-private images for one CTA per SM
+    // (lnx_world128_generic), [C + 1] for two CTAs per SM (lnx_world128_gen2)
+    const size_t one = (size_t)3 * p->d.nb_channels, two = 2 * lnx::host::gen2_scratch_planes(p->d.nb_channels);
+    return 256 + (size_t)p->sm_count * (one > two ? one : two) * PLANE_F4 * sizeof(float4);
 }
 
 int lnx_kernels_prepare(const lnx_plan* p, int32_t n_sols, const void* K_fft, void* table, void* stream) {
@@ -449,6 +466,7 @@ int lnx_rfftn(int32_t nb_dims, const int32_t* dims, int32_t n_images, const floa
     LNX_CUDA(cudaMallocAsync(&sa, bytes, st));
     LNX_CUDA(cudaMallocAsync(&sb, bytes, st));
     lnx::tiled::PassAArgs a;
+    memset(&a, 0, sizeof(a));
     a.state = images;
     a.spec = sa;
     a.tw = th::g_tw[dev];
@@ -509,6 +527,7 @@ int lnx_compute_stats(const lnx_plan* p, int32_t n_worlds, const float* cells, c
     a.K = p->d.nb_kernels;
     stats_partials_kernel<<<dim3(g.n_slabs, 1, n_worlds), TPB, 0, st>>>(a);
     PassDArgs d;
+    memset(&d, 0, sizeof(d));
     d.partials = partials;
     d.carry = carry;
     d.stats = stats;
@@ -579,6 +598,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
     LNX_CUDA(cudaMemcpyAsync(state, cells0, (size_t)worlds * C * g.cells * sizeof(float), cudaMemcpyDeviceToDevice, st));
     LNX_CUDA(cudaMemsetAsync(ws.carry, 0, (size_t)worlds * sizeof(WorldCarry), st));
     PassAArgs a;
+    memset(&a, 0, sizeof(a));
     a.state = state;
     a.spec = ws.spec;
     a.tw = tw;
@@ -616,6 +636,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
     c.state_fn = p->d.state_fn;
     c.mean = p->d.weighted_average;
     PassDArgs d;
+    memset(&d, 0, sizeof(d));
     d.partials = ws.partials;
     d.carry = ws.carry;
     d.stats = stats;
@@ -644,9 +665,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
     lnx::t2k::Extra x2k;
     x2k.tw = th::g_tw2k[p->device];
     x2k.ktab = static_cast<const float2*>(table) + (size_t)n_sols * g.spec;
-    for (int t = 0; t < max_run_iter; ++t) {
-        c.t = t;
-        d.t = t;
+    {
         if (line2k) {
             // a step = lead (+ pass D of the previous step) + the fused (inverse rows, update, forward rows of the next step) kernel
             using namespace lnx::t2k;
@@ -662,12 +681,21 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             if (rc != LNX_OK) return rc;
             d.t = max_run_iter - 1;  // the last step's statistics
             pass_d_kernel<<<nw, 128, 0, st>>>(d);
-            break;
         } else if (line64) {
-            // a step = lead + the fused (inverse planes, update, forward planes of the next step) kernel
-            if (t == 0) lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);
-            th::launch_lead64(b, (unsigned)worlds, st);
-            lnx::t64::plane_inv_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(c, a.spec);
+            // a step = lead + the fused (inverse planes, update, forward planes of the next step) kernel + pass D (all worlds per launch
+            // unless LNX_T64_BATCH asks for L2-sized batches, see t64_batch)
+            const int batch = th::t64_batch(worlds);
+            for (long long w0 = 0; w0 < worlds; w0 += batch) {
+                const unsigned nb = (unsigned)(worlds - w0 < batch ? worlds - w0 : batch);
+                a.world0 = b.world0 = c.world0 = d.world0 = (int)w0;
+                lnx::t64::plane_fwd_kernel<<<dim3(64, 1, nb), 32, 0, st>>>(a);
+                for (int tt = 0; tt < max_run_iter; ++tt) {
+                    c.t = d.t = tt;
+                    th::launch_lead64(b, nb, st);
+                    lnx::t64::plane_inv_kernel<<<dim3(64, 1, nb), 32, 0, st>>>(c, a.spec);
+                    pass_d_kernel<<<nb, th::pass_d_threads(g, nb), 0, st>>>(d);
+                }
+            }
         } else {
             // generic passes: four launches with step-independent arguments (t < 0: the step index is read from the carry), replayed
             c.t = -1;
@@ -681,9 +709,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
                 },
                 max_run_iter, st);
             if (rc != LNX_OK) return rc;
-            break;
         }
-        pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, st>>>(d);
     }
     LNX_CUDA(cudaGetLastError());
     return LNX_OK;
@@ -751,7 +777,9 @@ static bool use_fused(const lnx_plan* p, bool trajectory) {
 const char* lnx_run_scan_variant(const lnx_plan* p, int32_t with_trajectory) {
     if (!p) return "";
     if (p->tiled) return "tiled";
-    return use_fused(p, with_trajectory != 0) ? "fused" : "generic";
+    if (use_fused(p, with_trajectory != 0)) return "fused";
+    RunArgs a;
+    return !with_trajectory && lnx::host::gen2_plan(p->d, a) ? "generic2" : "generic";  // generic2 also needs LNX_RUN_WEIGHTS_MATCH_COUT
 }
 
 int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_run_iter, uint32_t run_flags, const float* cells0,
@@ -811,6 +839,13 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
         // caller opts into the fast one with LNX_RUN_ASSUME_FINITE (set by the Python layer after checking the parameters).
         const int grid2 = (int)(n_worlds < 2 * p->sm_count ? n_worlds : 2 * p->sm_count);  // TMEM-resident state, two worlds per SM
         return lnx::host::tm_launch(p->d.gf_id[0], p->d.state_fn, !(run_flags & LNX_RUN_ASSUME_FINITE), grid2, a, st);
+    }
+    // several channels / kernels: two worlds per SM when the declared weight pattern (desc.c_out) lets two tensor-memory accumulators
+    // suffice and the caller vouches that the weights tensor has no other non-zero entry; else one world per SM
+    if (!trajectory && (run_flags & LNX_RUN_WEIGHTS_MATCH_COUT) && !(run_flags & (LNX_RUN_GENERIC_OLD | LNX_RUN_GENERIC_1CTA)) &&
+        lnx::host::gen2_plan(p->d, a)) {
+        const int grid2 = (int)(n_worlds < 2 * p->sm_count ? n_worlds : 2 * p->sm_count);
+        return lnx::host::gen2_launch(grid2, a, st);
     }
     return lnx::host::generic_launch(lnx::host::gen_tm_supports(a.C) && !(run_flags & LNX_RUN_GENERIC_OLD), grid, a, st);
 }

@@ -15,7 +15,10 @@ constexpr int KT_F4 = 16 * NT;      // float4 per kernel table (complex multipli
 constexpr int KPQ_F4 = 32 * KPQ_LANES;  // float4 per packed-column table (Kp, Kq)
 constexpr int SCRATCH_BYTES = 2 * 4 * 32 * 8;  // packed-column exchange of warp 0
 constexpr int TW_BYTES = TW_TABLE_F4 * 16;     // run-time twiddle table of P2/P4
-constexpr int KTAB_F4 = KT_F4 + KPQ_F4;  // per (solution, kernel): complex multipliers, then the packed DC|Nyquist column
+constexpr int KREAL_F4 = 8 * NT;         // float4 per kernel: the real parts of the 32 multipliers of every thread (lnx_world128_gen2)
+constexpr int KTAB_REAL_F4 = KT_F4 + KPQ_F4;          // offsets inside the table of one (solution, kernel): complex multipliers,
+constexpr int KTAB_FLAG_F4 = KTAB_REAL_F4 + KREAL_F4; // packed DC|Nyquist column, real multipliers, flag word (1: the spectrum is real)
+constexpr int KTAB_F4 = KTAB_FLAG_F4 + 4;
 constexpr int PLANE_F4 = 16 * NT;  // float4 per thread-private image (L2 scratch of the multi-channel kernels)
 constexpr int NPART_FUSED = PT_FIXED + 1;
 constexpr int NPART_MAX = PT_FIXED + MAX_C;
@@ -69,6 +72,12 @@ struct RunArgs {
     unsigned flags;
     int c_in[MAX_K];
     int gf_id[MAX_K];
+    // schedule of lnx_world128_gen2 (host-built from the plan's c_in / c_out, lnx_kernel_gen2.cuh)
+    signed char c_out[MAX_K];      // output channel of kernel k, < 0: none
+    signed char acc_slot[MAX_K];   // tensor-memory accumulator slot (0 / 1) kernel k adds into
+    unsigned char upd_mask[MAX_K]; // channels whose state is updated after kernel k
+    signed char chan_slot[MAX_C];  // slot holding channel c's field at its update, < 0: no kernel feeds it (field 0)
+    unsigned acc_first;            // bit k: kernel k is the first to touch its slot in this step (plain store instead of add)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

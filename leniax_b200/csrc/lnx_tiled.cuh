@@ -141,6 +141,7 @@ struct PassAArgs {
     const float2* tw;
     Geom g;
     int C;
+    int world0;  // first world of this launch (the 64^3 line engine runs L2-sized batches of worlds; 0 elsewhere)
 };
 __global__ void __launch_bounds__(TPB) pass_a_kernel(PassAArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -204,6 +205,7 @@ struct PassBArgs {
     Geom g;
     int C, K, n_init;
     int two_buf;           // 1: some channel feeds several kernels (forward spectrum kept in F, products in T); 0: in place
+    int world0;
     int c_in[MAX_K];
 };
 __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
@@ -289,6 +291,7 @@ struct PassCArgs {
     Geom g;
     int C, K, n_init, max_iter, t;
     int state_fn, mean;
+    int world0;
     int gf_id[MAX_K];
 };
 __global__ void __launch_bounds__(TPB, 3) pass_c_kernel(PassCArgs P) {
@@ -469,6 +472,7 @@ struct PassDArgs {
     float* n_alive;
     Geom g;
     int C, n_sols, n_init, max_iter, t;
+    int world0;
     float R, stats_dt;
 };
 constexpr int PASS_D_MAX_WARPS = 16;
@@ -575,7 +579,8 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w, con
     P.n_alive[w] = S.n_alive;
 }
 __global__ void __launch_bounds__(32 * PASS_D_MAX_WARPS) pass_d_kernel(PassDArgs P) {  // 4..16 warps: see pass_d_threads()
-    pass_d_body(P, blockIdx.x, P.t >= 0 ? P.t : P.carry[blockIdx.x].step);
+    const int w = blockIdx.x + P.world0;
+    pass_d_body(P, w, P.t >= 0 ? P.t : P.carry[w].step);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

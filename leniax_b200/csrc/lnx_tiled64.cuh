@@ -326,7 +326,7 @@ LNX_HD void inv_update_dispatch(int lane, float* ps, float* __restrict__ st, flo
 // grid (64 planes, C, worlds), one warp
 __global__ void __launch_bounds__(32) plane_fwd_kernel(PassAArgs P) {
     __shared__ __align__(16) float sm[SMEM_FLOATS];
-    const int lane = threadIdx.x, l = blockIdx.x, c = blockIdx.y, w = blockIdx.z;
+    const int lane = threadIdx.x, l = blockIdx.x, c = blockIdx.y, w = blockIdx.z + P.world0;
     const size_t plane = ((size_t)w * P.C + c) * N + l;
     fwd_load(lane, P.state + plane * PLANE_CELLS, sm);
     __syncwarp();
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(32) plane_fwd_kernel(PassAArgs P) {
 // grid (33, C, worlds), 64 threads: thread = one spectral column
 template <int MINB>
 __global__ void __launch_bounds__(LEAD_TPB, MINB) lead_kernel(PassBArgs P) {
-    const int col = blockIdx.x * LEAD_TPB + threadIdx.x, c = blockIdx.y, w = blockIdx.z;
+    const int col = blockIdx.x * LEAD_TPB + threadIdx.x, c = blockIdx.y, w = blockIdx.z + P.world0;
     const float2* src = P.spec + ((size_t)w * P.C + c) * ((size_t)N * COLS) + col;
     float2 v[64];
     if (P.fwd_out) {
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(LEAD_TPB, MINB) lead_kernel(PassBArgs P) {
 // time loop is then lead + this kernel + pass D, after one plane_fwd launch for the first step.
 __global__ void __launch_bounds__(32, 12) plane_inv_kernel(PassCArgs P, float2* next_spec) {  // 12: three warps per scheduler (<= 168 registers)
     __shared__ __align__(16) float sm[SMEM_FLOATS];
-    const int lane = threadIdx.x, l = blockIdx.x, w = blockIdx.z;
+    const int lane = threadIdx.x, l = blockIdx.x, w = blockIdx.z + P.world0;
     const int sol = w / P.n_init, init = w - sol * P.n_init;
     const size_t plane = (size_t)w * N + l;
     float2* pl = reinterpret_cast<float2*>(sm);

@@ -62,9 +62,10 @@ class Plan:
     @classmethod
     def get(cls, *, world_size: Sequence[int], nb_channels: int, slots: Sequence[int], c_in: Sequence[int],
             gf_ids: Sequence[int], nb_slots: int, state_fn: str, weighted_average: bool, R: float, stats_dt: float,
-            device: torch.device, force_tiled: bool = False) -> 'Plan':
+            device: torch.device, force_tiled: bool = False, c_out: Optional[Sequence[int]] = None) -> 'Plan':
+        c_out = tuple(c_out) if c_out is not None else tuple(_lib.LNX_COUT_ANY for _ in slots)
         key = (tuple(world_size), nb_channels, tuple(slots), tuple(c_in), tuple(gf_ids), nb_slots, state_fn,
-               bool(weighted_average), float(R), float(stats_dt), str(device), bool(force_tiled))
+               bool(weighted_average), float(R), float(stats_dt), str(device), c_out, bool(force_tiled))
         plan = cls._cache.get(key)
         if plan is None:
             if state_fn not in STATE_FN_IDS:
@@ -81,7 +82,7 @@ class Plan:
             if len(slots) > _lib.LNX_MAX_KERNELS:
                 raise ValueError(f'at most {_lib.LNX_MAX_KERNELS} kernels are supported, got {len(slots)}')
             for k in range(len(slots)):
-                d.slot[k], d.c_in[k], d.gf_id[k] = int(slots[k]), int(c_in[k]), int(gf_ids[k])
+                d.slot[k], d.c_in[k], d.gf_id[k], d.c_out[k] = int(slots[k]), int(c_in[k]), int(gf_ids[k]), int(c_out[k])
             d.state_fn = STATE_FN_IDS[state_fn]
             d.weighted_average = 1 if weighted_average else 0
             d.R = float(R)

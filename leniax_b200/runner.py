@@ -5,6 +5,7 @@ Same names and positional signatures as the reference.  ``update_fn`` is a ``cor
 the reference builds its callables).  Arrays may be torch tensors (CUDA or CPU) or numpy arrays; results are CUDA
 tensors.  ``rng_key`` is accepted and ignored: no registered state function consumes randomness (core.py:245-319).
 """
+import weakref
 from typing import Dict, Tuple
 
 import numpy as np
@@ -27,15 +28,41 @@ def _check_fns(update_fn, compute_stats_fn):
         raise NotImplementedError('compute_stats_fn must come from leniax_b200.statistics.build_compute_stats_fn')
 
 
-def _finite_params(gf_params: torch.Tensor, weights: torch.Tensor, average: bool) -> bool:
-    """True when NaN cannot be born in the step: no growth width s == 0, no all-zero weight row."""
-    ok = bool((gf_params[..., 1] != 0).all().item()) and bool(torch.isfinite(gf_params).all().item())
+_PARAM_SUMMARY_CACHE = weakref.WeakKeyDictionary()
+
+
+def _param_summary(gf_params: torch.Tensor, weights: torch.Tensor, average: bool) -> Tuple[bool, Tuple[int, ...]]:
+    """What the launch needs to know about the device-side parameters, from ONE device reduction and ONE host sync (cached per
+    tensor object and version, so a loop over the same parameters syncs once):
+
+    * ``finite``: NaN cannot be born in the step — no growth width ``s == 0``, no all-zero weight row, nothing non-finite (SURVEY §7);
+    * ``c_out[k]``: the single channel whose weight is non-zero in column ``k`` for some solution (``kernels.py:110-111`` writes
+      ``W[c_out][k] = h``), ``LNX_COUT_NONE`` for an all-zero column; ``LNX_COUT_ANY`` everywhere when some column feeds several
+      channels (hand-made weights): the engine then uses the weights tensor as given.
+
+    ``gf_params [S, K, 2]``, ``weights [S, C, K]``."""
+    hit = _PARAM_SUMMARY_CACHE.get(weights)
+    key = (weights._version, id(gf_params), gf_params._version, bool(average))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    C, K = weights.shape[-2], weights.shape[-1]
+    bad = (~torch.isfinite(gf_params).all()) | (gf_params[..., 1] == 0).any() | (~torch.isfinite(weights).all())
     if average:
-        ok = ok and bool((weights.sum(dim=-1) != 0).all().item())
-    return ok and bool(torch.isfinite(weights).all().item())
+        bad = bad | (weights.sum(dim=-1) == 0).any()
+    nz = (weights.reshape(-1, C, K) != 0).any(dim=0)  # [C, K]
+    packed = torch.cat([bad.reshape(1), nz.reshape(-1)]).to(torch.uint8).cpu().tolist()  # the one synchronisation
+    finite = packed[0] == 0
+    c_out = []
+    for k in range(K):
+        rows = [c for c in range(C) if packed[1 + c * K + k]]
+        c_out.append(rows[0] if len(rows) == 1 else (_lib.LNX_COUT_NONE if not rows else None))
+    res = (finite, tuple(_lib.LNX_COUT_ANY for _ in range(K)) if any(v is None for v in c_out) else tuple(c_out))
+    _PARAM_SUMMARY_CACHE[weights] = (key, res)
+    return res
 
 
 GENERIC_OLD = False  # tests: several channels / kernels through the older lnx_world128_generic kernel (cross-check)
+GENERIC_1CTA = False  # tests / A-B runs: several channels / kernels through lnx_world128_gen_tm (one world per SM) instead of gen2
 TILED_GENERIC = False  # tests / A-B runs: 64^3 one-channel one-kernel worlds through the generic tiled passes instead of lnx_tiled64.cuh
 FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the tiled multi-pass engine as a cross-check
 
@@ -67,20 +94,25 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
         return _scan_conv(cells0, K, gf_params, weights, T, max_run_iter, update_fn, stats_fn, keep_trajectory)
     slots, c_in, gf_ids = update_fn.kernel_layout(C)
     K = K.reshape((n_sols, pf.nb_slots) + world_size)
+    gfp, wts = gf_params.reshape(n_sols, len(slots), 2), weights.reshape(n_sols, C, len(slots))
+    finite, c_out = _param_summary(gfp, wts, update_fn.get_field_fn.average)
     plan = engine.Plan.get(world_size=world_size, nb_channels=C, slots=slots, c_in=c_in, gf_ids=gf_ids, nb_slots=pf.nb_slots,
                            state_fn=update_fn.get_state_fn.slug, weighted_average=update_fn.get_field_fn.average, R=stats_fn.R,
-                           stats_dt=stats_fn.dt, device=dev, force_tiled=FORCE_TILED_ENGINE)
+                           stats_dt=stats_fn.dt, device=dev, force_tiled=FORCE_TILED_ENGINE, c_out=c_out)
     flags = 0
     if early_stop:
         flags |= _lib.LNX_RUN_EARLY_STOP
     if GENERIC_OLD:
         flags |= _lib.LNX_RUN_GENERIC_OLD
+    if GENERIC_1CTA:
+        flags |= _lib.LNX_RUN_GENERIC_1CTA
     if TILED_GENERIC:
         flags |= _lib.LNX_RUN_TILED_GENERIC
-    if _finite_params(gf_params, weights, update_fn.get_field_fn.average):
+    if finite:
         flags |= _lib.LNX_RUN_ASSUME_FINITE
+    if c_out[0] != _lib.LNX_COUT_ANY:
+        flags |= _lib.LNX_RUN_WEIGHTS_MATCH_COUT
     dt = (1. / T.reshape(n_sols)).contiguous()  # runner.py:307
-    gfp, wts = gf_params.reshape(n_sols, len(slots), 2), weights.reshape(n_sols, C, len(slots))
     if host_cells is not None:
         n_first = 2 * torch.cuda.get_device_properties(dev).multi_processor_count  # one full wave of CTAs of the fused kernel
         if n_sols == 1 and not keep_trajectory and n_init >= 4 * n_first:

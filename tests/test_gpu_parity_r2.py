@@ -140,7 +140,10 @@ def _report(tag, N, idx, o32, o64, steps):
     oN, oN64 = o32['N'], o64['N']
     oidx = _cells_of(o32['mass_density'], o32['mass_speed'])
     oidx64 = _cells_of(o64['mass_density'], o64['mass_speed'])
-    decided = (oN == oN64) & ((oN <= 100) | (oN == steps))
+    # "decided": the stop criteria fire within 100 steps in both oracle arithmetics.  A perlin soup is a chaotic transient — two arithmetics
+    # that start 1e-7 apart are 1e-4 apart after 50 steps and 1e-2 after 100 (measured on world 25 of tests/test_gpu_parity.py's sample with
+    # the CPU emulator) — so every later outcome, INCLUDING which soups condense into a surviving Orbium, is decided by rounding noise.
+    decided = (oN == oN64) & (oN <= 100)
     n = len(N)
     res = {
         'n': n, 'decided': int(decided.sum()),
@@ -152,7 +155,7 @@ def _report(tag, N, idx, o32, o64, steps):
         'cell_twin': float((oidx64 == oidx).all(axis=1).mean()),
     }
     record('[b] %s: %d worlds x %d steps | identical stop step N: whole sample %.1f %% (fp64 twin vs fp32 oracle: %.1f %%), decided class '
-           '(%d worlds: both oracle arithmetics agree and N <= 100 or N == T) %.1f %%, rounding-chaotic rest (%d worlds) %.1f %% (twin %.1f %%)'
+           '(%d worlds: N <= 100 in both oracle arithmetics) %.1f %%, rounding-chaotic rest (%d worlds) %.1f %% (twin %.1f %%)'
            % (tag, n, steps, 100 * res['N_all'], 100 * res['N_twin'], res['decided'], 100 * res['N_decided'], n - res['decided'],
               100 * res['N_late'], 100 * res['N_twin_late']))
     record('[b] %s: identical archive cell (20 x 20 GridArchive of mass_density x mass_speed): whole sample %.1f %% (twin %.1f %%), decided '
@@ -184,7 +187,7 @@ def test_integer_outputs_unfiltered_config_B(golden_dir):
     g = 16
     fit, ofit = N.reshape(-1, g).max(axis=1), o32['N'].reshape(-1, g).max(axis=1)
     record('[b] config B as %d configs of %d inits: identical fitness (max N) %.1f %%' % (len(fit), g, 100 * float((fit == ofit).mean())))
-    assert r['decided'] >= n // 4
+    assert r['decided'] >= n // 8
     assert r['N_decided'] >= 0.99 and r['cell_decided'] >= 0.99
     # whole sample: no worse than the reference arithmetic reproduces itself across precisions (minus sampling slack)
     assert r['N_all'] >= r['N_twin'] - 0.05, r
