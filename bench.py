@@ -370,8 +370,11 @@ class Workload:
         import leniax_b200
         from leniax_b200 import _lib
         lib = leniax_b200.load_library()
-        plan = next(p for p in leniax_b200.engine.Plan._cache.values()
-                    if tuple(p.key[0]) == tuple(self.dims) and p.desc.nb_channels == self.C and p.device == self.dev_cells.device)
+        plan = [p for p in leniax_b200.engine.Plan._cache.values()  # the plan the runner built for this workload (the latest that matches)
+                if tuple(p.key[0]) == tuple(self.dims) and p.desc.nb_channels == self.C and p.device == self.dev_cells.device][-1]
+        run_flags = _lib.LNX_RUN_ASSUME_FINITE | (_lib.LNX_RUN_WEIGHTS_MATCH_COUT if plan.desc.c_out[0] != _lib.LNX_COUT_ANY else 0)
+        if self.config == 'C':
+            self.kernel = {'generic2': 'lnx_world128_gen2', 'generic': 'lnx_world128_gen_tm'}[plan.variant(False)]
         n_sols, n_init = self.dev_cells.shape[:2]
         dev, f32 = self.dev_cells.device, torch.float32
         table = plan.prepare_kernels(self.K.reshape((n_sols, -1) + tuple(self.dims)), n_sols)
@@ -384,7 +387,7 @@ class Workload:
         stream = torch.cuda.current_stream().cuda_stream
 
         def launch():
-            _lib.check(lib.lnx_run_scan(plan.handle, n_sols, n_init, self.sim_steps, _lib.LNX_RUN_ASSUME_FINITE, self.dev_cells.data_ptr(),
+            _lib.check(lib.lnx_run_scan(plan.handle, n_sols, n_init, self.sim_steps, run_flags, self.dev_cells.data_ptr(),
                                         table.data_ptr(), gf.data_ptr(), w.data_ptr(), dt.data_ptr(), stats.data_ptr(), cm.data_ptr(), na.data_ptr(),
                                         None, None, None, None, ws.data_ptr(), ws.numel(), stream))
 

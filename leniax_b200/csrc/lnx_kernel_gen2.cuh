@@ -16,7 +16,7 @@
 // Statistics as in lnx_world128_tm: reduced behind the first barrier of the next step, batched finaliser every 32 steps.
 // Same arithmetic as gen_tm (growth_vec_dyn, state_update_dyn, weight -> accumulate -> * 1 / sum(W)), hence the same results.
 #pragma once
-#include "lnx_kernel_generic.cuh"
+#include "lnx_kernel_tm.cuh"  // TmCtrl
 
 namespace lnx {
 
@@ -118,6 +118,9 @@ __device__ __forceinline__ void g3_mul_complex_global(Regs& R, const float4* __r
     }
 }
 
+// GF / SF >= 0: every kernel uses this growth function / the plan this state function (compile-time arithmetic, smaller loop);
+// -1: selected per kernel / per launch at run time.  The loop must stay small: two CTAs stream it through one instruction cache.
+template <int GF, int SF>
 __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float2* W = reinterpret_cast<float2*>(smem);
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                         R.v[2 * i] = make_float2(s4.x, s4.y);
                         R.v[2 * i + 1] = make_float2(s4.z, s4.w);
                     }
+                    __syncthreads();  // every warp has read the previous potential out of W (phase5_load): phase3_ifft_store may overwrite it
                 }
                 // ---- multiply by kernel k, inverse transform ----
                 const float4* ktab = tab + (size_t)k * KTAB_F4;
@@ -276,9 +280,13 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                 phase4_compute_store(tid, R, W, twtab);
                 __syncwarp();
                 phase5_load(tid, R, W);
-                __syncthreads();  // W is free for the next transform
+                // (no CTA barrier here: P4 -> P5 and the next P1 -> P2 exchange inside the half-warp's own region of W; the next write
+                // to OTHER regions is phase3_ifft_store, behind the P2 -> P3 barrier or the one in front of it below)
                 phase5_ifft(R);
-                growth_vec_dyn<true, 32>(P.gf_id[k], R.v, gc->gf[k], cnt_p);
+                if constexpr (GF >= 0)
+                    growth_vec<GF, true, 32>(R.v, gc->gf[k], cnt_p);
+                else
+                    growth_vec_dyn<true, 32>(P.gf_id[k], R.v, gc->gf[k], cnt_p);
                 if (P.c_out[k] >= 0) {  // field accumulator (tensor memory), core.py:202-242
                     const uint32_t aa = acc0 + 64 * P.acc_slot[k];
                     const float2 w2 = pk_bc(gc->w[k]);
@@ -324,43 +332,60 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                     const uint32_t aa = acc0 + 64 * (slot < 0 ? 0 : slot);
                     float2 sa = make_float2(0.f, 0.f), sg = sa, mx = sa, mx2 = sa, gx = sa;
                     int cnt_a = 0, cnt_g = 0;
-                    float4 sv[16];  // the whole state of the channel first: all L2 loads in flight together (R.v is dead here)
+                    // rolled loop over the 8 chunks (the code of this phase is fetched every step by both CTAs of the SM): the L2 loads
+                    // run two chunks ahead of the arithmetic, the tensor-memory load one chunk ahead
+                    float4 a0 = st[0 * NT + tid], a1 = st[1 * NT + tid], b0 = st[2 * NT + tid], b1 = st[3 * NT + tid];
+                    float fb[2][8];
+                    if (slot >= 0) tm::ld8(aa, fb[0]);
+#pragma unroll 1
+                    for (int i = 0; i < 8; i += 2) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) sv[i] = st[i * NT + tid];
-                    float buf[2][8];
-                    if (slot >= 0) tm::ld8(aa, buf[0]);
+                        for (int h = 0; h < 2; ++h) {  // chunk i + h; unrolled by two so that the double buffers keep static names
+                            const int ci = i + h;
+                            float4 c0 = a0, c1 = a1;
+                            if (ci + 2 < 8) {
+                                c0 = st[(2 * ci + 4) * NT + tid];
+                                c1 = st[(2 * ci + 5) * NT + tid];
+                            }
+                            float* f = fb[h];
+                            if (slot >= 0) {
+                                tm::wait_ld8(f);
+                                if (ci + 1 < 8) tm::ld8(aa + 8 * (ci + 1), fb[h ^ 1]);
+                            } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float* f = buf[i & 1];
-                        if (slot >= 0) {
-                            tm::wait_ld8(f);
-                            if (i + 1 < 8) tm::ld8(aa + 8 * (i + 1), buf[(i + 1) & 1]);
-                        } else {
+                                for (int e = 0; e < 8; ++e) f[e] = 0.f;
+                            }
+                            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            const float4 x4 = xt[l * XT_STRIDE + ci], q4 = xt[(4 + l) * XT_STRIDE + ci];
+                            const float xc[4] = {x4.x, x4.y, x4.z, x4.w}, xc2[4] = {q4.x, q4.y, q4.z, q4.w};
+                            float n[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 A = make_float2(a[2 * e], a[2 * e + 1]);
+                                const float2 F = pk_mul(make_float2(f[2 * e], f[2 * e + 1]), inv2);
+                                sa = pk_add(sa, A);
+                                mx = pk_fma(A, pk_bc(xc[e]), mx);
+                                mx2 = pk_fma(A, pk_bc(xc2[e]), mx2);
+                                cnt_a += gt_bits(A.x, EPS) + gt_bits(A.y, EPS);
+                                const float2 G = make_float2(fmaxf(F.x, 0.f), fmaxf(F.y, 0.f));
+                                sg = pk_add(sg, G);
+                                gx = pk_fma(G, pk_bc(xc[e]), gx);
+                                cnt_g += gt_bits(F.x, EPS) + gt_bits(F.y, EPS);
+                                if constexpr (SF >= 0) {
+                                    n[2 * e] = state_update<SF, true>(A.x, F.x, dt);
+                                    n[2 * e + 1] = state_update<SF, true>(A.y, F.y, dt);
+                                } else {
+                                    n[2 * e] = state_update_dyn<true>(P.state_fn, A.x, F.x, dt);
+                                    n[2 * e + 1] = state_update_dyn<true>(P.state_fn, A.y, F.y, dt);
+                                }
+                            }
+                            st[(2 * ci) * NT + tid] = make_float4(n[0], n[1], n[2], n[3]);
+                            st[(2 * ci + 1) * NT + tid] = make_float4(n[4], n[5], n[6], n[7]);
+                            a0 = b0;
+                            a1 = b1;
+                            b0 = c0;
+                            b1 = c1;
                         }
-                        const float4 lo = sv[2 * i], hi = sv[2 * i + 1];
-                        const float a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                        const float4 x4 = xt[l * XT_STRIDE + i], q4 = xt[(4 + l) * XT_STRIDE + i];
-                        const float xc[4] = {x4.x, x4.y, x4.z, x4.w}, xc2[4] = {q4.x, q4.y, q4.z, q4.w};
-                        float n[8];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 A = make_float2(a[2 * e], a[2 * e + 1]);
-                            const float2 F = pk_mul(make_float2(f[2 * e], f[2 * e + 1]), inv2);
-                            sa = pk_add(sa, A);
-                            mx = pk_fma(A, pk_bc(xc[e]), mx);
-                            mx2 = pk_fma(A, pk_bc(xc2[e]), mx2);
-                            cnt_a += gt_bits(A.x, EPS) + gt_bits(A.y, EPS);
-                            const float2 G = make_float2(fmaxf(F.x, 0.f), fmaxf(F.y, 0.f));
-                            sg = pk_add(sg, G);
-                            gx = pk_fma(G, pk_bc(xc[e]), gx);
-                            cnt_g += gt_bits(F.x, EPS) + gt_bits(F.y, EPS);
-                            n[2 * e] = state_update_dyn<true>(P.state_fn, A.x, F.x, dt);
-                            n[2 * e + 1] = state_update_dyn<true>(P.state_fn, A.y, F.y, dt);
-                        }
-                        st[(2 * i) * NT + tid] = make_float4(n[0], n[1], n[2], n[3]);
-                        st[(2 * i + 1) * NT + tid] = make_float4(n[4], n[5], n[6], n[7]);
                     }
                     g3_part_add(part, PT_M00_C0 + c, tid, sa.x + sa.y);
                     g3_part_add(part, PT_MX_R, tid, xr0 * sa.x + xr1 * sa.y);

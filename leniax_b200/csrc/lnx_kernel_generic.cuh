@@ -258,11 +258,6 @@ constexpr int G2_OFF_CTRL = G2_OFF_GC + (((int)sizeof(GenericConsts) + 15) / 16)
 constexpr int G2_SMEM = G2_OFF_CTRL + 160;
 static_assert(G2_SMEM <= 227 * 1024, "generic TMEM kernel: shared memory over the per-CTA limit");
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // totals of one step -> ring row (C channels); warp 1 advances the shift carry and rebuilds the coordinate table
 __device__ __forceinline__ void g2_reduce_partials(const float* part, float* row, TmCtrl* ctrl, float4* xt, int C, int warp, int lane) {

@@ -5,12 +5,20 @@
 namespace lnx {
 namespace host {
 
+// the specialised instantiation covers what the reference's multi-channel configurations use (conf/config_qd_cmame_3c6k.yaml,
+// conf/species/2d/*: poly_quad4 growth, v1 update); everything else selects per kernel at run time
+static const void* gen2_kernel(bool poly_quad4_v1) {
+    return poly_quad4_v1 ? reinterpret_cast<const void*>(&lnx_world128_gen2<GF_POLY_QUAD4, SF_V1>) : reinterpret_cast<const void*>(&lnx_world128_gen2<-1, -1>);
+}
+
 int gen2_setup_device() {
     float2 tw[128];
     for (int k = 0; k < 128; ++k) tw[k] = make_float2(Tw128::c[k], Tw128::s[k]);
     LNX_CUDA(cudaMemcpyToSymbol(c_tw128, tw, sizeof(tw)));
-    LNX_CUDA(cudaFuncSetAttribute(lnx_world128_gen2, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
-    LNX_CUDA(cudaFuncSetAttribute(lnx_world128_gen2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (const void* fn : {gen2_kernel(true), gen2_kernel(false)}) {
+        LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM));
+        LNX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     return LNX_OK;
 }
 
@@ -19,8 +27,11 @@ bool gen2_plan(const lnx_desc& d, RunArgs& a) { return gen2_schedule(d.nb_channe
 size_t gen2_scratch_planes(int C) { return (size_t)(C + 1); }
 
 int gen2_launch(int grid, const RunArgs& a, cudaStream_t st) {
-    lnx_world128_gen2<<<grid, NT, G3_SMEM, st>>>(a);
-    LNX_CUDA(cudaGetLastError());
+    bool fast = a.state_fn == SF_V1;
+    for (int k = 0; k < a.K; ++k) fast = fast && a.gf_id[k] == GF_POLY_QUAD4;
+    RunArgs args = a;
+    void* kargs[] = {&args};
+    LNX_CUDA(cudaLaunchKernel(gen2_kernel(fast), dim3(grid), dim3(NT), kargs, G3_SMEM, st));
     return LNX_OK;
 }
 

@@ -600,3 +600,111 @@ def test_golden_fixture_distances_to_exact_arithmetic(golden_dir):
         o64 = lo.init_and_run(ocfg, with_jit=True, dtype=np.float64)[0][-1, 0]
         record('[d] %-20s last frame: GPU vs fp64 twin %.2e | fp32 oracle vs fp64 twin %.2e | GPU vs fp32 oracle %.2e'
                % (name, np.abs(got - o64).max(), np.abs(o32 - o64).max(), np.abs(got - o32).max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (g) lnx_world128_gen2 (several channels / kernels, two worlds per SM) against lnx_world128_gen_tm and the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _run_both_generic_kernels(args, steps, ufn, sfn):
+    stats2, final2 = runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn)
+    runner.GENERIC_1CTA = True
+    try:
+        stats1, final1 = runner.run_scan_mem_optimized(None, *args, steps, 13, ufn, sfn)
+    finally:
+        runner.GENERIC_1CTA = False
+    return stats2, final2, stats1, final1
+
+
+def test_gen2_kernel_matches_gen_tm_and_oracle():
+    n_sols, n_init, steps = 3, 6, 48
+    kps, args, ufn = _c3_solutions(n_sols, n_init, seed=8)
+    wp, rp = {'R': 13, 'T': 10, 'nb_channels': 3}, {'world_size': [128, 128]}
+    sfn = statistics.build_compute_stats_fn(wp, rp)
+    stats2, final2, stats1, final1 = _run_both_generic_kernels(args, steps, ufn, sfn)
+    plans = [p for p in leniax_b200.engine.Plan._cache.values() if p.desc.nb_kernels == 6 and p.desc.nb_channels == 3]
+    assert plans and all(p.variant(False) == 'generic2' for p in plans if p.desc.c_out[0] >= 0)
+    assert torch.equal(stats2['N'], stats1['N'])
+    d_final = float((final2 - final1).abs().max())
+    worst = {k: float(((stats2[k] - stats1[k]).abs() / (stats1[k].abs().amax() + 1e-12)).max()) for k in ('mass', 'growth', 'mass_volume', 'mass_speed', 'inertia')}
+    record('[g] gen2 vs gen_tm (3c6k, %d solutions x %d inits x %d steps): N identical, final state Linf %.2e, statistics (relative) %s'
+           % (n_sols, n_init, steps, d_final, {k: '%.1e' % v for k, v in worst.items()}))
+    assert d_final < 2e-5 and worst['mass'] < 1e-5 and worst['mass_volume'] < 2e-3
+    # the oracle on the same worlds: states after 32 steps, N over the whole run
+    errs = []
+    for s in range(n_sols):
+        oK, om = lo.get_kernels_and_mapping(copy.deepcopy(kps[s]), [128, 128], 3, 13)
+        ost, ofin = lo.run_scan(args[0][s].cpu().numpy(), oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), steps,
+                                lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp), False)
+        assert stats2['N'][s].cpu().numpy().tolist() == ost['N'].tolist()
+        np.testing.assert_allclose(stats2['mass'][s, :12].cpu().numpy(), ost['mass'][:12], rtol=2e-5, atol=2e-6)
+        # (perlin soups with random 3c6k parameters are chaotic transients: 1e-7 grows to 1e-4 within ~30 steps, so the state is compared
+        # after 6 steps and the integer outcome N over the whole run)
+        _, f10 = runner.run_scan_mem_optimized(None, *[a[s:s + 1] for a in args], 6, 13, ufn, sfn)
+        o10 = lo.run_scan(args[0][s].cpu().numpy(), oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), 6,
+                          lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp), False)[1]
+        errs.append(float(np.abs(f10[0].cpu().numpy() - o10).max()))
+    record('[g] gen2 vs fp32 oracle: N identical on %d worlds over %d steps, state Linf after 6 steps per solution: %s' % (n_sols * n_init, steps, _fmt(errs)))
+    assert max(errs) <= 1e-5, errs
+
+
+def test_gen2_complex_spectrum_and_fallbacks(golden_dir):
+    """States are compared after 10 steps (chaotic soups, see above), N over 24.  (i) a kernel whose spectrum is NOT real (ellipse_2d: odd gradient factor) takes its multipliers from L2 inside gen2; (ii) weights
+    that feed one kernel into two channels cannot be declared as a c_out pattern: the scan runs in gen_tm; (iii) a graph that needs three
+    live accumulators (every channel read last, written first) is refused by the schedule: gen_tm again.  All three against the oracle."""
+    steps = 24
+    rng = np.random.default_rng(3)
+    wp, rp = {'R': 13, 'T': 10, 'nb_channels': 2}, {'world_size': [128, 128]}
+    kp = [_kp('ellipse_2d', [1., [1.], .9, .6, .25], 'poly_quad', [4], 0, 0), _kp('circle_2d', [1., [1., .5]], 'poly_quad', [4], 0, 1),
+          _kp('circle_2d', [.8, [1.]], 'poly_quad', [4], 1, 1), _kp('circle_2d', [1., [1.]], 'poly_quad', [4], 1, 0)]
+    for p, g in zip(kp, ([.2, .03], [.25, .04], [.18, .03], [.3, .05])):
+        p['gf_params'], p['h'] = g, float(.4 + .5 * rng.random())
+    cells = (rng.random((1, 5, 2, 128, 128), dtype=np.float32) * np.kron(rng.random((1, 5, 2, 8, 8), dtype=np.float32), np.ones((16, 16), np.float32))).astype(np.float32)
+    K, mapping = kernels.get_kernels_and_mapping(copy.deepcopy(kp), [128, 128], 2, 13, device=DEV)
+    assert float(K.imag.abs().max()) > 1e-3  # the ellipse spectrum is genuinely complex
+    ufn = helpers.build_update_fn(K.shape, mapping)
+    sfn = statistics.build_compute_stats_fn(wp, rp)
+    gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
+    T = torch.tensor([10.], device=DEV)
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(kp), [128, 128], 2, 13)
+    osf = lo.build_compute_stats_fn(wp, rp)
+
+    def check(tag, weights_t, weights_np, expect_variant):
+        args = (torch.from_numpy(cells).to(DEV), K[None], gf, weights_t, T)
+        stats2, _, stats1, _ = _run_both_generic_kernels(args, steps, ufn, sfn)
+        _, final2, _, final1 = _run_both_generic_kernels(args, 10, ufn, sfn)
+        ost, _ = lo.run_scan(cells[0], oK, om.get_gf_params(), weights_np, np.float32(10.), steps, lo.build_update_fn(om), osf, False)
+        ofin = lo.run_scan(cells[0], oK, om.get_gf_params(), weights_np, np.float32(10.), 10, lo.build_update_fn(om), osf, False)[1]
+        e2, e1 = float(np.abs(final2[0].cpu().numpy() - ofin).max()), float(np.abs(final1[0].cpu().numpy() - ofin).max())
+        plan = [p for p in leniax_b200.engine.Plan._cache.values() if p.desc.nb_kernels == 4 and p.desc.nb_channels == 2][-1]
+        record('[g] %s: default kernel (%s) vs oracle after %d steps %.2e, gen_tm vs oracle %.2e, N %s / %s'
+               % (tag, expect_variant, 10, e2, e1, stats2['N'][0].cpu().numpy().tolist(), ost['N'].tolist()))
+        assert e2 <= 1e-5 and e1 <= 1e-5
+        assert stats2['N'][0].cpu().numpy().tolist() == ost['N'].tolist()
+        return plan
+
+    plan = check('complex spectrum (ellipse_2d) in gen2', w, om.get_kernels_weight_per_channel(), 'generic2')
+    assert plan.variant(False) == 'generic2' and [plan.desc.c_out[k] for k in range(4)] == [0, 1, 1, 0]
+    w_np = om.get_kernels_weight_per_channel().copy()
+    w_np[1, 0] = .3  # kernel 0 now feeds channels 0 AND 1
+    plan = check('kernel feeding two channels', torch.from_numpy(w_np).to(DEV)[None], w_np, 'generic')
+    assert [plan.desc.c_out[k] for k in range(4)] == [-1] * 4
+    # three live accumulators: 3 channels, kernels sorted by c_in = (0->1), (0->2), (1->2), (1->0), (2->0), (2->1): channel 0's accumulator is
+    # opened by kernel 3 while those of channels 1 and 2 (opened by kernels 0 and 1) are still waiting for kernels 5 and 2
+    pairs = [(0, 1), (0, 2), (1, 2), (1, 0), (2, 0), (2, 1)]
+    kp3 = [_kp('circle_2d', [1., [1.]], 'poly_quad', [4], a, b) for a, b in pairs]
+    for p in kp3:
+        p['gf_params'], p['h'] = [float(.15 + .1 * rng.random()), float(.03 + .02 * rng.random())], float(.4 + .5 * rng.random())
+    K3, m3 = kernels.get_kernels_and_mapping(copy.deepcopy(kp3), [128, 128], 3, 13, device=DEV)
+    cells3 = (rng.random((1, 4, 3, 128, 128), dtype=np.float32) * .5).astype(np.float32)
+    wp3 = {'R': 13, 'T': 10, 'nb_channels': 3}
+    ufn3, sfn3 = helpers.build_update_fn(K3.shape, m3), statistics.build_compute_stats_fn(wp3, rp)
+    st3, fin3 = runner.run_scan_mem_optimized(None, torch.from_numpy(cells3).to(DEV), K3[None], m3.get_gf_params(DEV)[None],
+                                              m3.get_kernels_weight_per_channel(DEV)[None], T, 10, 13, ufn3, sfn3)
+    plan3 = [p for p in leniax_b200.engine.Plan._cache.values() if p.desc.nb_kernels == 6 and [p.desc.c_out[k] for k in range(6)] == [1, 2, 2, 0, 0, 1]][-1]
+    assert plan3.variant(False) == 'generic'
+    oK3, om3 = lo.get_kernels_and_mapping(copy.deepcopy(kp3), [128, 128], 3, 13)
+    ofin3 = lo.run_scan(cells3[0], oK3, om3.get_gf_params(), om3.get_kernels_weight_per_channel(), np.float32(10.), 10, lo.build_update_fn(om3),
+                        lo.build_compute_stats_fn(wp3, rp), False)[1]
+    e3 = float(np.abs(fin3[0].cpu().numpy() - ofin3).max())
+    record('[g] graph with three live accumulators -> gen_tm: vs oracle after %d steps %.2e' % (10, e3))
+    assert e3 <= 1e-5
