@@ -25,6 +25,8 @@ constexpr int G3_MAX_K = 16;
 constexpr int G3_NPART = PT_FIXED + G3_MAX_C;
 constexpr int G3_PART_N = NT / 2;  // partial sums are added pairwise (one shuffle) before they go to shared memory
 constexpr int G3_TM_COLS = 256;
+constexpr int G3_RING_STRIDE = 16;  // floats per ring row: 12 channel-independent totals + G3_MAX_C channel masses
+static_assert(RING_M00 + G3_MAX_C <= G3_RING_STRIDE, "gen2 ring row too short");
 
 struct Gen2Consts {
     GfConst gf[G3_MAX_K];
@@ -35,8 +37,9 @@ struct Gen2Consts {
 };
 constexpr int G3_OFF_KT = 65536;
 constexpr int G3_OFF_PART = G3_OFF_KT + KREAL_F4 * 16;
-constexpr int G3_OFF_RING = G3_OFF_PART + G3_NPART * G3_PART_N * 4;
-constexpr int G3_OFF_SCRATCH = G3_OFF_RING + RING_ROWS * RING_STRIDE_C * 4;
+constexpr int G3_OFF_KPQ = G3_OFF_PART + G3_NPART * G3_PART_N * 4;  // packed DC|Nyquist column multipliers of the current kernel
+constexpr int G3_OFF_RING = G3_OFF_KPQ + KPQ_F4 * 16;
+constexpr int G3_OFF_SCRATCH = G3_OFF_RING + RING_ROWS * G3_RING_STRIDE * 4;
 constexpr int G3_OFF_TW = G3_OFF_SCRATCH + SCRATCH_BYTES;
 constexpr int G3_OFF_XT = G3_OFF_TW + TW_BYTES;
 constexpr int G3_OFF_GC = G3_OFF_XT + XT_F4 * 16;
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
     float2* W = reinterpret_cast<float2*>(smem);
     float4* KtBuf = reinterpret_cast<float4*>(smem + G3_OFF_KT);
     float* part = reinterpret_cast<float*>(smem + G3_OFF_PART);
+    float4* KpqBuf = reinterpret_cast<float4*>(smem + G3_OFF_KPQ);
     float* ring = reinterpret_cast<float*>(smem + G3_OFF_RING);
     float2* scratch = reinterpret_cast<float2*>(smem + G3_OFF_SCRATCH);
     float4* twtab = reinterpret_cast<float4*>(smem + G3_OFF_TW);
@@ -191,6 +195,10 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
 #pragma unroll 4
             for (int i = 0; i < 8; ++i) cp_async16(KtBuf + i * NT + tid, tab + KTAB_REAL_F4 + i * NT + tid);
         }
+        if (tid < 32) {  // ... and of its packed column: staged by the warp that uses them (no CTA barrier needed)
+#pragma unroll
+            for (int i = 0; i < KPQ_F4 / 32; ++i) cp_async16(KpqBuf + i * 32 + tid, tab + KT_F4 + i * 32 + tid);
+        }
         cp_async_commit();
         const float dt = gc->dt;
         const size_t idx_world = (size_t)sol * P.max_iter * P.n_init + init;
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                             stopped = true;
                             break;
                         }
-                        g3_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * RING_STRIDE_C, ctrl, xt, C, warp, lane);
+                        g3_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * G3_RING_STRIDE, ctrl, xt, C, warp, lane);
                     }
                     phase3_load_fft(tid, R, W);
                     if (k + 1 < K && P.c_in[k + 1] == cin) {  // other kernels read this spectrum too: thread-private slots of the L2 scratch
@@ -242,13 +250,13 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                 }
                 // ---- multiply by kernel k, inverse transform ----
                 const float4* ktab = tab + (size_t)k * KTAB_F4;
+                cp_async_wait_all();  // this thread's multipliers of kernel k are in KtBuf (if staged), warp 0's packed column in KpqBuf
                 if (tid < 32) {
                     phase3_col0_stash(tid, R, scratch);
                     __syncwarp();
-                    phase3_col0_compute(tid, scratch, ktab + KT_F4);
+                    phase3_col0_compute(tid, scratch, KpqBuf);
                     __syncwarp();
                 }
-                cp_async_wait_all();  // this thread's multipliers of kernel k are in KtBuf (if staged)
                 if (gc->kreal[k])
                     g3_mul_real(R, KtBuf, tid);
                 else
@@ -261,13 +269,17 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
 #pragma unroll 4
                         for (int i = 0; i < 8; ++i) cp_async16(KtBuf + i * NT + tid, src + i * NT + tid);
                     }
+                    if (tid < 32) {
+#pragma unroll
+                        for (int i = 0; i < KPQ_F4 / 32; ++i) cp_async16(KpqBuf + i * 32 + tid, tab + (size_t)kn * KTAB_F4 + KT_F4 + i * 32 + tid);
+                    }
                     cp_async_commit();
                 }
                 phase3_ifft_store(tid, R, W);
                 __syncthreads();
                 if (k == 0 && warp == 7 && t > 0 && (t & (RING_ROWS - 1)) == 0) {  // rows t-32 .. t-1 are complete
                     BatchCarry S = ctrl->carry;
-                    stats_finalize_batch<G3_MAX_C, RING_STRIDE_C>(ring, RING_ROWS, lane, C, P.stats, P.channel_mass, plane,
+                    stats_finalize_batch<G3_MAX_C, G3_RING_STRIDE>(ring, RING_ROWS, lane, C, P.stats, P.channel_mass, plane,
                                                                   idx_world + (size_t)S.rows * P.n_init, P.n_init, invR2, invR, inv_dt, S);
                     __syncwarp();
                     if (lane == 0) {
@@ -405,11 +417,11 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
         // the partial sums of the last completed update (step t-1) are not reduced yet; t >= 1 here
         cp_async_wait_all();
         __syncthreads();
-        g3_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * RING_STRIDE_C, ctrl, xt, C, warp, lane);
+        g3_reduce_partials(part, ring + ((t - 1) & (RING_ROWS - 1)) * G3_RING_STRIDE, ctrl, xt, C, warp, lane);
         __syncthreads();
         if (warp == 7) {
             BatchCarry S = ctrl->carry;
-            stats_finalize_batch<G3_MAX_C, RING_STRIDE_C>(ring, t - S.rows, lane, C, P.stats, P.channel_mass, plane,
+            stats_finalize_batch<G3_MAX_C, G3_RING_STRIDE>(ring, t - S.rows, lane, C, P.stats, P.channel_mass, plane,
                                                           idx_world + (size_t)S.rows * P.n_init, P.n_init, invR2, invR, inv_dt, S);
             if (lane == 0) P.n_alive[world] = S.n_alive;
         }

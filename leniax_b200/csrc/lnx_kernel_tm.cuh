@@ -96,6 +96,17 @@ __device__ __forceinline__ void phase3_multiply_tm(Regs& R, uint32_t kt_addr, fl
     }
 }
 
+// real spectrum (every circle_2d kernel: an even function): 32 real multipliers per thread, one packed multiply each
+__device__ __forceinline__ void phase3_multiply_tm_real(Regs& R, uint32_t kt_addr, float (&k)[2][8]) {  // k[0] already in flight
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        tm::wait_ld8(k[c & 1]);
+        if (c + 1 < 4) tm::ld8(kt_addr + 8 * (c + 1), k[(c + 1) & 1]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) R.v[8 * c + e] = pk_mul(R.v[8 * c + e], pk_bc(k[c & 1][e]));
+    }
+}
+
 template <int GF, int SF, bool NP>
 __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -123,6 +134,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
     const TmemStore st{tm::warp_addr(tbase, warp, (warp >> 2) * 64)};
     const uint32_t kt_addr = tm::warp_addr(tbase, warp, 128 + (warp >> 2) * 64);
     int loaded_sol = -1;
+    bool kreal = false;  // the loaded solution's spectrum is real (flag written by the table builder): multipliers in columns [0, 32) of its half
     Regs R;
 
     for (;;) {
@@ -154,8 +166,14 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
         }
         if (sol != loaded_sol) {
             const float4* src = P.table + (size_t)sol * KTAB_F4;
+            kreal = __float_as_int(__ldg(reinterpret_cast<const float*>(src + KTAB_FLAG_F4))) != 0;
+            if (kreal) {
 #pragma unroll 4
-            for (int i = 0; i < 16; ++i) tm::st4(kt_addr + 4 * i, __ldg(src + i * NT + tid));
+                for (int i = 0; i < 8; ++i) tm::st4(kt_addr + 4 * i, __ldg(src + KTAB_REAL_F4 + i * NT + tid));
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) tm::st4(kt_addr + 4 * i, __ldg(src + i * NT + tid));
+            }
             if (tid < KPQ_F4) Kpq[tid] = __ldg(src + KT_F4 + tid);  // made visible by the first barrier of step 0
             loaded_sol = sol;
         }
@@ -182,7 +200,10 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_tm(const RunArgs P) {
             tm::ld8(kt_addr, kbuf[0]);  // first multiplier chunk: lands during the column transforms
             phase3_load_fft(tid, R, W);
             if (tid < 32) phase3_col0_stash(tid, R, scratch);  // warp 0 owns the packed DC|Nyquist column (threads 0..3)
-            phase3_multiply_tm(R, kt_addr, kbuf);              // (their plain products are overwritten by the fetch below)
+            if (kreal)                                         // (the plain products of the packed column are overwritten by the fetch below)
+                phase3_multiply_tm_real(R, kt_addr, kbuf);
+            else
+                phase3_multiply_tm(R, kt_addr, kbuf);
             if (tid < 32) {  // the stash has landed behind the multiply; G' = G Kp + conj(G[-m]) Kq through the scratch
                 __syncwarp();
                 phase3_col0_compute(tid, scratch, Kpq);
