@@ -123,7 +123,37 @@ __device__ __forceinline__ void g3_mul_complex_global(Regs& R, const float4* __r
 
 // GF / SF >= 0: every kernel uses this growth function / the plan this state function (compile-time arithmetic, smaller loop);
 // -1: selected per kernel / per launch at run time.  The loop must stay small: two CTAs stream it through one instruction cache.
-template <int GF, int SF>
+// NP: propagate NaN through the clamps exactly like jnp.maximum / jnp.clip (needed when s == 0 or a zero weight row can occur); the
+// caller passes LNX_RUN_ASSUME_FINITE when it cannot, and the clamps become single min / max / saturate instructions.
+template <int GF, bool NP>
+__device__ __forceinline__ void g3_growth(float2* v, const GfConst& g, float& cnt_p) {
+    int bits = 0;  // potential > eps counts on the integer pipe (at most 64 hits: count_from_bits is exact up to 511)
+    if constexpr (GF == GF_POLY_QUAD4) {  // the arithmetic of growth<GF_POLY_QUAD4, NP, false> on (row p, row p + 64) pairs
+        const float2 nm = pk_bc(-g.m), nk0 = pk_bc(-g.k0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            bits += gt_bits(v[j].x, EPS) + gt_bits(v[j].y, EPS);  // statistics.py:70
+            const float2 t = pk_add(v[j], nm);
+            float2 o = pk_fma(pk_mul(t, t), nk0, pk_bc(1.0f));
+            if constexpr (NP)
+                o = make_float2((o.x < 0.f) ? 0.f : o.x, (o.y < 0.f) ? 0.f : o.y);
+            else
+                o = make_float2(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f));
+            const float2 o2 = pk_mul(o, o);
+            v[j] = pk_fma(pk_mul(o2, o2), pk_bc(2.0f), pk_bc(-1.0f));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            bits += gt_bits(v[j].x, EPS) + gt_bits(v[j].y, EPS);
+            v[j].x = growth<GF, NP, true>(v[j].x, g);
+            v[j].y = growth<GF, NP, true>(v[j].y, g);
+        }
+    }
+    cnt_p += count_from_bits(bits);
+}
+
+template <int GF, int SF, bool NP>
 __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float2* W = reinterpret_cast<float2*>(smem);
@@ -296,7 +326,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                 // to OTHER regions is phase3_ifft_store, behind the P2 -> P3 barrier or the one in front of it below)
                 phase5_ifft(R);
                 if constexpr (GF >= 0)
-                    growth_vec<GF, true, 32>(R.v, gc->gf[k], cnt_p);
+                    g3_growth<GF, NP>(R.v, gc->gf[k], cnt_p);
                 else
                     growth_vec_dyn<true, 32>(P.gf_id[k], R.v, gc->gf[k], cnt_p);
                 if (P.c_out[k] >= 0) {  // field accumulator (tensor memory), core.py:202-242
@@ -316,6 +346,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                         }
                     } else {
                         float buf[2][8];
+                        tm::wait_st();  // the stores of the previous kernels (issued one transform ago: long complete)
                         tm::ld8(aa, buf[0]);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -331,7 +362,6 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                             tm::st8(aa + 8 * i, a);
                         }
                     }
-                    tm::wait_st();
                 }
                 // ---- state update + statistics partials of the channels that are complete now ----
                 for (unsigned um = P.upd_mask[k]; um; um &= um - 1) {
@@ -344,21 +374,20 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                     const uint32_t aa = acc0 + 64 * (slot < 0 ? 0 : slot);
                     float2 sa = make_float2(0.f, 0.f), sg = sa, mx = sa, mx2 = sa, gx = sa;
                     int cnt_a = 0, cnt_g = 0;
-                    // rolled loop over the 8 chunks (the code of this phase is fetched every step by both CTAs of the SM): the L2 loads
-                    // run two chunks ahead of the arithmetic, the tensor-memory load one chunk ahead
-                    float4 a0 = st[0 * NT + tid], a1 = st[1 * NT + tid], b0 = st[2 * NT + tid], b1 = st[3 * NT + tid];
+                    // rolled loop over the 8 chunks, two per iteration (the code of this phase is fetched every step by both CTAs of the
+                    // SM): chunk i + 2 is requested from L2 into the registers of chunk i as soon as that chunk has been consumed, the
+                    // tensor-memory load runs one chunk ahead
+                    float4 sv[2][2] = {{st[0 * NT + tid], st[1 * NT + tid]}, {st[2 * NT + tid], st[3 * NT + tid]}};
                     float fb[2][8];
-                    if (slot >= 0) tm::ld8(aa, fb[0]);
+                    if (slot >= 0) {
+                        tm::wait_st();  // this kernel's accumulator stores
+                        tm::ld8(aa, fb[0]);
+                    }
 #pragma unroll 1
                     for (int i = 0; i < 8; i += 2) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {  // chunk i + h; unrolled by two so that the double buffers keep static names
+                        for (int h = 0; h < 2; ++h) {
                             const int ci = i + h;
-                            float4 c0 = a0, c1 = a1;
-                            if (ci + 2 < 8) {
-                                c0 = st[(2 * ci + 4) * NT + tid];
-                                c1 = st[(2 * ci + 5) * NT + tid];
-                            }
                             float* f = fb[h];
                             if (slot >= 0) {
                                 tm::wait_ld8(f);
@@ -367,7 +396,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) f[e] = 0.f;
                             }
-                            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            const float a[8] = {sv[h][0].x, sv[h][0].y, sv[h][0].z, sv[h][0].w, sv[h][1].x, sv[h][1].y, sv[h][1].z, sv[h][1].w};
                             const float4 x4 = xt[l * XT_STRIDE + ci], q4 = xt[(4 + l) * XT_STRIDE + ci];
                             const float xc[4] = {x4.x, x4.y, x4.z, x4.w}, xc2[4] = {q4.x, q4.y, q4.z, q4.w};
                             float n[8];
@@ -383,9 +412,12 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                                 sg = pk_add(sg, G);
                                 gx = pk_fma(G, pk_bc(xc[e]), gx);
                                 cnt_g += gt_bits(F.x, EPS) + gt_bits(F.y, EPS);
-                                if constexpr (SF >= 0) {
-                                    n[2 * e] = state_update<SF, true>(A.x, F.x, dt);
-                                    n[2 * e + 1] = state_update<SF, true>(A.y, F.y, dt);
+                                if constexpr (SF == SF_V1 && !NP) {  // clip(a + dt f, 0, 1) as one saturating FMA (no NaN possible here)
+                                    n[2 * e] = saturate01(A.x + dt * F.x);
+                                    n[2 * e + 1] = saturate01(A.y + dt * F.y);
+                                } else if constexpr (SF >= 0) {
+                                    n[2 * e] = state_update<SF, NP>(A.x, F.x, dt);
+                                    n[2 * e + 1] = state_update<SF, NP>(A.y, F.y, dt);
                                 } else {
                                     n[2 * e] = state_update_dyn<true>(P.state_fn, A.x, F.x, dt);
                                     n[2 * e + 1] = state_update_dyn<true>(P.state_fn, A.y, F.y, dt);
@@ -393,10 +425,10 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
                             }
                             st[(2 * ci) * NT + tid] = make_float4(n[0], n[1], n[2], n[3]);
                             st[(2 * ci + 1) * NT + tid] = make_float4(n[4], n[5], n[6], n[7]);
-                            a0 = b0;
-                            a1 = b1;
-                            b0 = c0;
-                            b1 = c1;
+                            if (ci + 2 < 8) {
+                                sv[h][0] = st[(2 * ci + 4) * NT + tid];
+                                sv[h][1] = st[(2 * ci + 5) * NT + tid];
+                            }
                         }
                     }
                     g3_part_add(part, PT_M00_C0 + c, tid, sa.x + sa.y);
@@ -446,6 +478,7 @@ __global__ void __launch_bounds__(NT, 2) lnx_world128_gen2(const RunArgs P) {
         }
         __syncthreads();  // world done
     }
+    tm::wait_st();
     __syncthreads();
     if (warp == 0) tm::dealloc(ctrl->tmem_base, G3_TM_COLS);
 }
