@@ -142,7 +142,7 @@ def update_individuals_from_summary(inds, summary: torch.Tensor, keys: List[str]
         ind.set_init_props(ind.rng_key, torch.nonzero(Ns[i] == mx).flatten().tolist())
         ind.fitness = float(fitness_coef * mx)
         if 'phenotype' in ind.qd_config:
-            tmp = ind.get_config()
+            tmp = dict(ind.get_config(read_only=True))
             tmp['behaviours'] = {k: float(s[i, best, 1 + j]) for j, k in enumerate(keys)}
             ind.features = [leniax_utils.get_param(tmp, key) for key in ind.qd_config['phenotype']]
     return inds

@@ -30,20 +30,28 @@ class LeniaIndividual(object):
     def set_init_cells(self, init_cells: str):
         self.qd_config['run_params']['init_cells'] = init_cells
 
-    def get_config(self) -> Dict:
+    def get_config(self, read_only: bool = False) -> Dict:
+        """lenia.py:56-78.  ``read_only=True`` (callers inside this package that only read the result, once per individual and
+        generation): the sub-trees the genotype cannot touch are shared with ``self.qd_config`` instead of deep-copied."""
         if 'genotype' not in self.qd_config:
             return self.qd_config
         genotype = self.get_genotype()
         raw_values = [round(float(v), 8) for v in self.params]  # lenia.py:66
         assert len(raw_values) == len(genotype)
-        return update_config(self.qd_config, get_update_config(genotype, raw_values))
+        return update_config(self.qd_config, get_update_config(genotype, raw_values), share_untouched=read_only)
 
     def get_genotype(self):
         return self.qd_config['genotype']
 
 
-def update_config(config, to_update):  # lenia.py:81-98
-    new_config = copy.deepcopy(config)
+def update_config(config, to_update, share_untouched: bool = False):  # lenia.py:81-98
+    if share_untouched:
+        new_config = dict(config)
+        for key in ('kernels_params', 'world_params'):
+            if key in new_config:
+                new_config[key] = copy.deepcopy(new_config[key])
+    else:
+        new_config = copy.deepcopy(config)
     if 'kernels_params' in to_update:
         for i, kernel in enumerate(to_update['kernels_params']):
             new_config['kernels_params'][i].update(kernel)
