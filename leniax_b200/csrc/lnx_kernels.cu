@@ -209,6 +209,36 @@ static int t64_batch(long long worlds) {
     }();
     return forced > 0 ? forced : (int)worlds;
 }
+// LNX_T64_STREAMS=2: the two halves of the world batch on two streams, so that the SMs could interleave one half's memory-latency-bound
+// lead pass with the other half's issue-bound plane pass.  Measured: 30.9 ms against 30.0 ms on one stream (256 worlds x 64 steps,
+// profiles/r2_e_two_streams.txt) - every launch already fills the machine, the kernels do not overlap.  Off by default, kept for A/B runs.
+static bool t64_two_streams() {
+    static const bool on = [] {
+        const char* e = getenv("LNX_T64_STREAMS");
+        return e && atoi(e) == 2;
+    }();
+    return on;
+}
+// per host thread and device: the second stream of the 64^3 engine and its fork / join events
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream(int dev) {
+    static thread_local SideStream tl[64];
+    SideStream& s = tl[dev];
+    if (!s.stream) {
+        cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            fail(LNX_ERR_CUDA, "64^3 engine: side stream setup failed: %s", cudaGetErrorString(e));
+            s = SideStream();
+            return nullptr;
+        }
+    }
+    return &s;
+}
 static bool is_cube64(const Geom& g) { return g.nd == 3 && g.dims[0] == 64 && g.dims[1] == 64 && g.dims[2] == 64; }
 static size_t tw_bytes(int logn) { return ((size_t)1 << (logn - 1)) * sizeof(float2); }  // shared-memory twiddle table of one pass
 static int log_inner(const Geom& g) { return g.logA2 > g.logA1 ? g.logA2 : g.logA1; }
@@ -682,18 +712,44 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             d.t = max_run_iter - 1;  // the last step's statistics
             pass_d_kernel<<<nw, 128, 0, st>>>(d);
         } else if (line64) {
-            // a step = lead + the fused (inverse planes, update, forward planes of the next step) kernel + pass D (all worlds per launch
-            // unless LNX_T64_BATCH asks for L2-sized batches, see t64_batch)
+            // a step = lead + the fused (inverse planes, update, forward planes of the next step) kernel + pass D, all worlds per launch
+            // (two experiments that did not pay are kept behind environment switches: t64_batch, t64_two_streams)
             const int batch = th::t64_batch(worlds);
-            for (long long w0 = 0; w0 < worlds; w0 += batch) {
-                const unsigned nb = (unsigned)(worlds - w0 < batch ? worlds - w0 : batch);
-                a.world0 = b.world0 = c.world0 = d.world0 = (int)w0;
-                lnx::t64::plane_fwd_kernel<<<dim3(64, 1, nb), 32, 0, st>>>(a);
+            const bool two = batch >= worlds && worlds >= 2 && th::t64_two_streams();
+            th::SideStream* side = two ? th::side_stream(p->device) : nullptr;
+            if (two && !side) return LNX_ERR_CUDA;
+            auto half = [&](cudaStream_t s, long long w0, unsigned nb, int phase, int tt) {
+                PassAArgs a2 = a;
+                PassBArgs b2 = b;
+                PassCArgs c2 = c;
+                PassDArgs d2 = d;
+                a2.world0 = b2.world0 = c2.world0 = d2.world0 = (int)w0;
+                c2.t = d2.t = tt;
+                if (phase == 0) {
+                    lnx::t64::plane_fwd_kernel<<<dim3(64, 1, nb), 32, 0, s>>>(a2);
+                } else {
+                    th::launch_lead64(b2, nb, s);
+                    lnx::t64::plane_inv_kernel<<<dim3(64, 1, nb), 32, 0, s>>>(c2, a2.spec);
+                    pass_d_kernel<<<nb, th::pass_d_threads(g, nb), 0, s>>>(d2);
+                }
+            };
+            if (two) {
+                const long long nA = (worlds + 1) / 2, nB = worlds - nA;
+                LNX_CUDA(cudaEventRecord(side->fork, st));
+                LNX_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+                half(st, 0, (unsigned)nA, 0, 0);
+                half(side->stream, nA, (unsigned)nB, 0, 0);
                 for (int tt = 0; tt < max_run_iter; ++tt) {
-                    c.t = d.t = tt;
-                    th::launch_lead64(b, nb, st);
-                    lnx::t64::plane_inv_kernel<<<dim3(64, 1, nb), 32, 0, st>>>(c, a.spec);
-                    pass_d_kernel<<<nb, th::pass_d_threads(g, nb), 0, st>>>(d);
+                    half(st, 0, (unsigned)nA, 1, tt);
+                    half(side->stream, nA, (unsigned)nB, 1, tt);
+                }
+                LNX_CUDA(cudaEventRecord(side->join, side->stream));
+                LNX_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+            } else {
+                for (long long w0 = 0; w0 < worlds; w0 += batch) {
+                    const unsigned nb = (unsigned)(worlds - w0 < batch ? worlds - w0 : batch);
+                    half(st, w0, nb, 0, 0);
+                    for (int tt = 0; tt < max_run_iter; ++tt) half(st, w0, nb, 1, tt);
                 }
             }
         } else {
