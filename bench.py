@@ -47,6 +47,24 @@ CONFIGS = {
 }
 
 
+def describe_workload(config, total_worlds, sim_steps):
+    """The `config.workload` string: identical in the B200 arm and in the reference arm for the same flags."""
+    what = {'B': f'configs[1]: {total_worlds} Orbium worlds in total, 1c1k 128x128 R=13 T=10',
+            'Bsearch': f'configs[1] in its search form: {total_worlds} perlin soups, Orbium physics, early stop ON (extension; N unchanged)',
+            'C': f'configs[2]: 3 channels 6 kernels 128x128, {total_worlds // 128} solutions x 128 perlin inits in total, per-solution K/gf/W/T',
+            'D': f'configs[3]: {total_worlds} world(s) 2048x2048 (one per GPU: the path does not shard a single world), 1c1k R=52, Orbium x4 at 16 positions',
+            'E': f'configs[4]: {total_worlds} worlds 64^3 in total, 1c1k R=13 spherical-shell kernel, uniform init'}[config]
+    return f'{what}, {sim_steps} sim steps per bench step, 12 statistics + stop criteria every step' + \
+        (', early stop OFF (Orbium at random toroidal shifts: all worlds survive)' if config == 'B' else '')
+
+
+def total_worlds_of(config, scaling, n_gpus, n_override=0):
+    base = n_override or (16 if config == 'C' else CONFIGS[config]['worlds'])
+    if config == 'C':
+        base *= 128
+    return base * (n_gpus if (scaling == 'weak' or config == 'D') else 1)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -205,6 +223,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     c = CONFIGS[args.config]
+    scaling = args.scaling or ('weak' if args.config == 'D' else 'strong')
     vals, sample = [], ''
     per_step_budget = max(5.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
     t_all = time.perf_counter()
@@ -216,10 +235,12 @@ def run_reference(args):
     line = {
         'impl': 'reference', 'metric': c['metric'], 'value': value, 'unit': 'cell-updates/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * (time.perf_counter() - t_all) / (args.warmup + args.steps), 'higher_is_better': True,
-        'scaling': args.scaling or ('weak' if args.config == 'D' else 'strong'), 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f"configs[{c['index']}] ({args.config}); each step = bounded CPU sample of it",
-                   'note': 'the reference is Python on JAX, which is not installable in this image; this arm times the NumPy/scipy.fft '
-                           'restatement of it (oracle/, validated on the reference golden fixtures) on all host cores'},
+        'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': describe_workload(args.config, total_worlds_of(args.config, scaling, args.gpus, args.worlds),
+                                                 args.sim_steps or c['sim_steps'])},
+        'arm': 'the reference is Python on JAX, which is not installable in this image; this arm times the NumPy/scipy.fft restatement of it '
+               '(oracle/, validated on the reference golden fixtures) on all host cores; each step = a bounded CPU sample of the workload '
+               '(worlds are independent and the cost per world-step is constant, so the rate carries over)',
         'cpu_baseline': {'value': value, 'unit': 'cell-updates/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -504,14 +525,7 @@ def run_b200(args):
         return res
 
     def describe(wl, scal):
-        per = f'{wl.local_worlds} world(s) on this GPU' if world > 1 else f'{wl.local_worlds} world(s)'
-        what = {'B': f'configs[1]: {wl.total_worlds} Orbium worlds in total ({per}), 1c1k 128x128 R=13 T=10',
-                'Bsearch': f'configs[1] in its search form: {wl.total_worlds} perlin soups, Orbium physics, early stop ON (extension; N unchanged)',
-                'C': f'configs[2]: 3 channels 6 kernels 128x128, {wl.total_worlds // 128} solutions x 128 perlin inits in total ({per}), per-solution K/gf/W/T',
-                'D': f'configs[3]: one 2048x2048 world per GPU (replicas), 1c1k R=52, Orbium x4 at 16 positions',
-                'E': f'configs[4]: {wl.total_worlds} worlds 64^3 in total ({per}), 1c1k R=13 spherical-shell kernel, uniform init'}[wl.config]
-        return f'{what}, {wl.sim_steps} sim steps per bench step, 12 statistics + stop criteria every step' + \
-            (', early stop OFF (Orbium at random toroidal shifts: all worlds survive)' if wl.config == 'B' else '')
+        return describe_workload(wl.config, wl.total_worlds, wl.sim_steps)
 
     primary = run_config(args.config, scaling, args.steps, args.warmup, with_clocks=True, n_override=args.worlds, sim_steps=args.sim_steps)
     wl = primary['wl']
@@ -522,8 +536,9 @@ def run_b200(args):
         line = {
             'metric': wl.c['metric'], 'value': primary['value'], 'unit': 'cell-updates/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': primary['ms_per_step'], 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {
-                'workload': describe(wl, scaling),
+            'config': {'workload': describe(wl, scaling)},
+            'arm': {
+                'per_gpu': f'{wl.local_worlds} world(s) on rank 0',
                 'parallelism': f'worlds sharded over {world} GPU(s) ({wl.shard_axis} axis, no data-path collective), one NCCL all-gather of the '
                                '[worlds, 12] fitness / behaviour block per step',
                 'cache': 'resident kernels keep state and spectra on-chip (tensor memory + shared memory); inputs are read from HBM once per '

@@ -5,6 +5,9 @@ the legacy run-length format used by the reference's test fixtures.
 """
 import base64
 import gzip
+import io
+import pickle
+import re
 from typing import Dict, List
 
 import numpy as np
@@ -97,7 +100,35 @@ def deprecated_decompress_array(cells_code: str, nb_dims: int) -> torch.Tensor:
     return torch.from_numpy(out)
 
 
-def decompress_array(string_cells: str, nb_dims: int = 0) -> torch.Tensor:  # loader.py:69-102 (best effort chain)
+def compress_array(cells) -> str:  # loader.py:33-66
+    """Cells state -> base64 string of the gzip-compressed int32 encoding (count, values, shape; little endian), the format
+    ``decompress_array_gzip`` reads and ``LeniaIndividual.set_cells`` / ``set_init_cells`` store."""
+    import codecs
+    arr = cells.detach().cpu().numpy() if isinstance(cells, torch.Tensor) else np.asarray(cells)
+    ints = np.round(arr.astype(np.float32) * np.float32(_MAX_VAL)).astype('<i4')
+    shape_bytes = b''.join(int(d).to_bytes(4, 'little') for d in ints.shape)
+    payload = int(ints.size).to_bytes(4, 'little') + ints.tobytes() + shape_bytes
+    return str(codecs.encode(gzip.compress(payload), 'base64'), 'utf-8')
+
+
+class _ArrayUnpickler(pickle.Unpickler):
+    """Unpickles NumPy arrays only: the reference's plain-base64 format is a pickled array (loader.py:132-146) and configuration
+    files are data, not code."""
+    def find_class(self, module, name):
+        if module.split('.')[0] == 'numpy' and name in ('_reconstruct', 'ndarray', 'dtype', 'scalar', '_frombuffer'):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f'{module}.{name} is not allowed in a cells string')
+
+
+def decompress_array_base64(string_cells: str) -> torch.Tensor:  # loader.py:132-146
+    """base64 of a pickled array."""
+    import codecs
+    raw = codecs.decode(string_cells.encode(), 'base64')
+    return torch.as_tensor(np.asarray(_ArrayUnpickler(io.BytesIO(raw)).load(), dtype=np.float32))
+
+
+def decompress_array(string_cells: str, nb_dims: int = 0) -> torch.Tensor:  # loader.py:69-102 (best-effort chain, same order)
+    import binascii
     try:
         return decompress_array_gzip(string_cells)
     except Exception:
@@ -107,10 +138,22 @@ def decompress_array(string_cells: str, nb_dims: int = 0) -> torch.Tensor:  # lo
         try:
             shape = [int(c) for c in parts[1].split(';')]
             vals = [ch2val(parts[0][i:i + 2]) for i in range(0, len(parts[0]), 2)]
-            return (torch.tensor(vals, dtype=torch.int32).reshape(shape) / _MAX_VAL).to(torch.float32)
+            ints = torch.tensor(vals, dtype=torch.int32).reshape(shape)
+            return ints.to(torch.float32) / torch.tensor(float(_MAX_VAL))
         except Exception:
             pass
-    return deprecated_decompress_array(string_cells, nb_dims)
+    try:  # an .npz archive stored as a latin1 string, uint8 cells under 'x'
+        return torch.from_numpy((np.load(io.BytesIO(string_cells.encode('latin1')))['x'] / 255.).astype(np.float32))
+    except Exception:
+        pass
+    try:
+        return decompress_array_base64(string_cells)
+    except (binascii.Error, pickle.UnpicklingError, ValueError, EOFError, IndexError, KeyError):
+        pass
+    # the legacy run-length format (loader.py:287-350): digits, '.', 'b', 'o', 'A'..'X', prefixes 'p'..'y' / '@', delimiters $ % #, final '!'
+    if nb_dims >= 1 and re.fullmatch(r'[0-9.boA-Xp-y@$%#]*!?', string_cells.strip()):
+        return deprecated_decompress_array(string_cells.strip(), nb_dims)
+    raise ValueError(f'no decoder of leniax.loader matches this cells string ({len(string_cells)} characters)')
 
 
 def load_raw_cells(config: Dict, use_init_cells: bool = True) -> torch.Tensor:  # loader.py:206-240

@@ -115,7 +115,7 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     dt = (1. / T.reshape(n_sols)).contiguous()  # runner.py:307
     if host_cells is not None:
         n_first = 2 * torch.cuda.get_device_properties(dev).multi_processor_count  # one full wave of CTAs of the fused kernel
-        if n_sols == 1 and not keep_trajectory and n_init >= 4 * n_first:
+        if n_sols == 1 and not keep_trajectory and n_init >= 4 * n_first and host_cells.is_pinned():  # (pageable copies block the host: no overlap)
             return _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev)
         cells0 = host_cells.to(dev, non_blocking=True)
     return plan.run_scan(cells0.contiguous(), K, gfp, wts, dt, max_run_iter, keep_trajectory=keep_trajectory, flags=flags)
@@ -125,7 +125,7 @@ _COPY_STREAMS: Dict[str, torch.cuda.Stream] = {}
 
 
 def _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev):
-    """Initial states given in host memory (one solution, many initialisations): the first wave of worlds is uploaded and
+    """Initial states given in PINNED host memory (one solution, many initialisations): the first wave of worlds is uploaded and
     started at once, the rest of the batch is uploaded on a copy stream while that wave computes, then runs as a second
     launch.  Worlds are independent, so the two launches give bit-identical rows to a single one."""
     main = torch.cuda.current_stream(dev)

@@ -263,3 +263,30 @@ def test_kernel_cache_key_distinguishes_numpy_and_tensor_scalars():
     assert kernels._kernel_cache_key(raw, [128, 128], 1, 13., True, 'cpu') is None  # arrays are not cached
     nested = [dict(k_slug='circle_2d', k_params=[1., [1., np.ones(2)]], kf_slug='poly_quad', kf_params=[4], c_in=0)]
     assert kernels._kernel_cache_key(nested, [128, 128], 1, 13., True, 'cpu') is None  # ... at any nesting level
+
+
+def test_cells_codec_round_trip_and_clear_error():
+    """compress_array / the npz and plain-base64 decoders of leniax/loader.py:33-146 were missing."""
+    import base64
+    import io
+
+    import torch
+    from leniax_b200 import loader
+    rng = np.random.default_rng(0)
+    cells = loader.make_array_compressible(torch.from_numpy(rng.random((1, 9, 7), dtype=np.float32)))
+    s = loader.compress_array(cells)
+    assert isinstance(s, str) and torch.equal(loader.decompress_array(s, 3), cells)
+    assert np.array_equal(lo.decompress_array_gzip(s), cells.numpy())  # the oracle's decoder reads what we write
+    # plain base64 = a pickled array (loader.py:132-146); anything but NumPy reconstruction is refused
+    import pickle
+    assert torch.equal(loader.decompress_array(base64.b64encode(pickle.dumps(cells.numpy())).decode(), 3), cells)
+    evil = base64.b64encode(pickle.dumps(print)).decode()
+    with pytest.raises(ValueError, match='no decoder'):
+        loader.decompress_array(evil, 3)
+    # npz archive as a latin1 string
+    buf = io.BytesIO()
+    np.savez(buf, x=(rng.random((2, 5, 5)) * 255).astype(np.uint8))
+    got = loader.decompress_array(buf.getvalue().decode('latin1'), 3)
+    assert got.shape == (2, 5, 5) and float(got.max()) <= 1.
+    with pytest.raises(ValueError, match='no decoder'):
+        loader.decompress_array('~~~ not a cells string ~~~', 3)
