@@ -124,6 +124,8 @@ static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
 }
 // lead kernel of the 64^3 engine: 6 CTAs of 64 threads per SM (166 registers, no spills; 8 CTAs / 128 registers measured slower)
 static void launch_lead64(const PassBArgs& b, unsigned images, cudaStream_t st) {
+    // (round 2: 32 / 96 / 192 threads per CTA measured 38.6 / 33.8 / 42.1 ms against 32.3 ms for 64 on the same box: the CTA width,
+    // i.e. the contiguous bytes a CTA touches per plane, is not what holds the pass at 65 % of the HBM rate; profiles/r2_e_lead_tpb.txt)
     const dim3 grid(lnx::t64::COLS / lnx::t64::LEAD_TPB, b.C, images);
     lnx::t64::lead_kernel<6><<<grid, lnx::t64::LEAD_TPB, 0, st>>>(b);
 }

@@ -339,9 +339,9 @@ __global__ void __launch_bounds__(32) plane_fwd_kernel(PassAArgs P) {
 }
 
 // grid (33, C, worlds), 64 threads: thread = one spectral column
-template <int MINB>
-__global__ void __launch_bounds__(LEAD_TPB, MINB) lead_kernel(PassBArgs P) {
-    const int col = blockIdx.x * LEAD_TPB + threadIdx.x, c = blockIdx.y, w = blockIdx.z + P.world0;
+template <int MINB, int TPB = LEAD_TPB>
+__global__ void __launch_bounds__(TPB, MINB) lead_kernel(PassBArgs P) {
+    const int col = blockIdx.x * TPB + threadIdx.x, c = blockIdx.y, w = blockIdx.z + P.world0;
     const float2* src = P.spec + ((size_t)w * P.C + c) * ((size_t)N * COLS) + col;
     float2 v[64];
     if (P.fwd_out) {
