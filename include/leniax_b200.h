@@ -244,6 +244,13 @@ int lnx_init_perlin(int32_t n_worlds, int32_t H, int32_t W, int32_t res0, int32_
 int lnx_init_perlin_seeded(int32_t n_seeds, const uint64_t* seeds, int32_t nb_init, int32_t H, int32_t W, int32_t res0, int32_t res1,
                            const float* scaling, float* out, void* stream);
 
+/* Host-only (no GPU needed): the channel-update order and tensor-memory slots lnx_world128_gen2 would use for this description
+ * (c_in sorted, c_out declared).  Returns 1 and fills acc_slot[K] (slot kernel k adds into), acc_first[K] (1: first touch of the slot in
+ * a step), upd_mask[K] (bit c: channel c is updated after kernel k), chan_slot[C] (slot holding channel c's field at its update, -1: no
+ * kernel feeds it); 0 when the kernel graph needs more than two live accumulators or is too large (the scan then runs one world per
+ * SM); negative lnx_status on bad arguments.  For tests and for callers that want to know which kernel a configuration will take. */
+int lnx_gen2_schedule(const lnx_desc* desc, int32_t* acc_slot, int32_t* acc_first, int32_t* upd_mask, int32_t* chan_slot);
+
 /* Name of the CUDA kernel family lnx_run_scan would launch for this plan/arguments ("fused", "generic2", "generic", "tiled"), for tests. */
 const char* lnx_run_scan_variant(const lnx_plan* plan, int32_t with_trajectory);
 

@@ -93,6 +93,7 @@ EXPORTS = {
     'lnx_init_uniform': (ctypes.c_int, [c_uint64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     'lnx_init_perlin': (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'lnx_init_perlin_seeded': (ctypes.c_int, [c_int32, POINTER(c_uint64), c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    'lnx_gen2_schedule': (ctypes.c_int, [POINTER(LnxDesc)] + [POINTER(c_int32)] * 4),
     'lnx_update_conv': (ctypes.c_int, [POINTER(LnxDesc), c_int32, c_int32, c_int32] + [c_void_p] * 4 + [c_float] + [c_void_p] * 4),
 }
 

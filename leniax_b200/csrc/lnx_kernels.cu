@@ -832,6 +832,22 @@ static bool use_fused(const lnx_plan* p, bool trajectory) {
     return tm_kernel_exists(d.gf_id[0], d.state_fn);
 }
 
+int lnx_gen2_schedule(const lnx_desc* d, int32_t* acc_slot, int32_t* acc_first, int32_t* upd_mask, int32_t* chan_slot) {
+    if (!d || !acc_slot || !acc_first || !upd_mask || !chan_slot) return fail(LNX_ERR_INVALID, "lnx_gen2_schedule: null argument");
+    if (d->nb_channels < 1 || d->nb_channels > MAX_C || d->nb_kernels < 1 || d->nb_kernels > MAX_K)
+        return fail(LNX_ERR_INVALID, "lnx_gen2_schedule: C must be in [1, %d] and K in [1, %d]", MAX_C, MAX_K);
+    RunArgs a;
+    memset(&a, 0, sizeof(a));
+    if (!lnx::host::gen2_plan(*d, a)) return 0;
+    for (int k = 0; k < d->nb_kernels; ++k) {
+        acc_slot[k] = a.acc_slot[k];
+        acc_first[k] = (a.acc_first >> k) & 1u;
+        upd_mask[k] = a.upd_mask[k];
+    }
+    for (int c = 0; c < d->nb_channels; ++c) chan_slot[c] = a.chan_slot[c];
+    return 1;
+}
+
 const char* lnx_run_scan_variant(const lnx_plan* p, int32_t with_trajectory) {
     if (!p) return "";
     if (p->tiled) return "tiled";

@@ -28,12 +28,16 @@ def _check_fns(update_fn, compute_stats_fn):
         raise NotImplementedError('compute_stats_fn must come from leniax_b200.statistics.build_compute_stats_fn')
 
 
-_PARAM_SUMMARY_CACHE = weakref.WeakKeyDictionary()
+_PARAM_SUMMARY_CACHE: Dict[int, tuple] = {}  # id(base tensor of the weights) -> (weakref to it, key, result)
+
+
+def _base_of(t: torch.Tensor) -> torch.Tensor:
+    return t._base if t._base is not None else t
 
 
 def _param_summary(gf_params: torch.Tensor, weights: torch.Tensor, average: bool) -> Tuple[bool, Tuple[int, ...]]:
     """What the launch needs to know about the device-side parameters, from ONE device reduction and ONE host sync (cached per
-    tensor object and version, so a loop over the same parameters syncs once):
+    tensor OBJECT and version — views are looked up through their base — so a loop over the same parameters syncs once):
 
     * ``finite``: NaN cannot be born in the step — no growth width ``s == 0``, no all-zero weight row, nothing non-finite (SURVEY §7);
     * ``c_out[k]``: the single channel whose weight is non-zero in column ``k`` for some solution (``kernels.py:110-111`` writes
@@ -41,10 +45,12 @@ def _param_summary(gf_params: torch.Tensor, weights: torch.Tensor, average: bool
       channels (hand-made weights): the engine then uses the weights tensor as given.
 
     ``gf_params [S, K, 2]``, ``weights [S, C, K]``."""
-    hit = _PARAM_SUMMARY_CACHE.get(weights)
-    key = (weights._version, id(gf_params), gf_params._version, bool(average))
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    wb, gb = _base_of(weights), _base_of(gf_params)
+    key = (wb._version, tuple(weights.shape), weights.storage_offset(), id(gb), gb._version, tuple(gf_params.shape),
+           gf_params.storage_offset(), bool(average))
+    hit = _PARAM_SUMMARY_CACHE.get(id(wb))
+    if hit is not None and hit[0]() is wb and hit[1]() is gb and hit[2] == key:
+        return hit[3]
     C, K = weights.shape[-2], weights.shape[-1]
     bad = (~torch.isfinite(gf_params).all()) | (gf_params[..., 1] == 0).any() | (~torch.isfinite(weights).all())
     if average:
@@ -57,7 +63,8 @@ def _param_summary(gf_params: torch.Tensor, weights: torch.Tensor, average: bool
         rows = [c for c in range(C) if packed[1 + c * K + k]]
         c_out.append(rows[0] if len(rows) == 1 else (_lib.LNX_COUT_NONE if not rows else None))
     res = (finite, tuple(_lib.LNX_COUT_ANY for _ in range(K)) if any(v is None for v in c_out) else tuple(c_out))
-    _PARAM_SUMMARY_CACHE[weights] = (key, res)
+    wid = id(wb)
+    _PARAM_SUMMARY_CACHE[wid] = (weakref.ref(wb, lambda _r, wid=wid: _PARAM_SUMMARY_CACHE.pop(wid, None)), weakref.ref(gb), key, res)
     return res
 
 

@@ -290,3 +290,82 @@ def test_cells_codec_round_trip_and_clear_error():
     assert got.shape == (2, 5, 5) and float(got.max()) <= 1.
     with pytest.raises(ValueError, match='no decoder'):
         loader.decompress_array('~~~ not a cells string ~~~', 3)
+
+
+def _schedule(c_in, c_out, C):
+    lib = _lib.load_library()
+    K = len(c_in)
+    d = _lib.LnxDesc(nb_dims=2, nb_channels=C, nb_kernels=K, nb_slots=K, R=13., stats_dt=.1)
+    d.dims[0] = d.dims[1] = 128
+    for k in range(K):
+        d.c_in[k], d.c_out[k], d.slot[k] = c_in[k], c_out[k], k
+    arr = lambda n: (ctypes.c_int32 * n)()  # noqa: E731
+    slot, first, upd, chan = arr(K), arr(K), arr(K), arr(C)
+    rc = lib.lnx_gen2_schedule(ctypes.byref(d), slot, first, upd, chan)
+    return rc, list(slot), list(first), list(upd), list(chan)
+
+
+def test_gen2_schedule_orders_channel_updates_for_two_accumulators():
+    """Host side of lnx_world128_gen2 (csrc/lnx_kernel_gen2.cuh: gen2_schedule): a channel is updated after its last kernel has been added
+    AND its own spectrum has been taken; never more than two accumulators are live; graphs that need three are refused."""
+    # conf/config_qd_cmame_3c6k.yaml: kernels sorted by c_in (kernels.py:90)
+    rc, slot, first, upd, chan = _schedule([0, 0, 1, 1, 2, 2], [0, 1, 1, 2, 2, 0], 3)
+    assert rc == 1
+    assert first == [1, 1, 0, 1, 0, 0]                      # kernels 0, 1, 3 open the accumulators of channels 0, 1, 2
+    assert upd == [0, 0, 0b010, 0, 0b100, 0b001]            # channel 1 after kernel 2, channel 2 after kernel 4, channel 0 after kernel 5
+    assert slot[0] == slot[5] and slot[1] == slot[2] and slot[3] == slot[4] and slot[0] != slot[1] and slot[3] == slot[1]
+    assert chan == [slot[0], slot[1], slot[3]]
+    # generic invariants on random graphs: every channel updated exactly once, at or after its last writer and its first reader; a slot is
+    # never shared by two live channels; refused graphs really need three
+    rng = np.random.default_rng(0)
+    accepted = refused = 0
+    for _ in range(300):
+        C, K = int(rng.integers(1, 5)), int(rng.integers(1, 9))
+        c_in = sorted(int(v) for v in rng.integers(0, C, K))
+        c_out = [int(v) if rng.random() > .1 else _lib.LNX_COUT_NONE for v in rng.integers(0, C, K)]
+        rc, slot, first, upd, chan = _schedule(c_in, c_out, C)
+        first_in = {c: min((k for k in range(K) if c_in[k] == c), default=-1) for c in range(C)}
+        last_out = {c: max((k for k in range(K) if c_out[k] == c), default=-1) for c in range(C)}
+        first_out = {c: min((k for k in range(K) if c_out[k] == c), default=K) for c in range(C)}
+        want = {c: max(last_out[c], first_in[c]) if max(last_out[c], first_in[c]) >= 0 else K - 1 for c in range(C)}
+        live = lambda k: [c for c in range(C) if first_out[c] <= k <= want[c]]  # noqa: E731  accumulators alive during kernel k
+        need = max(len(live(k)) for k in range(K))
+        if rc == 0:
+            refused += 1
+            assert need > 2, (c_in, c_out)
+            continue
+        accepted += 1
+        assert need <= 2
+        updated = [c for k in range(K) for c in range(C) if upd[k] >> c & 1]
+        assert sorted(updated) == list(range(C))
+        for c in range(C):
+            assert upd[want[c]] >> c & 1
+            assert (chan[c] >= 0) == (last_out[c] >= 0)
+        for k in range(K):
+            cs = live(k)
+            assert len({chan[c] for c in cs}) == len(cs)  # distinct slots while alive together
+            if c_out[k] >= 0:
+                assert slot[k] == chan[c_out[k]] and first[k] == (1 if k == first_out[c_out[k]] else 0)
+    assert accepted > 50 and refused > 20
+    # undeclared weight pattern -> not eligible
+    assert _schedule([0, 0], [_lib.LNX_COUT_ANY] * 2, 1)[0] == 0
+
+
+def test_param_summary_one_sync_flags_and_pattern():
+    import torch
+    from leniax_b200 import runner
+    gf = torch.tensor([[[.15, .015], [.2, .03], [.3, .04]]])
+    w = torch.tensor([[[.5, 0., .7], [0., 1., 0.]]])
+    finite, c_out = runner._param_summary(gf, w, True)
+    assert finite and c_out == (0, 1, 0)
+    assert runner._param_summary(gf, w, True) == (finite, c_out)                      # cached for the same tensors
+    w2 = w.clone()
+    w2[0, 1, 0] = .2                                                                   # kernel 0 feeds two channels: pattern undeclared
+    assert runner._param_summary(gf, w2, True)[1] == (_lib.LNX_COUT_ANY, ) * 3
+    w3 = torch.tensor([[[.5, 0., 0.], [0., 1., 0.]]])                                  # kernel 2 feeds nothing
+    assert runner._param_summary(gf, w3, True) == (True, (0, 1, _lib.LNX_COUT_NONE))
+    assert runner._param_summary(torch.tensor([[[.15, 0.], [.2, .03], [.3, .04]]]), w, True)[0] is False   # s == 0
+    assert runner._param_summary(gf, torch.tensor([[[.5, 0., .7], [0., 0., 0.]]]), True)[0] is False        # zero weight row (mean)
+    assert runner._param_summary(gf, torch.tensor([[[.5, 0., .7], [0., 0., 0.]]]), False)[0] is True        # ... fine for weighted_sum
+    w.mul_(2.)                                                                         # in-place change invalidates the cache entry
+    assert runner._param_summary(gf, w, True) == (True, (0, 1, 0))
