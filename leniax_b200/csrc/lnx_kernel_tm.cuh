@@ -7,8 +7,8 @@ namespace lnx {
 // ---------------------------------------------------------------------------------------------------------------------
 // fused kernel, TMEM variant (default): C = K = 1, two worlds (CTAs) per SM
 //
-// Same five phases as lnx_world128_fused, but the two thread-private arrays (state, kernel multipliers) live in tensor
-// memory instead of shared memory (lnx_tmem.cuh), the new state stays in registers from the cell phase to phase 1 of the
+// The five phases of lnx_world128.cuh with the two thread-private arrays (state, kernel multipliers) in tensor memory
+// instead of shared memory (lnx_tmem.cuh; round 1 started with them in shared memory: one world per SM), the new state stays in registers from the cell phase to phase 1 of the
 // next step, and there is no statistics warp: the partial sums of step t are reduced by warps 1..7 at the start of phase 3
 // of step t+1 (behind the barrier that is there anyway), warp 1 advances the shift carry, and warp 7 turns 32 steps of
 // totals into statistics rows at once (lnx_stats_batch.cuh).  256 threads x 128 registers + 83 KB of shared memory per
