@@ -79,7 +79,7 @@ def run_scan_mem_optimized_sharded(rng_key, cells0, K, gf_params, kernels_weight
     differ), ``'inits'``: only this rank's slice of the initialisation axis of every solution — no rank ever holds the whole batch.
     ``local_run`` defaults to ``runner.run_scan_mem_optimized`` (tests inject a CPU stand-in)."""
     if local_run is None:
-        local_run = lambda *a: leniax_runner.run_scan_mem_optimized(*a, early_stop=early_stop)  # noqa: E731
+        local_run = lambda *a: leniax_runner.run_scan_mem_optimized(*a, early_stop=early_stop, return_final_cells=False)  # noqa: E731
     on = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if on else 0
     world = dist.get_world_size(group) if on else 1

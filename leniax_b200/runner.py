@@ -75,7 +75,7 @@ FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the t
 
 
 def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, stats_fn: ComputeStatsFn, *, batched: bool,
-          keep_trajectory: bool, early_stop: bool = False):
+          keep_trajectory: bool, early_stop: bool = False, want_final_cells: bool = True):
     assert max_run_iter > 0, f"max_run_iter must be positive, value given: {max_run_iter}"  # runner.py:51
     dev = engine.require_cuda_device(cells0.device if isinstance(cells0, torch.Tensor) and cells0.is_cuda else None)
     f32 = torch.float32
@@ -123,15 +123,16 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
     if host_cells is not None:
         n_first = 2 * torch.cuda.get_device_properties(dev).multi_processor_count  # one full wave of CTAs of the fused kernel
         if n_sols == 1 and not keep_trajectory and n_init >= 4 * n_first and host_cells.is_pinned():  # (pageable copies block the host: no overlap)
-            return _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev)
+            return _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev, want_final_cells)
         cells0 = host_cells.to(dev, non_blocking=True)
-    return plan.run_scan(cells0.contiguous(), K, gfp, wts, dt, max_run_iter, keep_trajectory=keep_trajectory, flags=flags)
+    return plan.run_scan(cells0.contiguous(), K, gfp, wts, dt, max_run_iter, keep_trajectory=keep_trajectory, flags=flags,
+                         want_final_cells=want_final_cells)
 
 
 _COPY_STREAMS: Dict[str, torch.cuda.Stream] = {}
 
 
-def _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev):
+def _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_iter, flags, dev, want_final_cells=True):
     """Initial states given in PINNED host memory (one solution, many initialisations): the first wave of worlds is uploaded and
     started at once, the rest of the batch is uploaded on a copy stream while that wave computes, then runs as a second
     launch.  Worlds are independent, so the two launches give bit-identical rows to a single one."""
@@ -144,15 +145,16 @@ def _scan_pipelined_upload(plan, host_cells, n_first, K, gfp, wts, dt, max_run_i
             rest = host_cells[:, n_first:].to(dev, non_blocking=True)
             uploaded = torch.cuda.Event()
             uploaded.record(side)
-        r1 = plan.run_scan(first, K, gfp, wts, dt, max_run_iter, keep_trajectory=False, flags=flags)
+        r1 = plan.run_scan(first, K, gfp, wts, dt, max_run_iter, keep_trajectory=False, flags=flags, want_final_cells=want_final_cells)
         main.wait_event(uploaded)
         rest.record_stream(main)
-        r2 = plan.run_scan(rest, K, gfp, wts, dt, max_run_iter, keep_trajectory=False, flags=flags)
+        r2 = plan.run_scan(rest, K, gfp, wts, dt, max_run_iter, keep_trajectory=False, flags=flags, want_final_cells=want_final_cells)
     stats = {}
     for k, v in r1['stats'].items():
         axis = 2 if k == 'channel_mass' else (1 if k == 'N' else 2)  # [S, T, I, C] / [S, I] / [S, T, I]
         stats[k] = torch.cat([v, r2['stats'][k]], dim=axis)
-    return {'stats': stats, 'final_cells': torch.cat([r1['final_cells'], r2['final_cells']], dim=1), 'cells': None, 'field': None,
+    final = torch.cat([r1['final_cells'], r2['final_cells']], dim=1) if want_final_cells else None
+    return {'stats': stats, 'final_cells': final, 'cells': None, 'field': None,
             'potential': None}
 
 
@@ -214,18 +216,19 @@ def run_scan(rng_key, cells0, K, gf_params, kernels_weight_per_channel, T, max_r
 
 
 def run_scan_mem_optimized(rng_key, cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter: int, R: float,
-                           update_fn, compute_stats_fn, early_stop: bool = False
+                           update_fn, compute_stats_fn, early_stop: bool = False, return_final_cells: bool = True
                            ) -> Tuple[Dict[str, torch.Tensor], torch.Tensor]:
     """Simulate ``N_sols`` configurations x ``N_init`` initialisations (runner.py:167-215).
 
     ``cells0 [N_sols, N_init, C, H, W]``, ``K [N_sols, 1, C, max_k, H, W]``, ``gf_params [N_sols, K, 2]``,
     ``kernels_weight_per_channel [N_sols, C, K]``, ``T [N_sols]``.  Returns ``(stats {k: [N_sols, T, N_init]}, final_cells)``.
     ``early_stop=True`` (extension) lets a world stop once its stop criteria fired and 128 rows exist; the rows the QD
-    consumer reads (qd.py:181-185) are unaffected, later rows are zero.
+    consumer reads (qd.py:181-185) are unaffected, later rows are zero.  ``return_final_cells=False`` (extension; the QD evaluation,
+    which drops them, qd.py:63-66): the final states are neither allocated nor written, ``None`` is returned in their place.
     """
     _check_fns(update_fn, compute_stats_fn)
     res = _scan(cells0, K, gf_params, kernels_weight_per_channel, T, max_run_iter, update_fn, compute_stats_fn, batched=True,
-                keep_trajectory=False, early_stop=early_stop)
+                keep_trajectory=False, early_stop=early_stop, want_final_cells=return_final_cells)
     return res['stats'], res['final_cells']
 
 

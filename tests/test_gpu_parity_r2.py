@@ -708,3 +708,28 @@ def test_gen2_complex_spectrum_and_fallbacks(golden_dir):
     e3 = float(np.abs(fin3[0].cpu().numpy() - ofin3).max())
     record('[g] graph with three live accumulators -> gen_tm: vs oracle after %d steps %.2e' % (10, e3))
     assert e3 <= 1e-5
+
+
+def test_scan_without_final_cells_gives_identical_statistics(golden_dir):
+    """return_final_cells=False (what the QD evaluation and the sharded entry point use): same rows, no final-state buffer — in the fused
+    kernel, in gen2 and in a tiled engine (which then keeps its working state in the workspace)."""
+    cfg, _ = _setup(golden_dir, 'orbium-test')
+    cells, K, mapping, ufn, sfn = _engine_parts(cfg)
+    worlds = torch.stack([torch.roll(cells[0], (5 * i, 9 * i), dims=(1, 2)) for i in range(4)])[None]
+    args = (worlds, K[None], mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None], torch.tensor([10.], device=DEV))
+    a, fa = runner.run_scan_mem_optimized(None, *args, 40, 13, ufn, sfn)
+    b, fb = runner.run_scan_mem_optimized(None, *args, 40, 13, ufn, sfn, return_final_cells=False)
+    assert fb is None and fa is not None and all(torch.equal(a[k], b[k]) for k in a)
+    kps, args3, ufn3 = _c3_solutions(2, 3, seed=4)
+    sfn3 = statistics.build_compute_stats_fn({'R': 13, 'T': 10, 'nb_channels': 3}, {'world_size': [128, 128]})
+    a, _ = runner.run_scan_mem_optimized(None, *args3, 20, 13, ufn3, sfn3)
+    b, fb = runner.run_scan_mem_optimized(None, *args3, 20, 13, ufn3, sfn3, return_final_cells=False)
+    assert fb is None and all(torch.equal(a[k], b[k]) for k in a)
+    K2, m2 = kernels.get_kernels_and_mapping([_kp('circle_2d', [1., [1.]], 'poly_quad', [4])], [256, 256], 1, 13, device=DEV)
+    ufn2 = helpers.build_update_fn(K2.shape, m2)
+    sfn2 = statistics.build_compute_stats_fn({'R': 13, 'T': 10}, {'world_size': [256, 256]})
+    c2 = torch.rand((1, 2, 1, 256, 256), device=DEV) * .5
+    args2 = (c2, K2[None], m2.get_gf_params(DEV)[None], m2.get_kernels_weight_per_channel(DEV)[None], torch.tensor([10.], device=DEV))
+    a, _ = runner.run_scan_mem_optimized(None, *args2, 12, 13, ufn2, sfn2)
+    b, fb = runner.run_scan_mem_optimized(None, *args2, 12, 13, ufn2, sfn2, return_final_cells=False)
+    assert fb is None and all(torch.equal(a[k], b[k]) for k in a)
