@@ -256,40 +256,36 @@ constexpr size_t SMEM_LIMIT = 220 * 1024;  // dynamic part; pass C also has ~1 K
 
 static float2* g_tw2k[64] = {nullptr};  // (cos, sin)(2 pi i / 2048), i < 2048: twiddles of the four-step engine (lnx_tiled2k.cuh)
 static float2* g_tw[64] = {nullptr};  // library-owned twiddle master table per device: (cos, sin)(2 pi k / NMAX)
+static std::mutex g_tiled_init_mu;
 static int ensure_tiled_init(int dev) {
+    std::lock_guard<std::mutex> lk(g_tiled_init_mu);  // plans may be created from several host threads
     if (g_tw[dev]) return LNX_OK;
-    static float2 host[NMAX / 2];
+    std::vector<float2> host(NMAX / 2), host2k(2048);
     for (int k = 0; k < NMAX / 2; ++k) {
         const double a = 2.0 * 3.14159265358979323846 * k / NMAX;
         host[k] = make_float2((float)cos(a), (float)sin(a));
     }
-    float2* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, sizeof(host));
-    if (e == cudaSuccess) e = cudaMemcpy(d, host, sizeof(host), cudaMemcpyHostToDevice);
+    for (int k = 0; k < 2048; ++k) {
+        const double a = 2.0 * 3.14159265358979323846 * k / 2048;
+        host2k[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2 *d = nullptr, *d2 = nullptr;
+    cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpy(d, host.data(), host.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&d2, host2k.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpy(d2, host2k.data(), host2k.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lnx::t2k::rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lnx::t2k::ROWS_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lnx::t2k::rows_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lnx::t2k::ROWS_SMEM);
     if (e != cudaSuccess) {
+        if (d) cudaFree(d);
+        if (d2) cudaFree(d2);
         fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(e));
         return -1;
     }
-    {
-        static float2 host2k[2048];
-        for (int k = 0; k < 2048; ++k) {
-            const double a = 2.0 * 3.14159265358979323846 * k / 2048;
-            host2k[k] = make_float2((float)cos(a), (float)sin(a));
-        }
-        float2* d2 = nullptr;
-        e = cudaMalloc(&d2, sizeof(host2k));
-        if (e == cudaSuccess) e = cudaMemcpy(d2, host2k, sizeof(host2k), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) {
-            fail(LNX_ERR_CUDA, "tiled engine setup failed: %s", cudaGetErrorString(e));
-            return -1;
-        }
-        g_tw2k[dev] = d2;
-    }
+    g_tw2k[dev] = d2;
     g_tw[dev] = d;
     return LNX_OK;
 }
