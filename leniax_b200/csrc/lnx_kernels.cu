@@ -15,6 +15,7 @@
 #include "lnx_resident_common.cuh"
 #include "lnx_tiled.cuh"
 #include "lnx_tiled64.cuh"
+#include "lnx_tiled64h.cuh"
 #include "lnx_tiled2k.cuh"
 #include "lnx_conv.cuh"
 
@@ -713,6 +714,7 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             // a step = lead + the fused (inverse planes, update, forward planes of the next step) kernel + pass D, all worlds per launch
             // (two experiments that did not pay are kept behind environment switches: t64_batch, t64_two_streams)
             const int batch = th::t64_batch(worlds);
+            const bool line64_round1 = (run_flags & LNX_RUN_T64_LINE) != 0;
             const bool two = batch >= worlds && worlds >= 2 && th::t64_two_streams();
             th::SideStream* side = two ? th::side_stream(p->device) : nullptr;
             if (two && !side) return LNX_ERR_CUDA;
@@ -725,9 +727,12 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
                 c2.t = d2.t = tt;
                 if (phase == 0) {
                     lnx::t64::plane_fwd_kernel<<<dim3(64, 1, nb), 32, 0, s>>>(a2);
-                } else {
+                } else if (line64_round1) {
                     th::launch_lead64(b2, nb, s);
                     lnx::t64::plane_inv_kernel<<<dim3(64, 1, nb), 32, 0, s>>>(c2, a2.spec);
+                    pass_d_kernel<<<nb, th::pass_d_threads(g, nb), 0, s>>>(d2);
+                } else {  // half-line kernels (lnx_tiled64h.cuh): two threads per 64-point line, 20 warps per SM
+                    lnx::t64h::launch_step(b2, c2, a2.spec, nb, (run_flags & LNX_RUN_ASSUME_FINITE) != 0, s);
                     pass_d_kernel<<<nb, th::pass_d_threads(g, nb), 0, s>>>(d2);
                 }
             };

@@ -197,6 +197,7 @@ def emul64():
     lib = ctypes.CDLL(EMUL64)
     f, i, v = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
     lib.lnx_t64_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v, v]
+    lib.lnx_t64h_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v, v, i]
     return lib
 
 
@@ -217,10 +218,13 @@ def test_t64_rfftn_matches_numpy(emul64):
     assert np.abs(spec - ref).max() < 2e-7 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize('gf_slug,gf_id,sf_slug,sf_id,mean', [('poly_quad4', 0, 'v1', 0, 1), ('gaussian', 1, 'v2', 1, 0)])
-def test_t64_step_matches_oracle(emul64, gf_slug, gf_id, sf_slug, sf_id, mean):
-    """One Lenia step of a 64^3 world (plane_fwd -> lead -> plane_inv) against the oracle, and the per-plane statistics
-    partial sums against direct sums in the rolled frame (statistics.py:64-100)."""
+@pytest.mark.parametrize('engine', ['line', 'half_line', 'half_line_finite'])
+@pytest.mark.parametrize('gf_slug,gf_id,sf_slug,sf_id,mean', [('poly_quad4', 0, 'v1', 0, 1), ('gaussian', 1, 'v2', 1, 0), ('gaussian', 1, 'v1', 0, 1),
+                                                              ('poly_quad4', 0, 'v1', 0, 0)])
+def test_t64_step_matches_oracle(emul64, gf_slug, gf_id, sf_slug, sf_id, mean, engine):
+    """One Lenia step of a 64^3 world (plane_fwd -> lead -> plane_inv; 'half_line': the two-threads-per-line kernels of
+    lnx_tiled64h.cuh) against the oracle, and the per-plane statistics partial sums against direct sums in the rolled frame
+    (statistics.py:64-100)."""
     D, R = 64, 13
     kp = [dict(k_slug='raw', k_params=_shell_kernel_3d(R), kf_slug='poly_quad', kf_params=[4], gf_slug=gf_slug, gf_params=[.15, .015], h=.7,
                c_in=0, c_out=0)]
@@ -235,8 +239,11 @@ def test_t64_step_matches_oracle(emul64, gf_slug, gf_id, sf_slug, sf_id, mean):
     part = np.zeros((64, NP), np.float32)
     shift = np.array([5, 60, 17], np.int32)
     nxt = np.zeros((64, 64, 33), np.complex64)  # fused tail: axes-(1, 2) half spectra of the NEW cells, plane by plane
-    emul64.lnx_t64_emul_step(P(st), P(ktab), gf_id, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), mean, sf_id, 0.1, P(shift), P(pot), P(fld),
-                             P(part), P(nxt))
+    args = (P(st), P(ktab), gf_id, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), mean, sf_id, 0.1, P(shift), P(pot), P(fld), P(part), P(nxt))
+    if engine == 'line':
+        emul64.lnx_t64_emul_step(*args)
+    else:  # '_finite': single-instruction clamps (LNX_RUN_ASSUME_FINITE), otherwise the NaN-propagating forms
+        emul64.lnx_t64h_emul_step(*args, int(engine == 'half_line_finite'))
     ref_nxt = np.fft.rfft2(st.astype(np.float64), axes=(1, 2))
     assert np.abs(nxt - ref_nxt).max() < 2e-7 * np.abs(ref_nxt).max()
     assert np.abs(pot - op[0, 0]).max() < 1e-6

@@ -445,17 +445,24 @@ def _check_large_2d_world(size, scale, steps):
     np.testing.assert_allclose(stats['inertia'].cpu().numpy(), ostats['inertia'], rtol=1e-3)
 
 
-@pytest.mark.parametrize('engine', ['line64', 'generic'])
+@pytest.mark.parametrize('engine', ['half_line', 'line64', 'generic'])
 def test_3d_worlds_match_oracle(engine):
     """BASELINE config E shape (64^3, 1 channel / 1 kernel, raw spherical-shell kernel); the reference has no 3-D kernel
-    generator and no 3-D test: parity is oracle-only.  Both engines: the thread-per-line kernels of
-    lnx_tiled64.cuh (default for this shape) and the generic tiled passes."""
+    generator and no 3-D test: parity is oracle-only.  Three engines: the half-line kernels of
+    lnx_tiled64h.cuh (default for this shape), the round-1 thread-per-line kernels of lnx_tiled64.cuh and the generic tiled passes."""
     D, R, steps, n = 64, 13, 4, 3
-    runner.TILED_GENERIC = engine == 'generic'
+    runner.TILED_GENERIC, runner.T64_LINE = engine == 'generic', engine == 'line64'
     try:
         _check_3d_worlds(D, R, steps, n)
     finally:
-        runner.TILED_GENERIC = False
+        runner.TILED_GENERIC = runner.T64_LINE = False
+
+
+@pytest.mark.parametrize('gf_slug,sf_slug,mean', [('gaussian', 'v1', True), ('gaussian', 'v2', False), ('triangle', 'v1', False), ('poly_quad4', 'v1', False)])
+def test_3d_half_line_engine_every_cell_phase_form_matches_oracle(gf_slug, sf_slug, mean):
+    """The compiled forms of the half-line engine's cell phase (lnx_tiled64h.cuh: packed poly_quad4 / gaussian with the v1 update,
+    per-cell selection for everything else; weighted mean and weighted sum) against the oracle, 3 steps of 2 worlds."""
+    _check_3d_worlds(64, 13, 3, 2, gf_slug=gf_slug, sf_slug=sf_slug, mean=mean)
 
 
 def test_3d_line64_engine_agrees_with_generic_tiled_passes_over_a_long_run():
@@ -475,29 +482,31 @@ def test_3d_line64_engine_agrees_with_generic_tiled_passes_over_a_long_run():
     gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
     cells = torch.from_numpy(worlds).to(DEV)[None]
     res = {}
-    for eng in ('line64', 'generic'):
-        runner.TILED_GENERIC = eng == 'generic'
+    for eng in ('half_line', 'line64', 'generic'):
+        runner.TILED_GENERIC, runner.T64_LINE = eng == 'generic', eng == 'line64'
         try:
             res[eng] = runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn)
         finally:
-            runner.TILED_GENERIC = False
-    (sa, fa), (sb, fb) = res['line64'], res['generic']
-    assert sa['N'].cpu().numpy().tolist() == sb['N'].cpu().numpy().tolist()
-    assert np.abs(fa.cpu().numpy() - fb.cpu().numpy()).max() < 2e-5
-    for k in sa:
-        if k == 'N':
-            continue
-        a, b = sa[k].cpu().numpy(), sb[k].cpu().numpy()
-        # potential_volume counts cells whose potential exceeds 1e-7: far from the blobs the potential IS rounding noise of that size
-        # (differences of centroids amplify rounding noise: angle speed = change of direction of a sub-pixel displacement / dt)
-        tol = (dict(rtol=2e-3, atol=2e-3 * max(1., float(np.abs(b).max())))
-               if k in ('mass_angle_speed', 'mass_speed', 'mass_growth_dist', 'potential_volume') else dict(rtol=2e-4, atol=1e-5))
-        np.testing.assert_allclose(a, b, err_msg=k, **tol)
+            runner.TILED_GENERIC = runner.T64_LINE = False
+    for eng in ('half_line', 'line64'):
+        (sa, fa), (sb, fb) = res[eng], res['generic']
+        assert sa['N'].cpu().numpy().tolist() == sb['N'].cpu().numpy().tolist()
+        assert np.abs(fa.cpu().numpy() - fb.cpu().numpy()).max() < 2e-5
+        for k in sa:
+            if k == 'N':
+                continue
+            a, b = sa[k].cpu().numpy(), sb[k].cpu().numpy()
+            # potential_volume counts cells whose potential exceeds 1e-7: far from the blobs the potential IS rounding noise of that size
+            # (differences of centroids amplify rounding noise: angle speed = change of direction of a sub-pixel displacement / dt)
+            tol = (dict(rtol=2e-3, atol=2e-3 * max(1., float(np.abs(b).max())))
+                   if k in ('mass_angle_speed', 'mass_speed', 'mass_growth_dist', 'potential_volume') else dict(rtol=2e-4, atol=1e-5))
+            np.testing.assert_allclose(a, b, err_msg=eng + ' ' + k, **tol)
 
 
-def _check_3d_worlds(D, R, steps, n):
+def _check_3d_worlds(D, R, steps, n, gf_slug='poly_quad4', sf_slug='v1', mean=True):
     kern = kernels.sphere_nd(R, [1., [1.]], 'poly_quad', [4], device=DEV)  # [1, 26, 26, 26]
-    kp = [dict(k_slug='raw', k_params=kern, kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1., c_in=0, c_out=0)]
+    gfp = [.15, .05] if gf_slug == 'triangle' else [.15, .015]
+    kp = [dict(k_slug='raw', k_params=kern, kf_slug='poly_quad', kf_params=[4], gf_slug=gf_slug, gf_params=gfp, h=.8, c_in=0, c_out=0)]
     K, mapping = kernels.get_kernels_and_mapping(kp, [D, D, D], 1, R, device=DEV)
     okp = [dict(kp[0], k_params=kern.cpu().numpy())]
     oK, om = lo.get_kernels_and_mapping(okp, [D, D, D], 1, R)
@@ -505,15 +514,17 @@ def _check_3d_worlds(D, R, steps, n):
     rng = np.random.default_rng(3)
     maxv = np.linspace(0.4, 1., n, dtype=np.float32)[:, None, None, None, None]
     worlds = (rng.random((n, 1, D, D, D), dtype=np.float32) * maxv).astype(np.float32)  # initializations.py:26-28
-    ufn = helpers.build_update_fn(K.shape, mapping)
+    ufn = helpers.build_update_fn(K.shape, mapping, sf_slug, mean)
     wp, rp = {'R': R, 'T': 10}, {'world_size': [D, D, D]}
     sfn = statistics.build_compute_stats_fn(wp, rp)
     c, f, p, stats = runner.run_scan(None, torch.from_numpy(worlds).to(DEV), K, mapping.get_gf_params(DEV),
                                      mapping.get_kernels_weight_per_channel(DEV), 10., steps, R, ufn, sfn)
     oc, of, op, ostats = lo.run_scan(worlds, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), steps,
-                                     lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp))
+                                     lo.build_update_fn(om, sf_slug, mean), lo.build_compute_stats_fn(wp, rp))
     assert np.abs(p.cpu().numpy() - op).max() < 3e-6
-    assert np.abs(c.cpu().numpy() - oc).max() < 1e-5
+    # (triangle: slope 2 / s = 40 per unit of potential, i.e. 1.2e-4 of field for the 3e-6 the potentials may differ by)
+    assert np.abs(f.cpu().numpy() - of).max() < (2e-4 if gf_slug == 'triangle' else 2e-5)
+    assert np.abs(c.cpu().numpy() - oc).max() < (2e-5 if gf_slug == 'triangle' else 1e-5)
     for k in ('mass', 'mass_volume', 'growth', 'mass_speed', 'mass_growth_dist', 'potential_volume'):
         np.testing.assert_allclose(stats[k].cpu().numpy(), ostats[k], rtol=5e-4, atol=1e-4, err_msg=k)
     assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()

@@ -173,13 +173,14 @@ def config_e(steps):
     _, cells = initializations.random_uniform(initializations.RngKey(5), n, [D, D, D], R, [.15, .015], device=DEV)
     cells = cells[None, :, None]
     gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
-    ms, out = timed(lambda: runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn), reps=2)
+    ms, out = timed(lambda: runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn), reps=int(os.environ.get('LNX_BENCH_REPS', 2)))
     cu = n * D**3 * steps
     tfl = cu * 136 / (ms * 1e-3) / 1e12
     gbs = cu * 32 / (ms * 1e-3) / 1e9
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     hbm = peaks.get('hbm_gbs', 6650.0)
-    engine = 'generic tiled passes' if runner.TILED_GENERIC else 'thread-per-line passes (lnx_tiled64.cuh)'
+    engine = ('generic tiled passes' if runner.TILED_GENERIC else 'thread-per-line passes (lnx_tiled64.cuh)' if runner.T64_LINE
+              else 'half-line passes (lnx_tiled64h.cuh)')
     return {'config': 'E: 256 worlds 64^3, 1c1k, ' + engine, 'steps': steps, 'ms': ms, 'cell_updates_per_s': cu / (ms * 1e-3),
             'roofline': {'bound': 'fp32 (SURVEY) / hbm (multi-pass engines: 256 MB of state > L2)', 'flop_per_cell_update': 136, 'achieved_tflops': tfl,
                          'peak_tflops': fp32_peak(), 'frac': tfl / fp32_peak(), 'achieved_gbs_at_32B': gbs, 'hbm_peak_gbs': hbm,
@@ -191,8 +192,10 @@ if __name__ == '__main__':
     ap.add_argument('--configs', default='A,C,D,E')
     ap.add_argument('--steps', type=int, default=0)
     ap.add_argument('--tiled-generic', action='store_true', help='configs D / E through the generic tiled passes (A/B run)')
+    ap.add_argument('--t64-line', action='store_true', help='config E through the round-1 thread-per-line step kernels (A/B run)')
     a = ap.parse_args()
     runner.TILED_GENERIC = a.tiled_generic
+    runner.T64_LINE = a.t64_line
     default_steps = {'A': 1024, 'B': 1024, 'C': 1024, 'D': 256, 'E': 64}
     fns = {'A': config_a, 'B': config_b, 'C': config_c, 'D': config_d, 'E': config_e}
     for c in a.configs.split(','):
