@@ -352,7 +352,7 @@ class Workload:
             self.K, self.gf, self.w = K[None], mapping.get_gf_params(dev)[None], mapping.get_kernels_weight_per_channel(dev)[None]
             self.T = torch.tensor([10.], device=dev)
             self.shard_axis = 'sols'
-            self.kernel = 't2k::lead_kernel + t2k::rows_inv_kernel (graph-replayed step)'
+            self.kernel = 't2k::lead_kernel + t2k::rows1_inv_kernel (graph-replayed step)'
             self.launches_per_step = 2 * self.sim_steps + 6  # per sim step lead + fused rows; + table gathers, first rows, pass D, summary
         else:
             total = n_override or c['worlds']
@@ -367,7 +367,7 @@ class Workload:
             self.K, self.gf, self.w = K[None], mapping.get_gf_params(dev)[None], mapping.get_kernels_weight_per_channel(dev)[None]
             self.T = torch.tensor([10.], device=dev)
             self.shard_axis = 'inits'
-            self.kernel = 't64::lead_kernel + t64::plane_inv_kernel (+ pass D) per step'
+            self.kernel = 't64h::lead_h_kernel + t64h::plane_step_kernel (+ pass D) per step'
             self.launches_per_step = 3 * self.sim_steps + 4
         self.dims, self.C = dims, C
         self.dev_cells = self.host_cells.to(dev)
@@ -469,7 +469,11 @@ def roofline_of(wl, kernel_ms, value_local, fp32_peak, peaks):
              'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback of B200_PROFILING.md',
              'note': 'algorithmic bytes (SURVEY 8d convention: three streaming passes); the 48 MiB working set of one 2048^2 world sits in L2'}
     if 'bytes' in c and c['bound'] == 'fp32':  # config E: multi-pass engine, also report the HBM convention
-        r['hbm_convention'] = {'bytes_per_cell_update': c['bytes'], 'achieved_gbs': value_local * c['bytes'] / 1e9, 'peak_gbs': peaks.get('hbm_gbs')}
+        # engine_*: what the two passes of this engine really stream per cell-update (lead: half spectrum in + out = 2 x 4.125 B; plane_step:
+        # spectrum in + out, state in + out = 16.25 B; DRAM traffic measured by ncu equals it, profiles/r2_t64h_ncu_v2.txt)
+        r['hbm_convention'] = {'bytes_per_cell_update': c['bytes'], 'achieved_gbs': value_local * c['bytes'] / 1e9, 'peak_gbs': peaks.get('hbm_gbs'),
+                               'engine_bytes_per_cell_update': 24.5, 'engine_achieved_gbs': value_local * 24.5 / 1e9,
+                               'engine_frac': value_local * 24.5 / 1e9 / peaks['hbm_gbs'] if peaks.get('hbm_gbs') else None}
     r['kernel'], r['kernel_ms'] = wl.kernel, kernel_ms
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this exact shape, from a committed ncu capture (or null)
     try:

@@ -279,7 +279,7 @@ static int ensure_tiled_init(int dev) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pass_c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lnx::t2k::rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lnx::t2k::ROWS_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lnx::t2k::rows_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lnx::t2k::ROWS_SMEM);
+    if (e == cudaSuccess) e = lnx::t2k::set_rows_inv_attributes();
     if (e != cudaSuccess) {
         if (d) cudaFree(d);
         if (d2) cudaFree(d2);
@@ -700,11 +700,20 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             using namespace lnx::t2k;
             d.g.n_slabs = 1024 / ROWS_WARPS;  // rows_inv writes one row of partial sums per CTA (eight row pairs)
             const unsigned nw = (unsigned)worlds;
-            rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, nw), 32 * ROWS_WARPS, ROWS_SMEM, st>>>(a, x2k);  // the first step's forward rows
+            // rows kernels: one real row per warp (round 2; 16 rows per CTA) or the round-1 row pairs (8 pairs per CTA) - same layouts
+            const bool pairs = (run_flags & LNX_RUN_T2K_PAIRS) != 0;
+            const bool finite = (run_flags & LNX_RUN_ASSUME_FINITE) != 0;
+            if (pairs)
+                rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, nw), 32 * ROWS_WARPS, ROWS_SMEM, st>>>(a, x2k);  // the first step's forward rows
+            else
+                rows1_fwd_kernel<<<dim3(N / RR_WARPS, 1, nw), 32 * RR_WARPS, RR_SMEM, st>>>(a, x2k);
             const int rc = th::replay_steps(
                 [&](cudaStream_t cap) {
                     lnx::t2k::lead_kernel<<<dim3(1026, 1, nw), 32, 0, cap>>>(b, x2k, d);
-                    rows_inv_kernel<<<dim3(1024 / ROWS_WARPS, 1, nw), 32 * ROWS_WARPS, ROWS_SMEM, cap>>>(c, x2k, a.spec);
+                    if (pairs)
+                        launch_rows_inv(c, x2k, a.spec, nw, finite, cap);
+                    else
+                        launch_rows1_inv(c, x2k, a.spec, nw, finite, cap);
                 },
                 max_run_iter, st);
             if (rc != LNX_OK) return rc;

@@ -13,7 +13,7 @@
 // The per-lane phase functions are __host__ __device__: tests/emul/lnx_t64_emul.cu runs them lane by lane on the CPU.
 // Reference: leniax/core.py:52-102, :163-319, leniax/statistics.py:36-126.
 #pragma once
-#include "lnx_tiled64.cuh"
+#include "lnx_tiled64h.cuh"
 
 namespace lnx {
 namespace t2k {
@@ -200,7 +200,7 @@ struct CellParams2 {
 };
 // coalesced growth / mix / update of the two rows (4096 consecutive cells) + this lane's statistics partials
 // keep_state: the new cells also replace the potentials in `ps` (the fused step kernel transforms them for the next step)
-template <int GF, int SF>
+template <int GF, int SF, int ROWS = 2>
 LNX_HD void ri_update(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
                       float* __restrict__ pot_out, const CellParams2& cp, float* acc, bool keep_state) {
     constexpr int B = 8;
@@ -208,7 +208,7 @@ LNX_HD void ri_update(int lane, float* ps, float* __restrict__ st, float* __rest
     const float inv_wsum = cp.mean ? 1.0f / cp.wsum : 1.0f;
     const float x0a = (float)(((cp.row0 - cp.sh0) & (N - 1)) - N / 2), x0b = (float)(((cp.row0 + 1 - cp.sh0) & (N - 1)) - N / 2);
 #pragma unroll 1
-    for (int it0 = 0; it0 < 32; it0 += B) {
+    for (int it0 = 0; it0 < 16 * ROWS; it0 += B) {  // ROWS = 1: one row per warp (the real-row kernels)
         float4 avs[B], pvs[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) avs[b] = *reinterpret_cast<const float4*>(st + (it0 + b) * 128 + lane * 4);
@@ -275,19 +275,257 @@ LNX_HD void ri_update(int lane, float* ps, float* __restrict__ st, float* __rest
     acc[5 + 2 * MAXD] = gx1;
     acc[4 + 3 * MAXD] = m00;
 }
-LNX_HD void ri_update_dispatch(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
-                               float* __restrict__ pot_out, const CellParams2& cp, float* acc, bool keep_state = false) {
-    if (cp.state_fn == SF_V1 && cp.gf_id == GF_POLY_QUAD4)
-        ri_update<GF_POLY_QUAD4, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state);
-    else if (cp.state_fn == SF_V1 && cp.gf_id == GF_GAUSSIAN)
-        ri_update<GF_GAUSSIAN, SF_V1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state);
-    else
-        ri_update<-1, -1>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state);
+// The same cell phase on PAIRS of neighbouring cells with the packed FP32 instructions (compile-time growth function, v1 update;
+// lnx_tiled64h.cuh's update_pk for this layout): 15 instructions per cell instead of 34 - the cell phase was more than half of the
+// dependency chain of the rows warp.  Column coordinates as packed pairs (a quad wraps at most once per row), row sums folded into
+// the row moments at the end of each row.
+template <int GF, bool NP, int ROWS = 2>
+LNX_HD void ri_update_pk(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                         float* __restrict__ pot_out, const FusedConsts& K, int sh0, int sh1, int row0, float* acc, bool keep_state) {
+    constexpr int B = 8;
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 mA = z2, gA = z2, mx1 = z2, mx21 = z2, gx1 = z2;
+    float m00 = 0.f, g00 = 0.f, mx0 = 0.f, mx20 = 0.f, gx0 = 0.f;
+    int cnt_a = 0, cnt_g = 0, cnt_p = 0;  // at most 128 hits each
+    const float x0a = (float)(((row0 - sh0) & (N - 1)) - N / 2), x0b = (float)(((row0 + 1 - sh0) & (N - 1)) - N / 2);
+#pragma unroll 1
+    for (int it0 = 0; it0 < 16 * ROWS; it0 += B) {
+        float4 avs[B], pvs[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) avs[b] = *reinterpret_cast<const float4*>(st + (it0 + b) * 128 + lane * 4);
+#pragma unroll
+        for (int b = 0; b < B; ++b) pvs[b] = *reinterpret_cast<const float4*>(ps + (it0 + b) * 128 + lane * 4);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int i = (it0 + b) * 128 + lane * 4, n0 = i & (N - 1);
+            const float xb = (float)(((n0 - sh1) & (N - 1)) - N / 2);
+            float2 X01 = make_float2(xb, xb + 1.f), X23 = make_float2(xb + 2.f, xb + 3.f);
+            if (xb > (float)(N / 2 - 4)) {  // the quad crosses the seam of the rolled frame (one quad per row at most)
+                X01.y = X01.y >= (float)(N / 2) ? X01.y - (float)N : X01.y;
+                X23.x = X23.x >= (float)(N / 2) ? X23.x - (float)N : X23.x;
+                X23.y = X23.y >= (float)(N / 2) ? X23.y - (float)N : X23.y;
+            }
+            const float2 A0 = make_float2(avs[b].x, avs[b].y), A1 = make_float2(avs[b].z, avs[b].w);
+            const float2 P0 = make_float2(pvs[b].x, pvs[b].y), P1 = make_float2(pvs[b].z, pvs[b].w);
+            cnt_p += gt_bits(P0.x, EPS) + gt_bits(P0.y, EPS);  // statistics.py:70
+            cnt_p += gt_bits(P1.x, EPS) + gt_bits(P1.y, EPS);
+            const float2 F0 = field_fused_pk<GF, NP>(P0, K), F1 = field_fused_pk<GF, NP>(P1, K);
+            mA = pk_add(mA, pk_add(A0, A1));
+            const float2 AX0 = pk_mul(A0, X01), AX1 = pk_mul(A1, X23);
+            mx1 = pk_add(mx1, pk_add(AX0, AX1));
+            mx21 = pk_fma(AX0, X01, mx21);
+            mx21 = pk_fma(AX1, X23, mx21);
+            cnt_a += gt_bits(A0.x, EPS) + gt_bits(A0.y, EPS);
+            cnt_a += gt_bits(A1.x, EPS) + gt_bits(A1.y, EPS);
+            const float2 G0 = make_float2(fmaxf(F0.x, 0.f), fmaxf(F0.y, 0.f)), G1 = make_float2(fmaxf(F1.x, 0.f), fmaxf(F1.y, 0.f));  // statistics.py:65
+            gA = pk_add(gA, pk_add(G0, G1));
+            gx1 = pk_fma(G0, X01, gx1);
+            gx1 = pk_fma(G1, X23, gx1);
+            cnt_g += gt_bits(F0.x, EPS) + gt_bits(F0.y, EPS);  // max(f, 0) > eps <=> f > eps
+            cnt_g += gt_bits(F1.x, EPS) + gt_bits(F1.y, EPS);
+            float4 nw;
+            if constexpr (!NP) {  // clip(a + dt f, 0, 1) as one saturating FMA (no NaN possible here)
+                nw = make_float4(saturate01(A0.x + K.dt * F0.x), saturate01(A0.y + K.dt * F0.y), saturate01(A1.x + K.dt * F1.x),
+                                 saturate01(A1.y + K.dt * F1.y));
+            } else {
+                nw = make_float4(state_update<SF_V1, NP>(A0.x, F0.x, K.dt), state_update<SF_V1, NP>(A0.y, F0.y, K.dt),
+                                 state_update<SF_V1, NP>(A1.x, F1.x, K.dt), state_update<SF_V1, NP>(A1.y, F1.y, K.dt));
+            }
+            *reinterpret_cast<float4*>(st + i) = nw;
+            if (keep_state) *reinterpret_cast<float4*>(ps + i) = nw;
+            if (cells_out) *reinterpret_cast<float4*>(cells_out + i) = avs[b];
+            if (field_out) *reinterpret_cast<float4*>(field_out + i) = make_float4(F0.x, F0.y, F1.x, F1.y);
+            if (pot_out) *reinterpret_cast<float4*>(pot_out + i) = pvs[b];
+        }
+        if (((it0 + B) & 15) == 0) {  // end of a row: its sums enter the row-coordinate moments
+            const float x0 = it0 < 16 ? x0a : x0b, sa = mA.x + mA.y, sg = gA.x + gA.y;
+            m00 += sa;
+            g00 += sg;
+            mx0 += sa * x0;
+            mx20 += sa * x0 * x0;
+            gx0 += sg * x0;
+            mA = z2;
+            gA = z2;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) acc[i] = 0.f;
+    acc[0] = count_from_bits(cnt_a);
+    acc[1] = g00;
+    acc[2] = count_from_bits(cnt_g);
+    acc[3] = count_from_bits(cnt_p);
+    acc[4] = mx0;
+    acc[5] = mx1.x + mx1.y;
+    acc[4 + MAXD] = mx20;
+    acc[5 + MAXD] = mx21.x + mx21.y;
+    acc[4 + 2 * MAXD] = gx0;
+    acc[5 + 2 * MAXD] = gx1.x + gx1.y;
+    acc[4 + 3 * MAXD] = m00;
+}
+// the compiled forms of the cell phase (t64h::Mode): per-cell selection, or a compile-time growth function with the v1 update
+template <int MODE, int ROWS = 2>
+LNX_HD void ri_update_mode(int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out, float* __restrict__ field_out,
+                           float* __restrict__ pot_out, const CellParams2& cp, float* acc, bool keep_state) {
+    if constexpr (MODE == t64h::MODE_DYN) {
+        ri_update<-1, -1, ROWS>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state);
+    } else {
+        FusedConsts K;
+        K.gf = cp.gc;
+        K.c = cp.mean ? cp.wk * (1.0f / cp.wsum) : cp.wk;
+        K.c2 = 2.0f * K.c;
+        K.dt = cp.dt;
+        constexpr int GF = (MODE == t64h::MODE_PQ4 || MODE == t64h::MODE_PQ4_NP) ? GF_POLY_QUAD4 : GF_GAUSSIAN;
+        constexpr bool NP = MODE == t64h::MODE_PQ4_NP || MODE == t64h::MODE_GAUSS_NP;
+        ri_update_pk<GF, NP, ROWS>(lane, ps, st, cells_out, field_out, pot_out, K, cp.sh0, cp.sh1, cp.row0, acc, keep_state);
+    }
+}
+template <int ROWS = 2>
+LNX_HD void ri_update_by_mode(int mode, int lane, float* ps, float* __restrict__ st, float* __restrict__ cells_out,
+                              float* __restrict__ field_out, float* __restrict__ pot_out, const CellParams2& cp, float* acc,
+                              bool keep_state) {  // emulator entry
+    switch (mode) {
+        case t64h::MODE_PQ4_NP: ri_update_mode<t64h::MODE_PQ4_NP, ROWS>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state); break;
+        case t64h::MODE_PQ4: ri_update_mode<t64h::MODE_PQ4, ROWS>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state); break;
+        case t64h::MODE_GAUSS_NP: ri_update_mode<t64h::MODE_GAUSS_NP, ROWS>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state); break;
+        case t64h::MODE_GAUSS: ri_update_mode<t64h::MODE_GAUSS, ROWS>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state); break;
+        default: ri_update_mode<t64h::MODE_DYN, ROWS>(lane, ps, st, cells_out, field_out, pot_out, cp, acc, keep_state); break;
+    }
 }
 // the packed line of the row pair from the two rows of new cells left in shared memory by ri_update(keep_state)
 LNX_HD void rf_load_smem(int lane, const float* ps, float2* v) {
 #pragma unroll
     for (int n2 = 0; n2 < 64; ++n2) v[n2] = make_float2(ps[lane + 32 * n2], ps[N + lane + 32 * n2]);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Real-row variant of the two rows kernels (round 2): ONE REAL ROW PER WARP instead of a packed row pair.  The row of 2048 reals is
+// the complex line z[n] = x[2n] + i x[2n+1] of 1024 points = 32 x 32 (lane n1 transforms z[n1 + 32 n2] in 64 registers, twiddles
+// W_1024^(n1 k2), one exchange through shared memory, lane k2 transforms the other axis), followed by the twiddled untangle
+// X[k] = (Z[k] + conj Z[1024-k]) / 2 - i W_2048^k (Z[k] - conj Z[1024-k]) / 2.  Twice the warps with half the dependency chain each:
+// a single 2048^2 world is one wave of warps whose chain length IS the kernel time.  Layouts (T[k][row], the
+// kernel table, the partial sums of 16 rows per CTA) are unchanged, so lead_kernel and pass D serve both variants.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NC = N / 2;            // complex points of a packed real row
+constexpr int RR_WARPS = 16;         // rows per CTA: the sixteen 8-byte pieces of one k are one 128-byte line of T
+constexpr int NATS1 = 1058;          // complex values per warp buffer: >= 32 * 33 (exchange) and 1025 (raw half spectrum); even (128-bit row accesses), = 2 mod 16 (the cooperative 8-byte accesses of a warp fall on every bank exactly twice)
+constexpr size_t RR_SMEM = (size_t)RR_WARPS * NATS1 * sizeof(float2);
+
+// v[j] *= W_1024^(lane * k2) (INV: conjugate), k2 = br5(j): ten exact table values per lane, every twiddle one product of two
+template <bool INV>
+LNX_HD void twiddle32(int lane, float2* v, const float2* __restrict__ tab) {
+    float2 ta[8], tc[4];
+#pragma unroll
+    for (int a = 1; a < 8; ++a) ta[a] = LNX_T64_LDG(tab + ((2 * lane * a) & (N - 1)));
+#pragma unroll
+    for (int c = 1; c < 4; ++c) tc[c] = LNX_T64_LDG(tab + ((16 * lane * c) & (N - 1)));
+#pragma unroll
+    for (int j = 1; j < 32; ++j) {
+        const int k2 = br5(j), a = k2 & 7, c = k2 >> 3;
+        float2 w;
+        if (c == 0)
+            w = ta[a];
+        else if (a == 0)
+            w = tc[c];
+        else
+            w = make_float2(ta[a].x * tc[c].x - ta[a].y * tc[c].y, ta[a].y * tc[c].x + ta[a].x * tc[c].y);
+        v[j] = INV ? rot_inv(v[j], w.x, w.y) : rot_fwd(v[j], w.x, w.y);
+    }
+}
+// forward: v[n2] = z[lane + 32 n2]  ->  u[j] = Z[lane + 32 br5(j)]
+LNX_HD void f1_a(int lane, float2* v, const float2* __restrict__ tab) {
+    fft_dif<32>(v);
+    twiddle32<false>(lane, v, tab);
+}
+LNX_HD void f1_store(int lane, const float2* v, float2* ex) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ex[br5(j) * EXS + lane] = v[j];
+}
+LNX_HD void f1_b(int lane, const float2* ex, float2* u) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) u[q] = ex[lane * EXS + q];
+    fft_dif<32>(u);
+}
+LNX_HD void f1_nat_store(int lane, const float2* u, float2* nat) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) nat[lane + 32 * br5(j)] = u[j];
+}
+// inverse (un-normalised): Z in natural order -> v[n2] = z[lane + 32 n2]
+LNX_HD void i1_nat_load(int lane, const float2* nat, float2* u) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) u[j] = nat[lane + 32 * br5(j)];
+    ifft_dit<32>(u);
+}
+LNX_HD void i1_store(int lane, const float2* u, float2* ex) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) ex[lane * EXS + q] = u[q];
+}
+LNX_HD void i1_b(int lane, const float2* ex, float2* v, const float2* __restrict__ tab) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ex[br5(j) * EXS + lane];
+    twiddle32<true>(lane, v, tab);
+    ifft_dit<32>(v);
+}
+LNX_HD void rr_load(int lane, const float* __restrict__ row, float2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) v[n2] = LNX_T64_LDG(reinterpret_cast<const float2*>(row) + lane + 32 * n2);
+}
+LNX_HD void rr_load_smem(int lane, const float* ps, float2* v) {
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) v[n2] = reinterpret_cast<const float2*>(ps)[lane + 32 * n2];
+}
+LNX_HD void rr_pot_store(int lane, const float2* v, float* ps) {
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) reinterpret_cast<float2*>(ps)[lane + 32 * n2] = v[n2];
+}
+// CTA-cooperative: thread -> (row buffer w = tid & 15, k = (tid >> 4) + 32 i).  Untangle and write T[k][row0 + w]; dst = T + row0
+LNX_HD void rf16_untangle_store(int tid, const float2* nat_all, const float2* __restrict__ tab, float2* __restrict__ dst) {
+    const int w = tid & 15, kq = tid >> 4;
+    const float2* nat = nat_all + w * NATS1;
+#pragma unroll 4
+    for (int i = 0; i <= 32; ++i) {
+        const int k = kq + 32 * i;
+        if (i == 32 && kq != 0) break;  // k = 1024
+        const float2 z = nat[k & (NC - 1)], zc = nat[(NC - k) & (NC - 1)], t = LNX_T64_LDG(tab + k);
+        const float2 A = pk_add(z, make_float2(zc.x, -zc.y)), B = pk_add(z, make_float2(-zc.x, zc.y));
+        const float2 Q = cmul(B, make_float2(-0.5f * t.y, -0.5f * t.x));  // -i/2 W_2048^k B
+        dst[(size_t)k * N + w] = pk_fma(A, pk_bc(0.5f), Q);
+    }
+}
+// raw half spectrum X[0..1024] of row w -> nat[w][k]; src = P + row0
+LNX_HD void ri16_gather(int tid, const float2* __restrict__ src, float2* nat_all) {
+    const int w = tid & 15, kq = tid >> 4;
+    float2* nat = nat_all + w * NATS1;
+    float2 x[33];
+#pragma unroll
+    for (int i = 0; i <= 32; ++i) {
+        const int k = kq + 32 * i;
+        if (i < 32 || kq == 0) x[i] = LNX_T64_LDG(src + (size_t)k * N + w);
+    }
+#pragma unroll
+    for (int i = 0; i <= 32; ++i) {
+        if (i < 32 || kq == 0) nat[kq + 32 * i] = x[i];
+    }
+}
+// in place: nat[w][k] = Z[k] = (X[k] + conj X[1024-k]) + i W_2048^-k (X[k] - conj X[1024-k]), k = 0..1023; a thread owns both members of a pair
+LNX_HD void ri16_tangle(int tid, float2* nat_all, const float2* __restrict__ tab) {
+    const int w = tid & 15, kq = tid >> 4;
+    float2* nat = nat_all + w * NATS1;
+#pragma unroll 4
+    for (int i = 0; i <= 16; ++i) {
+        const int k = kq + 32 * i;
+        if (i == 16 && kq != 0) break;  // k = 512
+        const float2 x = nat[k], xc = nat[NC - k];
+        if (k == 0) {  // X[0] and X[1024] are real (their imaginary parts are ignored, as a complex-to-real transform does)
+            nat[0] = make_float2(x.x + xc.x, x.x - xc.x);
+            continue;
+        }
+        const float2 t = LNX_T64_LDG(tab + k);
+        const float2 A = pk_add(x, make_float2(xc.x, -xc.y)), B = pk_add(x, make_float2(-xc.x, xc.y));
+        const float2 Q = cmul(B, make_float2(-t.y, t.x));  // i W_2048^-k B
+        nat[k] = pk_add(A, Q);
+        if (k != NC / 2) nat[NC - k] = pk_add(make_float2(A.x, -A.y), make_float2(-Q.x, Q.y));  // conj(A - Q)
+    }
 }
 
 #ifdef __CUDACC__
@@ -364,6 +602,7 @@ __global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArg
 // grid (128, 1, worlds), 8 warps, dynamic shared memory ROWS_SMEM bytes.  next_spec != nullptr: fused step kernel — the updated row
 // pair is still in the warp's shared memory, so it is transformed for the NEXT step right away (rows_fwd without its launch, its
 // state read and its load latency); the time loop is then lead + this kernel, after one rows_fwd launch for the first step.
+template <int MODE>
 __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, Extra X, float2* next_spec) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* nat_all = reinterpret_cast<float2*>(smem_raw);
@@ -402,8 +641,8 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
     const size_t toff = traj * ((size_t)N * N) + (size_t)(2 * p) * N;
     float acc[NP_T];
     const bool fuse = next_spec != nullptr && cr.step + 1 < P.max_iter;
-    ri_update_dispatch(lane, reinterpret_cast<float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
-                       P.field_out ? P.field_out + toff : nullptr, P.potential_out ? P.potential_out + toff : nullptr, cp, acc, fuse);
+    ri_update_mode<MODE>(lane, reinterpret_cast<float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
+                         P.field_out ? P.field_out + toff : nullptr, P.potential_out ? P.potential_out + toff : nullptr, cp, acc, fuse);
 #pragma unroll
     for (int i = 0; i < NP_T; ++i) {
         float x = acc[i];
@@ -441,6 +680,139 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
         P.partials[((size_t)w * (N / 2 / ROWS_WARPS) + blockIdx.x) * NP_T + threadIdx.x] = x;
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) const_cast<WorldCarry*>(P.carry)[w].pending = 1;  // (only pass D, in a later launch, reads it)
+}
+
+// rows_inv in the compiled form of this plan (finite: LNX_RUN_ASSUME_FINITE)
+inline void launch_rows_inv(const PassCArgs& c, const Extra& x, float2* next_spec, unsigned nw, bool finite, cudaStream_t s) {
+    const dim3 grid(N / 2 / ROWS_WARPS, 1, nw);
+    switch (t64h::select_mode(c.gf_id[0], c.state_fn, finite)) {
+        case t64h::MODE_PQ4: (rows_inv_kernel<t64h::MODE_PQ4>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
+        case t64h::MODE_PQ4_NP: (rows_inv_kernel<t64h::MODE_PQ4_NP>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
+        case t64h::MODE_GAUSS: (rows_inv_kernel<t64h::MODE_GAUSS>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
+        case t64h::MODE_GAUSS_NP: (rows_inv_kernel<t64h::MODE_GAUSS_NP>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
+        default: (rows_inv_kernel<t64h::MODE_DYN>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
+    }
+}
+
+// ---- real-row variant: grid (128, 1, worlds), 16 warps; warp j of CTA c owns row 16 c + j; dynamic shared memory RR_SMEM bytes ----
+__global__ void __launch_bounds__(32 * RR_WARPS) rows1_fwd_kernel(PassAArgs P, Extra X) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* nat_all = reinterpret_cast<float2*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, row = blockIdx.x * RR_WARPS + wid, w = blockIdx.z;
+    float2* sm = nat_all + wid * NATS1;
+    float2 v[32];
+    rr_load(lane, P.state + (size_t)w * N * N + (size_t)row * N, v);
+    f1_a(lane, v, X.tw);
+    f1_store(lane, v, sm);
+    __syncwarp();
+    f1_b(lane, sm, v);
+    __syncwarp();
+    f1_nat_store(lane, v, sm);
+    __syncthreads();
+    rf16_untangle_store(threadIdx.x, nat_all, X.tw, P.spec + (size_t)w * SPEC + RR_WARPS * blockIdx.x);
+}
+template <int MODE>
+__global__ void __launch_bounds__(32 * RR_WARPS) rows1_inv_kernel(PassCArgs P, Extra X, float2* next_spec) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[RR_WARPS * NP_T];
+    float2* nat_all = reinterpret_cast<float2*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, row = blockIdx.x * RR_WARPS + wid, w = blockIdx.z;
+    float2* sm = nat_all + wid * NATS1;
+    const int sol = w / P.n_init, init = w - sol * P.n_init;
+    float* st = P.state + (size_t)w * N * N + (size_t)row * N;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)  // the state row is needed after the transform: have it in L1 by then
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(st + (j * 32 + lane) * 32));
+    ri16_gather(threadIdx.x, P.pot_spec + (size_t)w * SPEC + RR_WARPS * blockIdx.x, nat_all);
+    __syncthreads();
+    ri16_tangle(threadIdx.x, nat_all, X.tw);
+    __syncthreads();
+    float2 v[32];
+    i1_nat_load(lane, sm, v);
+    __syncwarp();
+    i1_store(lane, v, sm);
+    __syncwarp();
+    i1_b(lane, sm, v, X.tw);
+    __syncwarp();
+    rr_pot_store(lane, v, reinterpret_cast<float*>(sm));
+    __syncwarp();
+    const WorldCarry cr = P.carry[w];
+    CellParams2 cp;
+    cp.gf_id = P.gf_id[0];
+    cp.state_fn = P.state_fn;
+    cp.mean = P.mean;
+    cp.gc = gf_prepare(cp.gf_id, P.gf_params[(size_t)sol * 2], P.gf_params[(size_t)sol * 2 + 1]);
+    cp.wk = P.weights[sol];
+    cp.wsum = cp.wk;
+    cp.dt = P.dt[sol];
+    cp.sh0 = cr.shift[0];
+    cp.sh1 = cr.shift[1];
+    cp.row0 = row;
+    const size_t traj = ((size_t)sol * P.max_iter + cr.step) * P.n_init + init;
+    const size_t toff = traj * ((size_t)N * N) + (size_t)row * N;
+    float acc[NP_T];
+    const bool fuse = next_spec != nullptr && cr.step + 1 < P.max_iter;
+    ri_update_mode<MODE, 1>(lane, reinterpret_cast<float*>(sm), st, P.cells_out ? P.cells_out + toff : nullptr,
+                            P.field_out ? P.field_out + toff : nullptr, P.potential_out ? P.potential_out + toff : nullptr, cp, acc, fuse);
+#pragma unroll
+    for (int i = 0; i < NP_T; ++i) {
+        float x = acc[i];
+        if (i < 5 + 3 * MAXD) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        }
+        acc[i] = x;
+    }
+    if (lane == 0) {  // the sixteen rows of the CTA are summed below: pass D reads 128 slabs
+#pragma unroll
+        for (int i = 0; i < NP_T; ++i) red[wid * NP_T + i] = acc[i];
+    }
+    if (fuse) {  // (uniform over the CTA)
+        __syncwarp();
+        rr_load_smem(lane, reinterpret_cast<const float*>(sm), v);
+        f1_a(lane, v, X.tw);
+        __syncwarp();
+        f1_store(lane, v, sm);
+        __syncwarp();
+        f1_b(lane, sm, v);
+        __syncwarp();
+        f1_nat_store(lane, v, sm);
+        __syncthreads();
+        rf16_untangle_store(threadIdx.x, nat_all, X.tw, next_spec + (size_t)w * SPEC + RR_WARPS * blockIdx.x);
+    }
+    __syncthreads();
+    if (threadIdx.x < NP_T) {
+        float x = 0.f;
+#pragma unroll
+        for (int j = 0; j < RR_WARPS; ++j) x += red[j * NP_T + threadIdx.x];
+        P.partials[((size_t)w * (N / RR_WARPS) + blockIdx.x) * NP_T + threadIdx.x] = x;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) const_cast<WorldCarry*>(P.carry)[w].pending = 1;  // (only pass D, in a later launch, reads it)
+}
+inline void launch_rows1_inv(const PassCArgs& c, const Extra& x, float2* next_spec, unsigned nw, bool finite, cudaStream_t s) {
+    const dim3 grid(N / RR_WARPS, 1, nw);
+    switch (t64h::select_mode(c.gf_id[0], c.state_fn, finite)) {
+        case t64h::MODE_PQ4: (rows1_inv_kernel<t64h::MODE_PQ4>)<<<grid, 32 * RR_WARPS, RR_SMEM, s>>>(c, x, next_spec); break;
+        case t64h::MODE_PQ4_NP: (rows1_inv_kernel<t64h::MODE_PQ4_NP>)<<<grid, 32 * RR_WARPS, RR_SMEM, s>>>(c, x, next_spec); break;
+        case t64h::MODE_GAUSS: (rows1_inv_kernel<t64h::MODE_GAUSS>)<<<grid, 32 * RR_WARPS, RR_SMEM, s>>>(c, x, next_spec); break;
+        case t64h::MODE_GAUSS_NP: (rows1_inv_kernel<t64h::MODE_GAUSS_NP>)<<<grid, 32 * RR_WARPS, RR_SMEM, s>>>(c, x, next_spec); break;
+        default: (rows1_inv_kernel<t64h::MODE_DYN>)<<<grid, 32 * RR_WARPS, RR_SMEM, s>>>(c, x, next_spec); break;
+    }
+}
+
+inline cudaError_t set_rows_inv_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(rows_inv_kernel<t64h::MODE_DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_inv_kernel<t64h::MODE_PQ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_inv_kernel<t64h::MODE_PQ4_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_inv_kernel<t64h::MODE_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows_inv_kernel<t64h::MODE_GAUSS_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows1_inv_kernel<t64h::MODE_DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows1_inv_kernel<t64h::MODE_PQ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows1_inv_kernel<t64h::MODE_PQ4_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows1_inv_kernel<t64h::MODE_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rows1_inv_kernel<t64h::MODE_GAUSS_NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RR_SMEM);
+    return e;
 }
 
 // K_fft full complex [n_sols][nb_slots][2048][2048] (reference layout [m][k]) -> tab[sol][k][q * 32 + t] = K[m = freq_of(q, t)][k] * scale

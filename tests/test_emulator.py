@@ -275,22 +275,27 @@ def emul2k():
         g.build()
     lib = ctypes.CDLL(EMUL2K)
     f, i, v = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
-    lib.lnx_t2k_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v, v]
+    lib.lnx_t2k_emul_step.argtypes = [v, v, i, f, f, f, i, i, f, v, v, v, v, v, i, i]
+    lib.lnx_t2k_emul_rfft2.argtypes = [v, v, i]
     return lib
 
 
-def test_t2k_rfft2_matches_numpy(emul2k):
+@pytest.mark.parametrize('real_rows', [0, 1])
+def test_t2k_rfft2_matches_numpy(emul2k, real_rows):
     rng = np.random.default_rng(0)
     w = rng.random((2048, 2048), dtype=np.float32)
     spec = np.zeros((2048, 1025), np.complex64)
-    emul2k.lnx_t2k_emul_rfft2(P(w), P(spec))
+    emul2k.lnx_t2k_emul_rfft2(P(w), P(spec), real_rows)
     ref = np.fft.rfft2(w.astype(np.float64))
     assert np.abs(spec - ref).max() < 3e-7 * np.abs(ref).max()
 
 
-def test_t2k_step_matches_oracle(emul2k):
+@pytest.mark.parametrize('finite,real_rows', [(-1, 0), (0, 0), (1, 0), (-1, 1), (1, 1)])
+def test_t2k_step_matches_oracle(emul2k, finite, real_rows):
     """One Lenia step of a 2048^2 world, R = 52 (rows_fwd -> lead -> rows_inv) against the oracle, and the statistics partial
-    sums of the row pairs against direct sums in the rolled frame (statistics.py:64-100)."""
+    sums of the row pairs against direct sums in the rolled frame (statistics.py:64-100).  finite = -1: cell phase with per-cell
+    selection of the growth function; 0 / 1: the packed poly_quad4 form, NaN-propagating / single-instruction clamps.  real_rows: the
+    rows kernels with one real row per warp (round 2) instead of a packed row pair."""
     S, R = 2048, 52
     kp = [dict(k_slug='circle_2d', k_params=[1., [1.]], kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1.,
                c_in=0, c_out=0)]
@@ -305,11 +310,11 @@ def test_t2k_step_matches_oracle(emul2k):
     ns, of, op = lo.build_update_fn(om)(state[None, None], oK, gf, wt, np.float32(0.1))
     st, pot, fld = state.copy(), np.zeros_like(state), np.zeros_like(state)
     NP = emul2k.lnx_t2k_emul_np()
-    part = np.zeros((S // 2, NP), np.float32)
+    part = np.zeros((S if real_rows else S // 2, NP), np.float32)
     shift = np.array([700, 1999], np.int32)
     nxt = np.zeros((1025, 2048), np.complex64)  # fused tail: transposed row spectra T[k][row] of the NEW cells
     emul2k.lnx_t2k_emul_step(P(st), P(Kh), 0, float(gf[0, 0]), float(gf[0, 1]), float(wt[0, 0]), 1, 0, 0.1, P(shift), P(pot), P(fld), P(part),
-                             P(nxt))
+                             P(nxt), finite, real_rows)
     ref_nxt = np.fft.rfft(st.astype(np.float64), axis=1).T
     assert np.abs(nxt - ref_nxt).max() < 3e-7 * np.abs(ref_nxt).max()
     assert np.abs(pot - op[0, 0]).max() < 1e-6
