@@ -73,8 +73,8 @@ typedef enum {
                                         the thread-per-line / four-step kernels (A/B runs, cross-check in the tests) */
 #define LNX_RUN_T64_LINE 0x4000u /* 64^3 one-channel one-kernel worlds: the round-1 thread-per-line step kernels (lnx_tiled64.cuh) instead of
                                         the half-line kernels (lnx_tiled64h.cuh); A/B runs, cross-check in the tests */
-#define LNX_RUN_T2K_PAIRS 0x8000u /* 2048^2 one-channel one-kernel worlds: the round-1 rows kernels (a packed row pair per warp) instead of
-                                        one real row per warp; A/B runs, cross-check in the tests */
+#define LNX_RUN_T2K_REAL_ROWS 0x8000u /* 2048^2 one-channel one-kernel worlds: rows kernels with one real row per warp (twice the warps, half the
+                                        chain; measured no faster) instead of a packed row pair per warp; A/B runs, cross-check in the tests */
 #define LNX_RUN_ASSUME_FINITE 0x100u /* caller checked that no growth s == 0 and no weight row sums to 0: NaN cannot
                                         appear, the fused kernel may use min/max clamps that do not propagate NaN */
 

@@ -700,8 +700,9 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             using namespace lnx::t2k;
             d.g.n_slabs = 1024 / ROWS_WARPS;  // rows_inv writes one row of partial sums per CTA (eight row pairs)
             const unsigned nw = (unsigned)worlds;
-            // rows kernels: one real row per warp (round 2; 16 rows per CTA) or the round-1 row pairs (8 pairs per CTA) - same layouts
-            const bool pairs = (run_flags & LNX_RUN_T2K_PAIRS) != 0;
+            // rows kernels: a packed row pair per warp (8 pairs per CTA), or one real row per warp (16 rows per CTA; twice the warps with half
+            // the chain, measured no faster: 10.7 ms against 10.4 ms for 256 steps) - same layouts, same lead kernel
+            const bool pairs = (run_flags & LNX_RUN_T2K_REAL_ROWS) == 0;
             const bool finite = (run_flags & LNX_RUN_ASSUME_FINITE) != 0;
             if (pairs)
                 rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, nw), 32 * ROWS_WARPS, ROWS_SMEM, st>>>(a, x2k);  // the first step's forward rows

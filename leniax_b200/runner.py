@@ -72,7 +72,7 @@ GENERIC_OLD = False  # tests: several channels / kernels through the older lnx_w
 GENERIC_1CTA = False  # tests / A-B runs: several channels / kernels through lnx_world128_gen_tm (one world per SM) instead of gen2
 TILED_GENERIC = False  # tests / A-B runs: 64^3 one-channel one-kernel worlds through the generic tiled passes instead of lnx_tiled64.cuh
 T64_LINE = False  # tests / A-B runs: 64^3 worlds through the round-1 thread-per-line step kernels instead of the half-line kernels (lnx_tiled64h.cuh)
-T2K_PAIRS = False  # tests / A-B runs: 2048^2 worlds through the round-1 rows kernels (a packed row pair per warp)
+T2K_REAL_ROWS = False  # tests / A-B runs: 2048^2 worlds through the rows kernels with one real row per warp
 FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the tiled multi-pass engine as a cross-check
 
 
@@ -119,8 +119,8 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
         flags |= _lib.LNX_RUN_TILED_GENERIC
     if T64_LINE:
         flags |= _lib.LNX_RUN_T64_LINE
-    if T2K_PAIRS:
-        flags |= _lib.LNX_RUN_T2K_PAIRS
+    if T2K_REAL_ROWS:
+        flags |= _lib.LNX_RUN_T2K_REAL_ROWS
     if finite:
         flags |= _lib.LNX_RUN_ASSUME_FINITE
     if c_out[0] != _lib.LNX_COUT_ANY:

@@ -379,16 +379,16 @@ def _big_orbium(size, scale, n_copies, seed):
     return world
 
 
-@pytest.mark.parametrize('size,scale,steps,engine', [(512, 2, 6, 'generic'), (2048, 4, 3, 'line2k'), (2048, 4, 3, 'line2k_pairs'), (2048, 4, 3, 'generic')])
+@pytest.mark.parametrize('size,scale,steps,engine', [(512, 2, 6, 'generic'), (2048, 4, 3, 'line2k'), (2048, 4, 3, 'line2k_real_rows'), (2048, 4, 3, 'generic')])
 def test_large_2d_world_matches_oracle(size, scale, steps, engine):
     """BASELINE config D shape: one large world, R scaled with the pattern, 1 channel / 1 kernel.  2048^2 through three engines:
-    the four-step warp-per-line kernels of lnx_tiled2k.cuh with one real row per warp (default for this shape), the same with a packed
-    row pair per warp (round 1) and the generic tiled passes."""
-    runner.TILED_GENERIC, runner.T2K_PAIRS = engine == 'generic', engine == 'line2k_pairs'
+    the four-step warp-per-line kernels of lnx_tiled2k.cuh with a packed row pair per warp (default for this shape), the same with one
+    real row per warp and the generic tiled passes."""
+    runner.TILED_GENERIC, runner.T2K_REAL_ROWS = engine == 'generic', engine == 'line2k_real_rows'
     try:
         _check_large_2d_world(size, scale, steps)
     finally:
-        runner.TILED_GENERIC = runner.T2K_PAIRS = False
+        runner.TILED_GENERIC = runner.T2K_REAL_ROWS = False
 
 
 def test_2048_line2k_engine_agrees_with_generic_tiled_passes_over_a_long_run():
@@ -405,13 +405,13 @@ def test_2048_line2k_engine_agrees_with_generic_tiled_passes_over_a_long_run():
     gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
     cells = torch.from_numpy(world).to(DEV)[None, None, None]
     res = {}
-    for eng in ('line2k', 'line2k_pairs', 'generic'):
-        runner.TILED_GENERIC, runner.T2K_PAIRS = eng == 'generic', eng == 'line2k_pairs'
+    for eng in ('line2k', 'line2k_real_rows', 'generic'):
+        runner.TILED_GENERIC, runner.T2K_REAL_ROWS = eng == 'generic', eng == 'line2k_real_rows'
         try:
             res[eng] = runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn)
         finally:
-            runner.TILED_GENERIC = runner.T2K_PAIRS = False
-    for eng in ('line2k', 'line2k_pairs'):
+            runner.TILED_GENERIC = runner.T2K_REAL_ROWS = False
+    for eng in ('line2k', 'line2k_real_rows'):
         (sa, fa), (sb, fb) = res[eng], res['generic']
         assert sa['N'].cpu().numpy().tolist() == sb['N'].cpu().numpy().tolist()
         assert np.abs(fa.cpu().numpy() - fb.cpu().numpy()).max() < 2e-5

@@ -1,7 +1,15 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -k "2048 or large_2d or config_D" 2>&1 | tail -5 > gpurun_out/r2_t2k_tests_v2.log
-cat gpurun_out/r2_t2k_tests_v2.log
-( python tools/bench_configs.py --configs D --t2k-pairs; python tools/bench_configs.py --configs D; python tools/bench_configs.py --configs D --t2k-pairs; python tools/bench_configs.py --configs D ) 2>gpurun_out/r2_t2k_ab_v2.err | cut -c1-300 > gpurun_out/r2_t2k_ab_v2.txt
-cat gpurun_out/r2_t2k_ab_v2.txt
-ncu --set full --clock-control none --import-source on -k regex:"rows1_inv|lead_kernel" -s 40 -c 2 -f -o gpurun_out/r2_t2k_v2 python tools/bench_configs.py --configs D --steps 32 > gpurun_out/r2_t2k_ncu_v2.log 2>&1
-tail -2 gpurun_out/r2_t2k_ncu_v2.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_gpu_tests_v8.log
+cat gpurun_out/r2_gpu_tests_v8.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py > gpurun_out/r2_bench_v10.json 2> gpurun_out/r2_bench_v10.err
+python - <<'PY'
+import json
+d = json.loads(open('gpurun_out/r2_bench_v10.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['clocks'])
+for k, v in d.get('secondary', {}).items():
+    print(k, v.get('value'), v.get('ms_per_step'), v.get('roofline', {}).get('frac'), v.get('roofline', {}).get('hbm_convention', {}).get('engine_frac'), v.get('error'))
+PY
+export LNX_BENCH_REPS=5
+( python tools/bench_configs.py --configs E; python tools/bench_configs.py --configs E --t64-line; python tools/bench_configs.py --configs D; python tools/bench_configs.py --configs D --t2k-real-rows ) 2>/dev/null > gpurun_out/r2_configs_de_v2.jsonl
+cut -c1-220 gpurun_out/r2_configs_de_v2.jsonl

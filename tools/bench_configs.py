@@ -156,7 +156,7 @@ def config_d(steps):
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     hbm = peaks.get('hbm_gbs', 6650.0)
     engine = ('generic tiled passes' if runner.TILED_GENERIC else 'four-step warp-per-line passes (lnx_tiled2k.cuh), '
-              + ('row pair per warp' if runner.T2K_PAIRS else 'real row per warp') + ', CUDA-graph step loop')
+              + ('real row per warp' if runner.T2K_REAL_ROWS else 'row pair per warp') + ', CUDA-graph step loop')
     return {'config': 'D: one 2048x2048 world, 1c1k, R=52, ' + engine, 'steps': steps, 'ms': ms, 'cell_updates_per_s': cu / (ms * 1e-3),
             'roofline': {'bound': 'hbm', 'bytes_per_cell_update': 32, 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
                          'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'},
@@ -193,12 +193,12 @@ if __name__ == '__main__':
     ap.add_argument('--configs', default='A,C,D,E')
     ap.add_argument('--steps', type=int, default=0)
     ap.add_argument('--tiled-generic', action='store_true', help='configs D / E through the generic tiled passes (A/B run)')
-    ap.add_argument('--t2k-pairs', action='store_true', help='config D through the round-1 rows kernels, a packed row pair per warp (A/B run)')
+    ap.add_argument('--t2k-real-rows', action='store_true', help='config D through the rows kernels with one real row per warp (A/B run)')
     ap.add_argument('--t64-line', action='store_true', help='config E through the round-1 thread-per-line step kernels (A/B run)')
     a = ap.parse_args()
     runner.TILED_GENERIC = a.tiled_generic
     runner.T64_LINE = a.t64_line
-    runner.T2K_PAIRS = a.t2k_pairs
+    runner.T2K_REAL_ROWS = a.t2k_real_rows
     default_steps = {'A': 1024, 'B': 1024, 'C': 1024, 'D': 256, 'E': 64}
     fns = {'A': config_a, 'B': config_b, 'C': config_c, 'D': config_d, 'E': config_e}
     for c in a.configs.split(','):
