@@ -75,6 +75,9 @@ typedef enum {
                                         the half-line kernels (lnx_tiled64h.cuh); A/B runs, cross-check in the tests */
 #define LNX_RUN_T2K_REAL_ROWS 0x8000u /* 2048^2 one-channel one-kernel worlds: rows kernels with one real row per warp (twice the warps, half the
                                         chain; measured no faster) instead of a packed row pair per warp; A/B runs, cross-check in the tests */
+#define LNX_RUN_T64_STEPWISE 0x10000u /* 64^3 one-channel one-kernel worlds: one launch per pass and step (lead_h, plane_step, pass D) whatever the
+                                        number of worlds (default above 128 worlds); A/B runs, cross-check in the tests */
+#define LNX_RUN_T64_WHOLE_SCAN 0x20000u /* ... the persistent whole-scan kernel whatever the number of worlds (default up to 128 worlds) */
 #define LNX_RUN_ASSUME_FINITE 0x100u /* caller checked that no growth s == 0 and no weight row sums to 0: NaN cannot
                                         appear, the fused kernel may use min/max clamps that do not propagate NaN */
 

@@ -21,6 +21,8 @@ LNX_RUN_GENERIC_1CTA = 0x1000
 LNX_RUN_WEIGHTS_MATCH_COUT = 0x2000
 LNX_RUN_T64_LINE = 0x4000
 LNX_RUN_T2K_REAL_ROWS = 0x8000
+LNX_RUN_T64_STEPWISE = 0x10000
+LNX_RUN_T64_WHOLE_SCAN = 0x20000
 LNX_PLAN_FORCE_TILED = 1
 
 LNX_OK, LNX_ERR_INVALID, LNX_ERR_UNSUPPORTED, LNX_ERR_CUDA, LNX_ERR_NO_DEVICE = 0, -1, -2, -3, -4

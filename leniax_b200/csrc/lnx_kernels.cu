@@ -212,6 +212,18 @@ static int t64_batch(long long worlds) {
     }();
     return forced > 0 ? forced : (int)worlds;
 }
+// worlds per window of the 64^3 whole-scan kernel: a window runs ALL its steps before the next one starts, so that its working set
+// (3.2 MB per world) stays in L2.  Measured: DRAM reads fall 7x (52.8 -> 7.5 GB for 256 worlds x 64 steps at 24 worlds per window) but
+// the scan gets SLOWER (27.5 / 23.9 / 23.0 ms at 24 / 48 / all worlds per window): the kernel is bound by instruction fetch and
+// latency, not by HBM, and a small window starves it of independent work.  Default: one window; LNX_T64_WINDOW=n for A/B runs.
+static int t64_window(int worlds) {
+    static const int v = [] {
+        const char* e = getenv("LNX_T64_WINDOW");
+        const int n = e ? atoi(e) : 0;
+        return n > 0 ? n : 0;
+    }();
+    return v > 0 && v < worlds ? v : worlds;
+}
 // LNX_T64_STREAMS=2: the two halves of the world batch on two streams, so that the SMs could interleave one half's memory-latency-bound
 // lead pass with the other half's issue-bound plane pass.  Measured: 30.9 ms against 30.0 ms on one stream (256 worlds x 64 steps,
 // profiles/r2_e_two_streams.txt) - every launch already fills the machine, the kernels do not overlap.  Off by default, kept for A/B runs.
@@ -725,6 +737,36 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             // (two experiments that did not pay are kept behind environment switches: t64_batch, t64_two_streams)
             const int batch = th::t64_batch(worlds);
             const bool line64_round1 = (run_flags & LNX_RUN_T64_LINE) != 0;
+            // Up to 128 worlds: the whole scan as ONE persistent launch (t64h::scan_kernel: work queue + per-world completion counters; no
+            // wave tails, no launch gaps: 32 worlds 3.6 ms against 4.3 ms, 96 worlds 9.0 against 9.9 ms).  Above that the launch per pass and
+            // step is faster (256 worlds: 22.1 ms against 23.0 ms - eight CTAs per SM at different places of one 70 KB kernel saturate the
+            // instruction cache); profiles/r2_scan_ab.jsonl.  LNX_RUN_T64_WHOLE_SCAN / LNX_RUN_T64_STEPWISE force either.
+            const bool scan_ok = !line64_round1 && !cells_out && !field_out && !potential_out && batch >= worlds && !th::t64_two_streams() &&
+                                 (long long)worlds * max_run_iter * lnx::t64h::SCAN_ITEMS < 2000000000LL;
+            const bool whole_scan = scan_ok && !(run_flags & LNX_RUN_T64_STEPWISE) && (worlds <= 128 || (run_flags & LNX_RUN_T64_WHOLE_SCAN));
+            if (whole_scan) {
+                lnx::t64::plane_fwd_kernel<<<dim3(64, 1, (unsigned)worlds), 32, 0, st>>>(a);  // the first step's forward planes
+                int* ctr = nullptr;
+                const size_t ctr_bytes = (1 + 3 * (size_t)worlds) * sizeof(int);
+                LNX_CUDA(cudaMallocAsync(&ctr, ctr_bytes, st));
+                LNX_CUDA(cudaMemsetAsync(ctr, 0, ctr_bytes, st));
+                lnx::t64h::ScanArgs m;
+                m.queue = ctr;
+                m.cnt = ctr + 1;
+                m.worlds = (int)worlds;
+                m.steps = max_run_iter;
+                m.window = th::t64_window((int)worlds);
+                const cudaError_t e = lnx::t64h::launch_scan(b, c, d, a.spec, m, (run_flags & LNX_RUN_ASSUME_FINITE) != 0, p->sm_count, st);
+                if (e != cudaSuccess) {
+                    cudaFreeAsync(ctr, st);
+                    return fail(LNX_ERR_CUDA, "64^3 scan kernel: %s", cudaGetErrorString(e));
+                }
+                d.t = max_run_iter - 1;  // the last step's statistics
+                pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, st>>>(d);
+                LNX_CUDA(cudaFreeAsync(ctr, st));
+                LNX_CUDA(cudaGetLastError());
+                return LNX_OK;
+            }
             const bool two = batch >= worlds && worlds >= 2 && th::t64_two_streams();
             th::SideStream* side = two ? th::side_stream(p->device) : nullptr;
             if (two && !side) return LNX_ERR_CUDA;

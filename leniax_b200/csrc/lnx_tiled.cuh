@@ -266,6 +266,13 @@ __global__ void __launch_bounds__(TPB) pass_b_kernel(PassBArgs P) {
 // pass C: inverse inner transforms of every kernel's potential spectrum, growth, mix, state update, statistics partials
 //   grid (n_slabs, 1, worlds).  smem: pl [slab_rows][half] complex, z [pairs][A2] complex, field [C][slab_rows][A2]
 // ---------------------------------------------------------------------------------------------------------------------
+// Loads of data that another CTA of the SAME launch may have written (persistent whole-scan kernel of lnx_tiled64h.cuh): the L1 of an SM is
+// not coherent with the other SMs' stores, so these go to L2 (ld.global.cg).  For the multi-launch engines it is the same streaming data.
+#ifdef __CUDA_ARCH__
+#define LNX_MUT_LD(p) __ldcg(p)
+#else
+#define LNX_MUT_LD(p) (*(p))
+#endif
 struct WorldCarry {   // per world, device memory
     int shift[3];
     float centroid[3];
@@ -489,7 +496,7 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w, con
     for (int s = threadIdx.x; s < g.n_slabs; s += blockDim.x) {
         const float* p = P.partials + ((size_t)w * g.n_slabs + s) * NP_T;
 #pragma unroll
-        for (int i = 0; i < NP_T; ++i) acc[i] += p[i];
+        for (int i = 0; i < NP_T; ++i) acc[i] += LNX_MUT_LD(p + i);
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -507,7 +514,14 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w, con
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
-    WorldCarry S = P.carry[w];
+    WorldCarry S;
+    {
+        static_assert(sizeof(WorldCarry) % sizeof(int) == 0, "WorldCarry is copied word by word");
+        const int* src = reinterpret_cast<const int*>(P.carry + w);
+        int* dst = reinterpret_cast<int*>(&S);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(WorldCarry) / sizeof(int)); ++i) dst[i] = LNX_MUT_LD(src + i);
+    }
     const int nd = g.nd, C = P.C;
     // reference: R**2 is used for every "volume" normalisation whatever the dimension (statistics.py:70-78)
     const float R2 = P.R * P.R, R = P.R, dt = P.stats_dt;

@@ -61,7 +61,7 @@ LNX_HD void half_twiddle(float2* u) {
 // flat copy of the potential-spectrum plane into shared memory (the shared plane has the global layout [m1][33])
 LNX_HD void inv_load(int tid, const float2* __restrict__ src, float2* pl) {
 #pragma unroll 11
-    for (int it = 0; it < PLANE_SPEC / TPB; ++it) pl[it * TPB + tid] = LNX_T64_LDG(src + it * TPB + tid);
+    for (int it = 0; it < PLANE_SPEC / TPB; ++it) pl[it * TPB + tid] = LNX_MUT_LD(src + it * TPB + tid);
 }
 // columns 0 and 32 of a row are spectra of real sequences along axis 1: they travel as ONE complex column f0 + i f32 (slot 0)
 LNX_HD void inv_pack(int tid, float2* pl) {
@@ -123,7 +123,7 @@ LNX_HD void update(int t, float* ps, float* __restrict__ st, float* __restrict__
     for (int it0 = 0; it0 < 16; it0 += B) {
         float4 avs[B], pvs[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) avs[b] = *reinterpret_cast<const float4*>(st + (it0 + b) * 256 + t * 4);
+        for (int b = 0; b < B; ++b) avs[b] = LNX_MUT_LD(reinterpret_cast<const float4*>(st + (it0 + b) * 256 + t * 4));
 #pragma unroll
         for (int b = 0; b < B; ++b) pvs[b] = *reinterpret_cast<const float4*>(ps + (4 * (it0 + b) + rs) * SRS + n0);
 #pragma unroll
@@ -212,7 +212,7 @@ LNX_HD void update_pk(int t, float* ps, float* __restrict__ st, float* __restric
     for (int it0 = 0; it0 < 16; it0 += B) {
         float4 avs[B], pvs[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) avs[b] = *reinterpret_cast<const float4*>(st + (it0 + b) * 256 + t * 4);
+        for (int b = 0; b < B; ++b) avs[b] = LNX_MUT_LD(reinterpret_cast<const float4*>(st + (it0 + b) * 256 + t * 4));
 #pragma unroll
         for (int b = 0; b < B; ++b) pvs[b] = *reinterpret_cast<const float4*>(ps + (4 * (it0 + b) + rs) * SRS + n0);
 #pragma unroll
@@ -382,7 +382,7 @@ LNX_HD void fwd_packed_store(int m, const float2* zs, float2* __restrict__ dst) 
 LNX_HD void lead_fwd(int h, const float2* __restrict__ src, float2* u) {
     const float2 sg = pk_bc(h ? -1.f : 1.f);
 #pragma unroll
-    for (int n = 0; n < 32; ++n) u[n] = pk_fma(LNX_T64_LDG(src + (size_t)(n + 32) * COLS), sg, LNX_T64_LDG(src + (size_t)n * COLS));
+    for (int n = 0; n < 32; ++n) u[n] = pk_fma(LNX_MUT_LD(src + (size_t)(n + 32) * COLS), sg, LNX_MUT_LD(src + (size_t)n * COLS));
     if (h) half_twiddle<0, false, false>(u);
     fft_dif<32>(u);  // u[j] = X[2 br5(j) + h]
 }
@@ -403,9 +403,9 @@ LNX_HD float2 lead_combine(int h, float2 own, float2 other) { return pk_fma(own,
 // grid (66, 1, worlds), 64 threads: lane = 16 h + cc, warp wq: column 32 blockIdx.x + 16 wq + cc
 // 8 CTAs per SM = 16 warps at 128 registers (compiled for 10 CTAs / 96 registers the kernels spill: lead_h 202 us against 103 us,
 // profiles/r2_t64h_ncu_v1.txt)
-__global__ void __launch_bounds__(TPB, 8) lead_h_kernel(PassBArgs P) {
+__device__ __forceinline__ void lead_h_body(const PassBArgs& P, const int tile, const int w) {
     const int lane = threadIdx.x & 31, h = lane >> 4;
-    const int col = blockIdx.x * LEAD_COLS + (threadIdx.x >> 5) * 16 + (lane & 15), w = blockIdx.z + P.world0;
+    const int col = tile * LEAD_COLS + (threadIdx.x >> 5) * 16 + (lane & 15);
     const int sol = w / P.n_init;
     const size_t img = (size_t)N * COLS;
     float2 u[32];
@@ -420,16 +420,14 @@ __global__ void __launch_bounds__(TPB, 8) lead_h_kernel(PassBArgs P) {
         dst[(size_t)n * COLS] = lead_combine(h, u[n], o);
     }
 }
+__global__ void __launch_bounds__(TPB, 8) lead_h_kernel(PassBArgs P) { lead_h_body(P, blockIdx.x, blockIdx.z + P.world0); }
 
-// grid (64 planes, 1, worlds), 64 threads; one channel, one kernel.  next_spec != nullptr: the updated plane is transformed for the
-// NEXT step right away (as t64::plane_inv_kernel does)
+// plane l of world w at step t; next_spec != nullptr: the updated plane is transformed for the NEXT step right away (as
+// t64::plane_inv_kernel does).  sm / zs / red: the CTA's shared memory (SMEM_FLOATS floats, N complex, NRED floats)
 template <int MODE>
-__global__ void __launch_bounds__(TPB, 8) plane_step_kernel(PassCArgs P, float2* next_spec) {
-    __shared__ __align__(16) float sm[SMEM_FLOATS];
-    __shared__ float2 zs[N];
-    __shared__ float red[NRED];
-    const int tid = threadIdx.x, lane = tid & 31, c = tid & 31, h = tid >> 5;
-    const int l = blockIdx.x, w = blockIdx.z + P.world0;
+__device__ __forceinline__ void plane_step_body(const PassCArgs& P, float2* next_spec, const int l, const int w, const int t, float* sm,
+                                                float2* zs, float* red) {
+    const int tid = threadIdx.x, c = tid & 31, h = tid >> 5;
     const int sol = w / P.n_init, init = w - sol * P.n_init;
     const size_t plane = (size_t)w * N + l;
     float2* pl = reinterpret_cast<float2*>(sm);
@@ -450,7 +448,6 @@ __global__ void __launch_bounds__(TPB, 8) plane_step_kernel(PassCArgs P, float2*
     ifft_dit<32>(u);
     __syncthreads();  // every thread has its spectrum in registers: the buffer becomes the potential plane
     inv_pot_store(tid, u, sm);
-    const WorldCarry cr = P.carry[w];
     CellParams cp;
     cp.gf_id = P.gf_id[0];
     cp.state_fn = P.state_fn;
@@ -459,15 +456,15 @@ __global__ void __launch_bounds__(TPB, 8) plane_step_kernel(PassCArgs P, float2*
     cp.wk = P.weights[sol];
     cp.wsum = cp.wk;
     cp.dt = P.dt[sol];
-    cp.sh0 = cr.shift[0];
-    cp.sh1 = cr.shift[1];
-    cp.sh2 = cr.shift[2];
+    cp.sh0 = LNX_MUT_LD(&P.carry[w].shift[0]);
+    cp.sh1 = LNX_MUT_LD(&P.carry[w].shift[1]);
+    cp.sh2 = LNX_MUT_LD(&P.carry[w].shift[2]);
     cp.l = l;
-    const size_t traj = ((size_t)sol * P.max_iter + P.t) * P.n_init + init;
+    const size_t traj = ((size_t)sol * P.max_iter + t) * P.n_init + init;
     const size_t toff = traj * ((size_t)N * PLANE_CELLS) + (size_t)l * PLANE_CELLS;
     __syncthreads();
     float acc[NP_T];
-    const bool fuse = next_spec != nullptr && P.t + 1 < P.max_iter;
+    const bool fuse = next_spec != nullptr && t + 1 < P.max_iter;
     update_mode<MODE>(tid, sm, stp, P.cells_out ? P.cells_out + toff : nullptr, P.field_out ? P.field_out + toff : nullptr,
                       P.potential_out ? P.potential_out + toff : nullptr, cp, acc, fuse);
 #pragma unroll
@@ -497,8 +494,143 @@ __global__ void __launch_bounds__(TPB, 8) plane_step_kernel(PassCArgs P, float2*
     fwd_col_store(c, h, u, dst, zs);
     __syncthreads();
     fwd_packed_store(tid, zs, dst);
-    (void)lane;
 }
+// grid (64 planes, 1, worlds), 64 threads; one channel, one kernel
+template <int MODE>
+__global__ void __launch_bounds__(TPB, 8) plane_step_kernel(PassCArgs P, float2* next_spec) {
+    __shared__ __align__(16) float sm[SMEM_FLOATS];
+    __shared__ float2 zs[N];
+    __shared__ float red[NRED];
+    plane_step_body<MODE>(P, next_spec, blockIdx.x, blockIdx.z + P.world0, P.t, sm, zs, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The WHOLE scan as one persistent kernel.  The work of (world w, step t) is 66 lead tiles + the statistics finaliser of step t - 1 +
+// 64 planes; CTAs take these items from one global queue (atomicAdd) and wait on per-world completion counters:
+//     lead tile (w, t), finaliser (w, t - 1)   need all 64 planes of (w, t - 1)
+//     plane (w, t)                              needs all 66 lead tiles of (w, t) and the finaliser of (w, t - 1)
+// Queue order: windows of `window` worlds run ALL their steps before the next window starts; inside a window, step by step, first the
+// lead tiles + finalisers of every world, then the planes of every world.  (a) A dependency is always EARLIER in the queue than its
+// dependents, so whoever holds it is running or done: the spin-waits cannot deadlock, whatever the number of resident CTAs.  (b) It is
+// about 1 500 items earlier - more than the CTAs in flight - so the waits are almost never taken.  (c) The working set of a window
+// (3.2 MB per world: state, spectrum, potential spectrum) stays in the 126 MB L2: HBM sees the initial states and the statistics rows.
+// (d) No launch gaps or wave tails, and HBM-latency-bound lead tiles share an SM with shared-memory-bound planes.
+// Everything another CTA may have written is read with LNX_MUT_LD (L2); the per-solution tables stay on the read-only path.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ScanArgs {
+    int* queue;     // [1] next item, zeroed by the host
+    int* cnt;       // [3][worlds] completed lead tiles / planes / finalisers per world, zeroed by the host
+    int worlds;     // worlds of this launch (PassBArgs::world0 etc. = 0)
+    int steps;
+    int window;     // worlds per L2-resident window
+};
+constexpr int SCAN_TILES = COLS / LEAD_COLS;            // 66 lead tiles per world and step
+constexpr int SCAN_ITEMS = SCAN_TILES + 1 + N;          // + finaliser + 64 planes
+__device__ __forceinline__ void scan_wait(const int* p, const int need) {
+    while (*reinterpret_cast<const volatile int*>(p) < need) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 700
+        __nanosleep(64);
+#endif
+    }
+}
+__device__ __forceinline__ void scan_wait2(const int* p, const int need_p, const int* q, const int need_q) {  // both loads in flight together
+    for (;;) {
+        const int a = *reinterpret_cast<const volatile int*>(p), b = *reinterpret_cast<const volatile int*>(q);
+        if (a >= need_p && b >= need_q) return;
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 700
+        __nanosleep(64);
+#endif
+    }
+}
+template <int MODE>
+__global__ void __launch_bounds__(TPB, 8) scan_kernel(PassBArgs B, PassCArgs C, tiled::PassDArgs D, float2* spec, ScanArgs M) {
+    __shared__ __align__(16) float sm[SMEM_FLOATS];
+    __shared__ float2 zs[N];
+    __shared__ float red[NRED];
+    __shared__ int s_item;
+    const int tid = threadIdx.x;
+    int* cntL = M.cnt;
+    int* cntP = M.cnt + M.worlds;
+    int* cntD = M.cnt + 2 * M.worlds;
+    const int total = M.worlds * M.steps * SCAN_ITEMS;
+    const int win_items = M.window * M.steps * SCAN_ITEMS;
+    // the queue is read one item ahead (the atomic's round trip through L2 runs under the current item's work); a CTA then holds two
+    // items, the later one not started: the no-deadlock argument is unchanged (the holder of the earliest unfinished item is running it)
+    int next = 0;
+    if (tid == 0) next = atomicAdd(M.queue, 1);
+    for (;;) {
+        if (tid == 0) {
+            s_item = next;
+            if (next < total) next = atomicAdd(M.queue, 1);
+        }
+        __syncthreads();
+        const int q = s_item;
+        if (q >= total) break;
+        const int win = q / win_items, w0 = win * M.window;
+        const int W = M.worlds - w0 < M.window ? M.worlds - w0 : M.window;
+        int r = q - win * win_items;
+        const int t = r / (W * SCAN_ITEMS);
+        r -= t * (W * SCAN_ITEMS);
+        int kind, wl, j;  // kind 0: lead tile j, 1: plane j, 2: finaliser of step t - 1
+        if (r < W * (SCAN_TILES + 1)) {
+            wl = r / (SCAN_TILES + 1);
+            j = r - wl * (SCAN_TILES + 1);
+            kind = j < SCAN_TILES ? 0 : 2;
+        } else {
+            r -= W * (SCAN_TILES + 1);
+            wl = r / N;
+            j = r - wl * N;
+            kind = 1;
+        }
+        const int w = w0 + wl;
+        if (tid == 0) {
+            if (kind == 1) {
+                scan_wait2(cntL + w, SCAN_TILES * (t + 1), cntD + w, t + 1);
+            } else if (t > 0) {
+                scan_wait(cntP + w, N * t);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (kind == 0)
+            lead_h_body(B, j, w);
+        else if (kind == 1)
+            plane_step_body<MODE>(C, spec, j, w, t, sm, zs, red);
+        else if (t > 0)
+            tiled::pass_d_body(D, w, t - 1);
+        __syncthreads();
+        if (tid == 0) {  // (the barrier orders the CTA's stores before this fence: the pattern of a grid-wide barrier)
+            __threadfence();
+            atomicAdd(kind == 0 ? cntL + w : (kind == 1 ? cntP + w : cntD + w), 1);
+        }
+    }
+}
+template <int MODE>
+inline cudaError_t launch_scan_mode(const PassBArgs& b, const PassCArgs& c, const tiled::PassDArgs& d, float2* spec, const ScanArgs& m, int sms,
+                                    cudaStream_t s) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<MODE>, TPB, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)per_sm * sms;
+    const long long total = (long long)m.worlds * m.steps * SCAN_ITEMS;
+    if (grid > total) grid = total;
+    scan_kernel<MODE><<<(unsigned)grid, TPB, 0, s>>>(b, c, d, spec, m);
+    return cudaGetLastError();
+}
+// all steps of `m.worlds` worlds (world0 = 0 in the argument structs) in ONE launch; the caller has run plane_fwd for step 0 and
+// finalises the last step's statistics (pass D with t = steps - 1) afterwards
+inline cudaError_t launch_scan(const PassBArgs& b, const PassCArgs& c, const tiled::PassDArgs& d, float2* spec, const ScanArgs& m, bool finite,
+                               int sms, cudaStream_t s) {
+    switch (select_mode(c.gf_id[0], c.state_fn, finite)) {
+        case MODE_PQ4: return launch_scan_mode<MODE_PQ4>(b, c, d, spec, m, sms, s);
+        case MODE_PQ4_NP: return launch_scan_mode<MODE_PQ4_NP>(b, c, d, spec, m, sms, s);
+        case MODE_GAUSS: return launch_scan_mode<MODE_GAUSS>(b, c, d, spec, m, sms, s);
+        case MODE_GAUSS_NP: return launch_scan_mode<MODE_GAUSS_NP>(b, c, d, spec, m, sms, s);
+        default: return launch_scan_mode<MODE_DYN>(b, c, d, spec, m, sms, s);
+    }
+}
+
 // lead_h + plane_step of one step for `nb` worlds (finite: LNX_RUN_ASSUME_FINITE)
 inline void launch_step(const PassBArgs& b, const PassCArgs& c, float2* next_spec, unsigned nb, bool finite, cudaStream_t s) {
     lead_h_kernel<<<dim3(COLS / LEAD_COLS, 1, nb), TPB, 0, s>>>(b);

@@ -73,6 +73,8 @@ GENERIC_1CTA = False  # tests / A-B runs: several channels / kernels through lnx
 TILED_GENERIC = False  # tests / A-B runs: 64^3 one-channel one-kernel worlds through the generic tiled passes instead of lnx_tiled64.cuh
 T64_LINE = False  # tests / A-B runs: 64^3 worlds through the round-1 thread-per-line step kernels instead of the half-line kernels (lnx_tiled64h.cuh)
 T2K_REAL_ROWS = False  # tests / A-B runs: 2048^2 worlds through the rows kernels with one real row per warp
+T64_STEPWISE = False  # tests / A-B runs: 64^3 worlds with one launch per pass and step whatever the number of worlds (default above 128)
+T64_WHOLE_SCAN = False  # ... with the persistent whole-scan kernel whatever the number of worlds (default up to 128)
 FORCE_TILED_ENGINE = False  # tests set this to run 128x128 worlds through the tiled multi-pass engine as a cross-check
 
 
@@ -121,6 +123,10 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
         flags |= _lib.LNX_RUN_T64_LINE
     if T2K_REAL_ROWS:
         flags |= _lib.LNX_RUN_T2K_REAL_ROWS
+    if T64_STEPWISE:
+        flags |= _lib.LNX_RUN_T64_STEPWISE
+    if T64_WHOLE_SCAN:
+        flags |= _lib.LNX_RUN_T64_WHOLE_SCAN
     if finite:
         flags |= _lib.LNX_RUN_ASSUME_FINITE
     if c_out[0] != _lib.LNX_COUT_ANY:

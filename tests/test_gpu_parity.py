@@ -484,13 +484,20 @@ def test_3d_line64_engine_agrees_with_generic_tiled_passes_over_a_long_run():
     gf, w = mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None]
     cells = torch.from_numpy(worlds).to(DEV)[None]
     res = {}
-    for eng in ('half_line', 'line64', 'generic'):
-        runner.TILED_GENERIC, runner.T64_LINE = eng == 'generic', eng == 'line64'
+    # 'whole_scan': the half-line kernels as ONE persistent launch for all steps (the default up to 128 worlds); '_stepwise': the same
+    # kernels launched per pass and step (the default above); 'line64': the round-1 thread-per-line kernels
+    for eng in ('whole_scan', 'half_line_stepwise', 'line64', 'generic'):
+        runner.TILED_GENERIC, runner.T64_LINE, runner.T64_STEPWISE = eng == 'generic', eng == 'line64', eng == 'half_line_stepwise'
+        runner.T64_WHOLE_SCAN = eng == 'whole_scan'
         try:
             res[eng] = runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn)
         finally:
-            runner.TILED_GENERIC = runner.T64_LINE = False
-    for eng in ('half_line', 'line64'):
+            runner.TILED_GENERIC = runner.T64_LINE = runner.T64_STEPWISE = runner.T64_WHOLE_SCAN = False
+    # same kernels, same arithmetic, different launch structure: bit-identical
+    for k in res['whole_scan'][0]:
+        assert torch.equal(res['whole_scan'][0][k], res['half_line_stepwise'][0][k]), k
+    assert torch.equal(res['whole_scan'][1], res['half_line_stepwise'][1])
+    for eng in ('whole_scan', 'line64'):
         (sa, fa), (sb, fb) = res[eng], res['generic']
         assert sa['N'].cpu().numpy().tolist() == sb['N'].cpu().numpy().tolist()
         assert np.abs(fa.cpu().numpy() - fb.cpu().numpy()).max() < 2e-5

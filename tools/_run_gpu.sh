@@ -1,15 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_gpu_tests_v8.log
-cat gpurun_out/r2_gpu_tests_v8.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py > gpurun_out/r2_bench_v10.json 2> gpurun_out/r2_bench_v10.err
-python - <<'PY'
-import json
-d = json.loads(open('gpurun_out/r2_bench_v10.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['clocks'])
-for k, v in d.get('secondary', {}).items():
-    print(k, v.get('value'), v.get('ms_per_step'), v.get('roofline', {}).get('frac'), v.get('roofline', {}).get('hbm_convention', {}).get('engine_frac'), v.get('error'))
-PY
-export LNX_BENCH_REPS=5
-( python tools/bench_configs.py --configs E; python tools/bench_configs.py --configs E --t64-line; python tools/bench_configs.py --configs D; python tools/bench_configs.py --configs D --t2k-real-rows ) 2>/dev/null > gpurun_out/r2_configs_de_v2.jsonl
-cut -c1-220 gpurun_out/r2_configs_de_v2.jsonl
+( for n in 2 8 32 96; do echo "worlds $n"; LNX_T64_WINDOW=256 timeout 300 python tools/ab_config_e.py --reps 12 --worlds $n; done ) > gpurun_out/r2_scan_ab_small.jsonl 2>gpurun_out/r2_scan_ab_small.err
+cut -c1-120 gpurun_out/r2_scan_ab_small.jsonl; tail -2 gpurun_out/r2_scan_ab_small.err

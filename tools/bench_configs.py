@@ -181,7 +181,7 @@ def config_e(steps):
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     hbm = peaks.get('hbm_gbs', 6650.0)
     engine = ('generic tiled passes' if runner.TILED_GENERIC else 'thread-per-line passes (lnx_tiled64.cuh)' if runner.T64_LINE
-              else 'half-line passes (lnx_tiled64h.cuh)')
+              else 'half-line passes (lnx_tiled64h.cuh), ' + ('persistent whole-scan kernel' if runner.T64_WHOLE_SCAN else 'one launch per pass and step'))
     return {'config': 'E: 256 worlds 64^3, 1c1k, ' + engine, 'steps': steps, 'ms': ms, 'cell_updates_per_s': cu / (ms * 1e-3),
             'roofline': {'bound': 'fp32 (SURVEY) / hbm (multi-pass engines: 256 MB of state > L2)', 'flop_per_cell_update': 136, 'achieved_tflops': tfl,
                          'peak_tflops': fp32_peak(), 'frac': tfl / fp32_peak(), 'achieved_gbs_at_32B': gbs, 'hbm_peak_gbs': hbm,
@@ -194,10 +194,12 @@ if __name__ == '__main__':
     ap.add_argument('--steps', type=int, default=0)
     ap.add_argument('--tiled-generic', action='store_true', help='configs D / E through the generic tiled passes (A/B run)')
     ap.add_argument('--t2k-real-rows', action='store_true', help='config D through the rows kernels with one real row per warp (A/B run)')
+    ap.add_argument('--t64-whole-scan', action='store_true', help='config E through the persistent whole-scan kernel (default only up to 128 worlds; A/B run)')
     ap.add_argument('--t64-line', action='store_true', help='config E through the round-1 thread-per-line step kernels (A/B run)')
     a = ap.parse_args()
     runner.TILED_GENERIC = a.tiled_generic
     runner.T64_LINE = a.t64_line
+    runner.T64_WHOLE_SCAN = a.t64_whole_scan
     runner.T2K_REAL_ROWS = a.t2k_real_rows
     default_steps = {'A': 1024, 'B': 1024, 'C': 1024, 'D': 256, 'E': 64}
     fns = {'A': config_a, 'B': config_b, 'C': config_c, 'D': config_d, 'E': config_e}
