@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-( for n in 2 8 32 96; do echo "worlds $n"; LNX_T64_WINDOW=256 timeout 300 python tools/ab_config_e.py --reps 12 --worlds $n; done ) > gpurun_out/r2_scan_ab_small.jsonl 2>gpurun_out/r2_scan_ab_small.err
-cut -c1-120 gpurun_out/r2_scan_ab_small.jsonl; tail -2 gpurun_out/r2_scan_ab_small.err
+LNX_T64_PERSIST=1 timeout 300 python -m pytest tests -m gpu -x -q -k "3d or config_E or full_size_3d" 2>&1 | tail -3
+( timeout 300 python tools/ab_config_e.py --reps 16
+  LNX_T64_PERSIST=1 timeout 300 python tools/ab_config_e.py --reps 16 ) > gpurun_out/r2_persist_ab_v1.jsonl 2>gpurun_out/r2_persist_ab_v1.err
+cut -c1-150 gpurun_out/r2_persist_ab_v1.jsonl; tail -2 gpurun_out/r2_persist_ab_v1.err
