@@ -54,11 +54,20 @@ LNX_HD int col_of(int a, int c) {
 // ---- shared-memory layouts (complex indices inside a 512-element region) -----------------------------------------
 // E1 view [q][k1][l] with XOR swizzles: conflict-free for 64-bit accesses of (q,l) lanes at fixed k1 (P1/P5) and
 // 128-bit accesses of lanes a -> k1 in {a, 32-a} at fixed q (P2/P4).
-LNX_HD int e1_addr(int q, int k1, int l) {
-    return q * 128 + (((k1 & 28) | ((k1 ^ q) & 3)) << 2) + ((((l >> 1) ^ (k1 >> 2)) & 1) << 1) + (l & 1);
-}
-// E2 view [col][unit u][2]: unit = the pair of m2 handled together by a P3 thread.
-LNX_HD int e2_addr(int col, int u) { return col * 8 + ((u ^ ((col >> 1) & 3)) << 1); }
+// The address is the XOR of a (q, l) part and a k1 part whose bit fields are disjoint or swizzled against each other:
+//     bits 7-8: q   | bits 4-6: k1 bits 2-4 | bits 2-3: (k1 ^ q) & 3 | bit 1: (l >> 1) ^ (k1 >> 2) & 1 | bit 0: l & 1
+// so a phase computes the part that depends on the THREAD once and every access is one XOR with a compile-time constant (the
+// unswizzled bits even fold into the instruction's immediate offset) instead of four or five logic instructions per access.
+LNX_HDC int e1_ql(int q, int l) { return q * 128 + ((q & 3) << 2) + (((l >> 1) & 1) << 1) + (l & 1); }
+LNX_HDC int e1_k(int k1) { return ((k1 & 28) << 2) + ((k1 & 3) << 2) + (((k1 >> 2) & 1) << 1); }
+LNX_HDC int e1_k_lo(int k1) { return e1_k(k1) & 0xE; }    // the bits swizzled against (q, l)
+LNX_HDC int e1_k_hi(int k1) { return e1_k(k1) & ~0xE; }   // plain offset
+LNX_HDC int e1_ql_lo(int q, int l) { return e1_ql(q, l) & 0xE; }
+LNX_HDC int e1_ql_hi(int q, int l) { return e1_ql(q, l) & ~0xE; }
+LNX_HDC int e1_addr(int q, int k1, int l) { return e1_ql(q, l) ^ e1_k(k1); }
+// E2 view [col][unit u][2]: unit = the pair of m2 handled together by a P3 thread.  = e2_col(col) ^ (u << 1)
+LNX_HDC int e2_col(int col) { return col * 8 + (((col >> 1) & 3) << 1); }
+LNX_HDC int e2_addr(int col, int u) { return e2_col(col) ^ (u << 1); }
 
 // ---- twiddle table setup (once per kernel, threads 0..15 fill row `tid` of both tables) ----------------------------
 LNX_HD void init_twiddle_table(int tid, float4* table, const float2* tw128 /* [128] = (cos, sin)(2 pi k / 128) */) {
@@ -101,16 +110,17 @@ LNX_HD float2 tw_inv(float2 d, float2 tw) { return rot_inv(d, tw.x, tw.y); }
 // P1: v[j] = (a[p][4j+l], a[p+64][4j+l]) already loaded by the caller.  radix-32 DIF, store E1.
 // =================================================================================================================
 template <int POS>
-LNX_HD void p1_store(const Regs& R, float2* reg, int q, int l) {
+LNX_HD void p1_store(const Regs& R, float2* reg, int ql) {  // ql = e1_ql(q, l) of this thread
     if constexpr (POS < 32) {
-        reg[e1_addr(q, bitrev(POS, 5), l)] = R.v[POS];
-        p1_store<POS + 1>(R, reg, q, l);
+        constexpr int k1 = bitrev(POS, 5);
+        reg[(ql ^ e1_k_lo(k1)) + e1_k_hi(k1)] = R.v[POS];
+        p1_store<POS + 1>(R, reg, ql);
     }
 }
 LNX_HD void phase1(int tid, Regs& R, float2* W) {
-    const int sub = t_sub(tid), q = sub >> 2, l = sub & 3;
+    const int sub = t_sub(tid);
     fft_dif<32>(R.v);
-    p1_store<0>(R, W + t_group(tid) * REGION, q, l);
+    p1_store<0>(R, W + t_group(tid) * REGION, e1_ql(sub >> 2, sub & 3));
 }
 
 // =================================================================================================================
@@ -119,14 +129,14 @@ LNX_HD void phase1(int tid, Regs& R, float2* W) {
 LNX_HD void phase2_load(int tid, Regs& R, const float2* W) {
     const int a = t_sub(tid);
     const float4* reg4 = reinterpret_cast<const float4*>(W + t_group(tid) * REGION);
+    const int ks[2] = {e1_k(k1_of(a, 0)) >> 1, e1_k(k1_of(a, 1)) >> 1};  // float4 index: bit 0 of the element index is l & 1 = 0
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            const int k1 = k1_of(a, s);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const float4 t = reg4[e1_addr(q, k1, 2 * h) >> 1];
+                const float4 t = reg4[(ks[s] ^ (e1_ql_lo(q, 2 * h) >> 1)) + (e1_ql_hi(q, 2 * h) >> 1)];
                 R.v[q * 8 + s * 4 + 2 * h] = make_float2(t.x, t.y);
                 R.v[q * 8 + s * 4 + 2 * h + 1] = make_float2(t.z, t.w);
             }
@@ -222,11 +232,11 @@ LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W, const float4* twta
         fft_dif<8>(hc);  // over i; output position pos <-> m2 = bitrev3(pos)
 #pragma unroll
         for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_fwd(hc[pos], T.twc[bitrev(pos, 3) - 1]);
-        const int col = col_of(a, c);
+        const int ec = e2_col(col_of(a, c)) >> 1;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const float2 f = hc[unit_pos(u, 0)], g = hc[unit_pos(u, 1)];
-            reg4[e2_addr(col, u) >> 1] = make_float4(f.x, f.y, g.x, g.y);
+            reg4[ec ^ u] = make_float4(f.x, f.y, g.x, g.y);
         }
     }
 }
@@ -328,10 +338,10 @@ LNX_HD void phase4_load(int tid, Regs& R, const float2* W) {
     const float4* reg4 = reinterpret_cast<const float4*>(W + t_group(tid) * REGION);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const int col = col_of(a, c);
+        const int ec = e2_col(col_of(a, c)) >> 1;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float4 t = reg4[e2_addr(col, u) >> 1];
+            const float4 t = reg4[ec ^ u];
             R.v[c * 8 + unit_pos(u, 0)] = make_float2(t.x, t.y);
             R.v[c * 8 + unit_pos(u, 1)] = make_float2(t.z, t.w);
         }
@@ -354,6 +364,7 @@ LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W, const float4* twta
     else
         p4_retangle<false>(R.v, z);
     float4* reg4 = reinterpret_cast<float4*>(W + t_group(tid) * REGION);
+    const int ks[2] = {e1_k(k1_of(a, 0)) >> 1, e1_k(k1_of(a, 1)) >> 1};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -366,9 +377,8 @@ LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W, const float4* twta
             const float2 u2 = tw_inv(csub(t0, t2), T.twr[s][1]);
             const float2 u1 = tw_inv(cadd(t1, t3), T.twr[s][0]);
             const float2 u3 = tw_inv(csub(t1, t3), T.twr[s][2]);
-            const int k1 = k1_of(a, s);
-            reg4[e1_addr(q, k1, 0) >> 1] = make_float4(u0.x, u0.y, u1.x, u1.y);
-            reg4[e1_addr(q, k1, 2) >> 1] = make_float4(u2.x, u2.y, u3.x, u3.y);
+            reg4[(ks[s] ^ (e1_ql_lo(q, 0) >> 1)) + (e1_ql_hi(q, 0) >> 1)] = make_float4(u0.x, u0.y, u1.x, u1.y);
+            reg4[(ks[s] ^ (e1_ql_lo(q, 2) >> 1)) + (e1_ql_hi(q, 2) >> 1)] = make_float4(u2.x, u2.y, u3.x, u3.y);
         }
 }
 
@@ -376,15 +386,16 @@ LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W, const float4* twta
 // P5: load E1, radix-32 inverse DIT -> v[j] = (potential[p][4j+l], potential[p+64][4j+l])
 // =================================================================================================================
 template <int POS>
-LNX_HD void p5_load(Regs& R, const float2* reg, int q, int l) {
+LNX_HD void p5_load(Regs& R, const float2* reg, int ql) {
     if constexpr (POS < 32) {
-        R.v[POS] = reg[e1_addr(q, bitrev(POS, 5), l)];
-        p5_load<POS + 1>(R, reg, q, l);
+        constexpr int k1 = bitrev(POS, 5);
+        R.v[POS] = reg[(ql ^ e1_k_lo(k1)) + e1_k_hi(k1)];
+        p5_load<POS + 1>(R, reg, ql);
     }
 }
 LNX_HD void phase5_load(int tid, Regs& R, const float2* W) {
     const int sub = t_sub(tid);
-    p5_load<0>(R, W + t_group(tid) * REGION, sub >> 2, sub & 3);
+    p5_load<0>(R, W + t_group(tid) * REGION, e1_ql(sub >> 2, sub & 3));
 }
 LNX_HD void phase5_ifft(Regs& R) { ifft_dit<32>(R.v); }
 
