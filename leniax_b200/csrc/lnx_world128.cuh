@@ -65,6 +65,17 @@ LNX_HDC int e1_k_hi(int k1) { return e1_k(k1) & ~0xE; }   // plain offset
 LNX_HDC int e1_ql_lo(int q, int l) { return e1_ql(q, l) & 0xE; }
 LNX_HDC int e1_ql_hi(int q, int l) { return e1_ql(q, l) & ~0xE; }
 LNX_HDC int e1_addr(int q, int k1, int l) { return e1_ql(q, l) ^ e1_k(k1); }
+// &base[idx ^ x] for a swizzle x < 16 elements, with the XOR applied to the BYTE offset: `idx * sizeof(T)` is computed once per phase
+// and every access is one logic instruction away from it (index, scale and base were rebuilt for each access before: three
+// instructions); the pointer stays "array + integer offset", so the compiler still sees shared memory
+template <class T>
+LNX_HD T* swz(T* base, int idx_bytes, int x) {
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + (idx_bytes ^ (x * (int)sizeof(T))));
+}
+template <class T>
+LNX_HD const T* swz(const T* base, int idx_bytes, int x) {
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (idx_bytes ^ (x * (int)sizeof(T))));
+}
 // E2 view [col][unit u][2]: unit = the pair of m2 handled together by a P3 thread.  = e2_col(col) ^ (u << 1)
 LNX_HDC int e2_col(int col) { return col * 8 + (((col >> 1) & 3) << 1); }
 LNX_HDC int e2_addr(int col, int u) { return e2_col(col) ^ (u << 1); }
@@ -110,17 +121,17 @@ LNX_HD float2 tw_inv(float2 d, float2 tw) { return rot_inv(d, tw.x, tw.y); }
 // P1: v[j] = (a[p][4j+l], a[p+64][4j+l]) already loaded by the caller.  radix-32 DIF, store E1.
 // =================================================================================================================
 template <int POS>
-LNX_HD void p1_store(const Regs& R, float2* reg, int ql) {  // ql = e1_ql(q, l) of this thread
+LNX_HD void p1_store(const Regs& R, float2* reg, int ql) {  // reg = W, ql = byte offset of element e1_ql(q, l) of this thread's region
     if constexpr (POS < 32) {
         constexpr int k1 = bitrev(POS, 5);
-        reg[(ql ^ e1_k_lo(k1)) + e1_k_hi(k1)] = R.v[POS];
+        swz(reg, ql, e1_k_lo(k1))[e1_k_hi(k1)] = R.v[POS];
         p1_store<POS + 1>(R, reg, ql);
     }
 }
 LNX_HD void phase1(int tid, Regs& R, float2* W) {
     const int sub = t_sub(tid);
     fft_dif<32>(R.v);
-    p1_store<0>(R, W + t_group(tid) * REGION, e1_ql(sub >> 2, sub & 3));
+    p1_store<0>(R, W, (t_group(tid) * REGION + e1_ql(sub >> 2, sub & 3)) * (int)sizeof(float2));
 }
 
 // =================================================================================================================
@@ -128,15 +139,16 @@ LNX_HD void phase1(int tid, Regs& R, float2* W) {
 // =================================================================================================================
 LNX_HD void phase2_load(int tid, Regs& R, const float2* W) {
     const int a = t_sub(tid);
-    const float4* reg4 = reinterpret_cast<const float4*>(W + t_group(tid) * REGION);
-    const int ks[2] = {e1_k(k1_of(a, 0)) >> 1, e1_k(k1_of(a, 1)) >> 1};  // float4 index: bit 0 of the element index is l & 1 = 0
+    const float4* reg4 = reinterpret_cast<const float4*>(W);
+    const int g4 = t_group(tid) * (REGION / 2);  // float4 index: bit 0 of the element index is l & 1 = 0
+    const int ks[2] = {(g4 + (e1_k(k1_of(a, 0)) >> 1)) * (int)sizeof(float4), (g4 + (e1_k(k1_of(a, 1)) >> 1)) * (int)sizeof(float4)};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const float4 t = reg4[(ks[s] ^ (e1_ql_lo(q, 2 * h) >> 1)) + (e1_ql_hi(q, 2 * h) >> 1)];
+                const float4 t = swz(reg4, ks[s], e1_ql_lo(q, 2 * h) >> 1)[e1_ql_hi(q, 2 * h) >> 1];
                 R.v[q * 8 + s * 4 + 2 * h] = make_float2(t.x, t.y);
                 R.v[q * 8 + s * 4 + 2 * h + 1] = make_float2(t.z, t.w);
             }
@@ -225,18 +237,19 @@ LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W, const float4* twta
         p2_untangle<true>(R.v, h);
     else
         p2_untangle<false>(R.v, h);
-    float4* reg4 = reinterpret_cast<float4*>(W + t_group(tid) * REGION);
+    float4* reg4 = reinterpret_cast<float4*>(W);
+    const int g4 = t_group(tid) * (REGION / 2);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float2* hc = h + c * 8;
         fft_dif<8>(hc);  // over i; output position pos <-> m2 = bitrev3(pos)
 #pragma unroll
         for (int pos = 1; pos < 8; ++pos) hc[pos] = tw_fwd(hc[pos], T.twc[bitrev(pos, 3) - 1]);
-        const int ec = e2_col(col_of(a, c)) >> 1;
+        const int ec = (g4 + (e2_col(col_of(a, c)) >> 1)) * (int)sizeof(float4);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const float2 f = hc[unit_pos(u, 0)], g = hc[unit_pos(u, 1)];
-            reg4[ec ^ u] = make_float4(f.x, f.y, g.x, g.y);
+            *swz(reg4, ec, u) = make_float4(f.x, f.y, g.x, g.y);
         }
     }
 }
@@ -335,13 +348,14 @@ LNX_HD void phase3_multiply(int tid, Regs& R, const float4* Kt) { p3_mul_generic
 // =================================================================================================================
 LNX_HD void phase4_load(int tid, Regs& R, const float2* W) {
     const int a = t_sub(tid);
-    const float4* reg4 = reinterpret_cast<const float4*>(W + t_group(tid) * REGION);
+    const float4* reg4 = reinterpret_cast<const float4*>(W);
+    const int g4 = t_group(tid) * (REGION / 2);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const int ec = e2_col(col_of(a, c)) >> 1;
+        const int ec = (g4 + (e2_col(col_of(a, c)) >> 1)) * (int)sizeof(float4);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const float4 t = reg4[ec ^ u];
+            const float4 t = *swz(reg4, ec, u);
             R.v[c * 8 + unit_pos(u, 0)] = make_float2(t.x, t.y);
             R.v[c * 8 + unit_pos(u, 1)] = make_float2(t.z, t.w);
         }
@@ -363,8 +377,9 @@ LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W, const float4* twta
         p4_retangle<true>(R.v, z);
     else
         p4_retangle<false>(R.v, z);
-    float4* reg4 = reinterpret_cast<float4*>(W + t_group(tid) * REGION);
-    const int ks[2] = {e1_k(k1_of(a, 0)) >> 1, e1_k(k1_of(a, 1)) >> 1};
+    float4* reg4 = reinterpret_cast<float4*>(W);
+    const int g4 = t_group(tid) * (REGION / 2);
+    const int ks[2] = {(g4 + (e1_k(k1_of(a, 0)) >> 1)) * (int)sizeof(float4), (g4 + (e1_k(k1_of(a, 1)) >> 1)) * (int)sizeof(float4)};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -377,8 +392,8 @@ LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W, const float4* twta
             const float2 u2 = tw_inv(csub(t0, t2), T.twr[s][1]);
             const float2 u1 = tw_inv(cadd(t1, t3), T.twr[s][0]);
             const float2 u3 = tw_inv(csub(t1, t3), T.twr[s][2]);
-            reg4[(ks[s] ^ (e1_ql_lo(q, 0) >> 1)) + (e1_ql_hi(q, 0) >> 1)] = make_float4(u0.x, u0.y, u1.x, u1.y);
-            reg4[(ks[s] ^ (e1_ql_lo(q, 2) >> 1)) + (e1_ql_hi(q, 2) >> 1)] = make_float4(u2.x, u2.y, u3.x, u3.y);
+            swz(reg4, ks[s], e1_ql_lo(q, 0) >> 1)[e1_ql_hi(q, 0) >> 1] = make_float4(u0.x, u0.y, u1.x, u1.y);
+            swz(reg4, ks[s], e1_ql_lo(q, 2) >> 1)[e1_ql_hi(q, 2) >> 1] = make_float4(u2.x, u2.y, u3.x, u3.y);
         }
 }
 
@@ -389,13 +404,13 @@ template <int POS>
 LNX_HD void p5_load(Regs& R, const float2* reg, int ql) {
     if constexpr (POS < 32) {
         constexpr int k1 = bitrev(POS, 5);
-        R.v[POS] = reg[(ql ^ e1_k_lo(k1)) + e1_k_hi(k1)];
+        R.v[POS] = swz(reg, ql, e1_k_lo(k1))[e1_k_hi(k1)];
         p5_load<POS + 1>(R, reg, ql);
     }
 }
 LNX_HD void phase5_load(int tid, Regs& R, const float2* W) {
     const int sub = t_sub(tid);
-    p5_load<0>(R, W + t_group(tid) * REGION, e1_ql(sub >> 2, sub & 3));
+    p5_load<0>(R, W, (t_group(tid) * REGION + e1_ql(sub >> 2, sub & 3)) * (int)sizeof(float2));
 }
 LNX_HD void phase5_ifft(Regs& R) { ifft_dit<32>(R.v); }
 
