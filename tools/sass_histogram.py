@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'leniax_b200', 'libleniax_b200.so')
 out = subprocess.run(['cuobjdump', '-sass', LIB], capture_output=True, text=True).stdout
 fams = collections.OrderedDict((k, collections.Counter()) for k in ('lnx_world128_tm', 'lnx_world128_gen2', 'lnx_world128_gen_tm', 'lnx_world128_generic',
-                                                                  't64::', 't2k::', 'tiled::', 'setup::', 'other'))
+                                                                  't64h::', 't64::', 't2k::', 'tiled::', 'setup::', 'other'))
 n_kernels = collections.Counter()
 fam = None
 for line in out.splitlines():
