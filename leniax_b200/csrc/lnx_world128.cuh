@@ -166,43 +166,38 @@ LNX_HD void retangle_pair(float2 A, float2 B, float2& z, float2& zc) {
     zc = pk_add(make_float2(A.x, -A.y), pk_swap(B));
 }
 
-template <bool A0>
-LNX_HD void p2_untangle(const float2* z /* [q*8 + s*4 + k2] */, float2* h /* [c*8 + i] */) {
+// Lanes a = 0 (k1 in {0, 16}: columns {0|64 packed, 32, 16, 48}) pair the entries differently from lanes a > 0 (columns a, a+32, 32-a,
+// 64-a).  Both cases run through the SAME instructions with per-lane selects: every warp holds two a = 0 lanes, so a branch made each
+// warp execute both variants one after the other (and merge their registers with ~40 moves) in phase 2 and in phase 4.
+LNX_HD float2 sel2(bool c, float2 x, float2 y) { return make_float2(c ? x.x : y.x, c ? x.y : y.y); }
+LNX_HD void p2_untangle(bool a0, const float2* z /* [q*8 + s*4 + k2] */, float2* h /* [c*8 + i] */) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float2* zq = z + q * 8;
-        if constexpr (A0) {
-            // k1 in {0,16}: columns {0|64 packed, 32, 16, 48}
-            h[0 * 8 + q] = make_float2(2.f * zq[0].x, 2.f * zq[2].x);
-            h[0 * 8 + q + 4] = make_float2(2.f * zq[0].y, 2.f * zq[2].y);
-            untangle_pair(zq[1], zq[3], h[1 * 8 + q], h[1 * 8 + q + 4]);          // 32 <-> 96
-            untangle_pair(zq[4 + 0], zq[4 + 3], h[2 * 8 + q], h[2 * 8 + q + 4]);  // 16 <-> 112
-            untangle_pair(zq[4 + 1], zq[4 + 2], h[3 * 8 + q], h[3 * 8 + q + 4]);  // 48 <-> 80
-        } else {
-            untangle_pair(zq[0], zq[4 + 3], h[0 * 8 + q], h[0 * 8 + q + 4]);  // a      <-> (32-a)+96
-            untangle_pair(zq[1], zq[4 + 2], h[1 * 8 + q], h[1 * 8 + q + 4]);  // a+32   <-> (32-a)+64
-            untangle_pair(zq[4 + 0], zq[3], h[2 * 8 + q], h[2 * 8 + q + 4]);  // 32-a   <-> a+96
-            untangle_pair(zq[4 + 1], zq[2], h[3 * 8 + q], h[3 * 8 + q + 4]);  // 64-a   <-> a+64
-        }
+        // a > 0: a <-> (32-a)+96, a+32 <-> (32-a)+64, 32-a <-> a+96, 64-a <-> a+64;   a = 0: 32 <-> 96, 16 <-> 112, 48 <-> 80
+        float2 g0, g0b;
+        untangle_pair(zq[0], zq[4 + 3], g0, g0b);
+        h[0 * 8 + q] = sel2(a0, make_float2(2.f * zq[0].x, 2.f * zq[2].x), g0);
+        h[0 * 8 + q + 4] = sel2(a0, make_float2(2.f * zq[0].y, 2.f * zq[2].y), g0b);
+        untangle_pair(zq[1], sel2(a0, zq[3], zq[4 + 2]), h[1 * 8 + q], h[1 * 8 + q + 4]);
+        untangle_pair(zq[4 + 0], sel2(a0, zq[4 + 3], zq[3]), h[2 * 8 + q], h[2 * 8 + q + 4]);
+        untangle_pair(zq[4 + 1], sel2(a0, zq[4 + 2], zq[2]), h[3 * 8 + q], h[3 * 8 + q + 4]);
     }
 }
-template <bool A0>
-LNX_HD void p4_retangle(const float2* h /* [c*8 + i] */, float2* z /* [q*8 + s*4 + k2] */) {
+LNX_HD void p4_retangle(bool a0, const float2* h /* [c*8 + i] */, float2* z /* [q*8 + s*4 + k2] */) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float2* zq = z + q * 8;
-        if constexpr (A0) {
-            zq[0] = make_float2(h[0 * 8 + q].x, h[0 * 8 + q + 4].x);
-            zq[2] = make_float2(h[0 * 8 + q].y, h[0 * 8 + q + 4].y);
-            retangle_pair(h[1 * 8 + q], h[1 * 8 + q + 4], zq[1], zq[3]);
-            retangle_pair(h[2 * 8 + q], h[2 * 8 + q + 4], zq[4 + 0], zq[4 + 3]);
-            retangle_pair(h[3 * 8 + q], h[3 * 8 + q + 4], zq[4 + 1], zq[4 + 2]);
-        } else {
-            retangle_pair(h[0 * 8 + q], h[0 * 8 + q + 4], zq[0], zq[4 + 3]);
-            retangle_pair(h[1 * 8 + q], h[1 * 8 + q + 4], zq[1], zq[4 + 2]);
-            retangle_pair(h[2 * 8 + q], h[2 * 8 + q + 4], zq[4 + 0], zq[3]);
-            retangle_pair(h[3 * 8 + q], h[3 * 8 + q + 4], zq[4 + 1], zq[2]);
-        }
+        float2 u0, v0, v1, v2, v3;
+        retangle_pair(h[0 * 8 + q], h[0 * 8 + q + 4], u0, v0);
+        retangle_pair(h[1 * 8 + q], h[1 * 8 + q + 4], zq[1], v1);
+        retangle_pair(h[2 * 8 + q], h[2 * 8 + q + 4], zq[4 + 0], v2);
+        retangle_pair(h[3 * 8 + q], h[3 * 8 + q + 4], zq[4 + 1], v3);
+        zq[0] = sel2(a0, make_float2(h[0 * 8 + q].x, h[0 * 8 + q + 4].x), u0);
+        zq[2] = sel2(a0, make_float2(h[0 * 8 + q].y, h[0 * 8 + q + 4].y), v3);
+        zq[3] = sel2(a0, v1, v2);
+        zq[4 + 2] = sel2(a0, v3, v1);
+        zq[4 + 3] = sel2(a0, v2, v0);
     }
 }
 
@@ -233,10 +228,7 @@ LNX_HD void phase2_compute_store(int tid, Regs& R, float2* W, const float4* twta
             y[3] = csub(t1, t3);
         }
     float2 h[32];
-    if (a == 0)
-        p2_untangle<true>(R.v, h);
-    else
-        p2_untangle<false>(R.v, h);
+    p2_untangle(a == 0, R.v, h);
     float4* reg4 = reinterpret_cast<float4*>(W);
     const int g4 = t_group(tid) * (REGION / 2);
 #pragma unroll
@@ -373,10 +365,7 @@ LNX_HD void phase4_compute_store(int tid, Regs& R, float2* W, const float4* twta
         ifft_dit<8>(hc);  // -> natural i
     }
     float2 z[32];
-    if (a == 0)
-        p4_retangle<true>(R.v, z);
-    else
-        p4_retangle<false>(R.v, z);
+    p4_retangle(a == 0, R.v, z);
     float4* reg4 = reinterpret_cast<float4*>(W);
     const int g4 = t_group(tid) * (REGION / 2);
     const int ks[2] = {(g4 + (e1_k(k1_of(a, 0)) >> 1)) * (int)sizeof(float4), (g4 + (e1_k(k1_of(a, 1)) >> 1)) * (int)sizeof(float4)};
