@@ -87,7 +87,9 @@ typedef enum {
 typedef struct {
     int32_t nb_dims;                     /* world dimensions: 2 or 3 */
     int32_t dims[3];                     /* world size per dimension, powers of two in [8, 4096]; 128x128 worlds run in the
-                                            shared-memory resident kernels, everything else in the tiled multi-pass engine */
+                                            shared-memory resident kernels, everything else in the tiled multi-pass engine.
+                                            Any other size in [1, 4096] gives a plan that serves lnx_compute_stats only: such
+                                            worlds are stepped by lnx_update_conv (2-D), the FFT entry points refuse the plan */
     int32_t nb_channels;                 /* C */
     int32_t nb_kernels;                  /* K = number of true kernels (after tc_indices) */
     int32_t nb_slots;                    /* C * max_k_per_channel = leading size of the reference's K tensor */

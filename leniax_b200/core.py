@@ -110,6 +110,14 @@ def update(rng_key, state, K, gf_params, kernels_weight_per_channel, dt, get_pot
     slots, c_in, gf_ids = ufn.kernel_layout(C)
     if not get_potential_fn.fft:
         return update_conv(state_t, K, gf_params, kernels_weight_per_channel, dt, ufn)
+    from . import kernels as _kernels
+    if not _kernels.is_pow2_world(world_size):
+        # the FFT engines need powers of two; the reference's fftn does not (core.py:81): same potential by direct convolution
+        Kt = engine.as_device_tensor(K, torch.complex64, dev)
+        taps = _kernels.spatial_from_spectrum(Kt, get_potential_fn.nb_slots, world_size)
+        import dataclasses
+        conv_ufn = UpdateFn(dataclasses.replace(get_potential_fn, fft=False), get_field_fn, sfn)
+        return update_conv(state_t, taps, gf_params, kernels_weight_per_channel, dt, conv_ufn)
     dt_t = engine.as_device_tensor(dt, torch.float32, dev).reshape(-1)[:1]
     plan = engine.Plan.get(world_size=world_size, nb_channels=C, slots=slots, c_in=c_in, gf_ids=gf_ids,
                            nb_slots=get_potential_fn.nb_slots, state_fn=sfn.slug, weighted_average=get_field_fn.average,

@@ -68,6 +68,8 @@ struct lnx_plan {
     int device;
     int sm_count;
     bool tiled;            // false: resident 128x128 kernels, true: multi-pass tiled engine
+    bool stats_only;       // world size is not a power of two: the plan serves lnx_compute_stats only (the scans need powers of two;
+                           // the direct-convolution update lnx_update_conv takes any 2-D size and needs no plan)
     lnx::tiled::Geom g;    // tiled engine geometry
 };
 
@@ -82,6 +84,31 @@ static int ilog2i(int n) {
     int l = 0;
     while ((1 << l) < n) ++l;
     return l;
+}
+// geometry of a world of ANY size for the stand-alone statistics (lnx_compute_stats): one leading index per slab
+static bool make_geom_any(int nd, const int32_t* dims, Geom* g, const char** why) {
+    memset(g, 0, sizeof(*g));
+    if (nd != 2 && nd != 3) {
+        *why = "only 2-D and 3-D worlds are supported";
+        return false;
+    }
+    for (int d = 0; d < nd; ++d) {
+        if (dims[d] < 1 || dims[d] > NMAX) {
+            *why = "every world dimension must be in [1, 4096]";
+            return false;
+        }
+        g->dims[d] = dims[d];
+    }
+    g->nd = nd;
+    g->L = dims[0];
+    g->A1 = nd == 3 ? dims[1] : 1;
+    g->A2 = dims[nd - 1];
+    g->rows = g->L * g->A1;
+    g->cells = (long long)g->rows * g->A2;
+    g->slab_rows = g->A1;
+    g->n_slabs = g->L;
+    g->any_size = 1;
+    return true;
 }
 static bool make_geom(int nd, const int32_t* dims, Geom* g, const char** why) {
     memset(g, 0, sizeof(*g));
@@ -390,12 +417,16 @@ int lnx_plan_create(const lnx_desc* d, lnx_plan** out) {
     const bool resident = d->nb_dims == 2 && d->dims[0] == WS && d->dims[1] == WS && !(d->flags & LNX_PLAN_FORCE_TILED);
     lnx::tiled::Geom geom;
     memset(&geom, 0, sizeof(geom));
+    bool stats_only = false;
     if (!resident) {
         const char* why = "";
-        if (!th::make_geom(d->nb_dims, d->dims, &geom, &why))
-            return fail(LNX_ERR_UNSUPPORTED, "unsupported world shape (nb_dims=%d, dims=%d x %d x %d): %s", d->nb_dims, d->dims[0], d->dims[1],
-                        d->nb_dims > 2 ? d->dims[2] : 1, why);
-        if (th::smem_a(geom) > th::SMEM_LIMIT || th::smem_b(geom) > th::SMEM_LIMIT || th::smem_c(geom, d->nb_channels) > th::SMEM_LIMIT)
+        if (!th::make_geom(d->nb_dims, d->dims, &geom, &why)) {
+            if (!th::make_geom_any(d->nb_dims, d->dims, &geom, &why))
+                return fail(LNX_ERR_UNSUPPORTED, "unsupported world shape (nb_dims=%d, dims=%d x %d x %d): %s", d->nb_dims, d->dims[0],
+                            d->dims[1], d->nb_dims > 2 ? d->dims[2] : 1, why);
+            stats_only = true;
+        }
+        if (!stats_only && (th::smem_a(geom) > th::SMEM_LIMIT || th::smem_b(geom) > th::SMEM_LIMIT || th::smem_c(geom, d->nb_channels) > th::SMEM_LIMIT))
             return fail(LNX_ERR_UNSUPPORTED, "world too large for the tiled engine's shared-memory slabs (A %zu, B %zu, C %zu bytes)",
                         th::smem_a(geom), th::smem_b(geom), th::smem_c(geom, d->nb_channels));
     }
@@ -420,8 +451,9 @@ int lnx_plan_create(const lnx_desc* d, lnx_plan** out) {
     p->device = dev;
     p->sm_count = sms;
     p->tiled = !resident;
+    p->stats_only = stats_only;
     p->g = geom;
-    if (p->tiled && th::ensure_tiled_init(dev) != LNX_OK) {
+    if (p->tiled && !stats_only && th::ensure_tiled_init(dev) != LNX_OK) {
         delete p;
         return LNX_ERR_CUDA;  // message set by ensure_tiled_init
     }
@@ -438,6 +470,7 @@ int lnx_plan_destroy(lnx_plan* p) {
 size_t lnx_workspace_bytes(const lnx_plan* p);
 
 size_t lnx_kernel_table_bytes(const lnx_plan* p) {
+    if (p && p->stats_only) return 0;
     if (!p) return 0;
     // 2048^2 one-channel one-kernel plans hold the table twice: [n_sols][spec] in the generic layout, then in lnx_tiled2k.cuh's
     if (p->tiled) return (size_t)(th::line2k_plan(p->g, p->d.nb_channels, p->d.nb_kernels) ? 2 : 1) * p->d.nb_kernels * p->g.spec * sizeof(float2);
@@ -445,12 +478,14 @@ size_t lnx_kernel_table_bytes(const lnx_plan* p) {
 }
 
 size_t lnx_workspace_bytes_for(const lnx_plan* p, int32_t n_sols, int32_t n_init) {
+    if (p && p->stats_only) return 0;
     if (!p) return 0;
     if (!p->tiled) return lnx_workspace_bytes(p);
     return th::carve(p->g, p->d.nb_channels, p->d.nb_kernels, (long long)n_sols * n_init, nullptr).bytes;
 }
 
 size_t lnx_workspace_bytes(const lnx_plan* p) {
+    if (p && p->stats_only) return 0;
     if (!p) return 0;
     if (p->tiled) return th::carve(p->g, p->d.nb_channels, p->d.nb_kernels, 1, nullptr).bytes;
     // 256 B header (world queue counter) + per-CTA scratch of the multi-channel kernels: [3][C] thread-private images for one CTA per SM
@@ -460,6 +495,7 @@ size_t lnx_workspace_bytes(const lnx_plan* p) {
 }
 
 int lnx_kernels_prepare(const lnx_plan* p, int32_t n_sols, const void* K_fft, void* table, void* stream) {
+    if (p && p->stats_only) return fail(LNX_ERR_UNSUPPORTED, "this plan describes a world whose size is not a power of two: it serves lnx_compute_stats only (lnx_update_conv steps such worlds; the FFT scans need powers of two)");
     if (!p || !K_fft || !table || n_sols < 1) return fail(LNX_ERR_INVALID, "lnx_kernels_prepare: bad argument");
     if (p->tiled) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -483,6 +519,7 @@ int lnx_kernels_prepare(const lnx_plan* p, int32_t n_sols, const void* K_fft, vo
 }
 
 int lnx_rfft2(const lnx_plan* p, int32_t n_images, const float* images, void* spectra, void* stream) {
+    if (p && p->stats_only) return fail(LNX_ERR_UNSUPPORTED, "this plan describes a world whose size is not a power of two: it serves lnx_compute_stats only (lnx_update_conv steps such worlds; the FFT scans need powers of two)");
     (void)p;  // the plan is optional here
     if (!images || !spectra || n_images < 1) return fail(LNX_ERR_INVALID, "lnx_rfft2: bad argument");
     const int rc = ensure_device_init(nullptr, nullptr);
@@ -547,7 +584,8 @@ int lnx_compute_stats(const lnx_plan* p, int32_t n_worlds, const float* cells, c
     if (n_worlds > 65535) return fail(LNX_ERR_INVALID, "lnx_compute_stats: at most 65535 worlds per call");
     Geom g;
     const char* why = "";
-    if (!th::make_geom(p->d.nb_dims, p->d.dims, &g, &why)) return fail(LNX_ERR_UNSUPPORTED, "lnx_compute_stats: %s", why);
+    if (!th::make_geom(p->d.nb_dims, p->d.dims, &g, &why) && !th::make_geom_any(p->d.nb_dims, p->d.dims, &g, &why))
+        return fail(LNX_ERR_UNSUPPORTED, "lnx_compute_stats: %s", why);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* partials = nullptr;
     WorldCarry* carry = nullptr;
@@ -902,6 +940,7 @@ int lnx_gen2_schedule(const lnx_desc* d, int32_t* acc_slot, int32_t* acc_first, 
 }
 
 const char* lnx_run_scan_variant(const lnx_plan* p, int32_t with_trajectory) {
+    if (p && p->stats_only) return "unsupported";
     if (!p) return "";
     if (p->tiled) return "tiled";
     if (use_fused(p, with_trajectory != 0)) return "fused";
@@ -913,6 +952,7 @@ int lnx_run_scan(const lnx_plan* p, int32_t n_sols, int32_t n_init, int32_t max_
                  const void* table, const float* gf_params, const float* weights, const float* dt, float* stats, float* channel_mass,
                  float* n_alive, float* final_cells, float* cells_out, float* field_out, float* potential_out, void* workspace,
                  size_t workspace_bytes, void* stream) {
+    if (p && p->stats_only) return fail(LNX_ERR_UNSUPPORTED, "this plan describes a world whose size is not a power of two: it serves lnx_compute_stats only (lnx_update_conv steps such worlds; the FFT scans need powers of two)");
     if (!p) return fail(LNX_ERR_INVALID, "lnx_run_scan: null plan");
     if (n_sols < 1 || n_init < 1) return fail(LNX_ERR_INVALID, "lnx_run_scan: n_sols and n_init must be >= 1");
     if (max_run_iter < 1) return fail(LNX_ERR_INVALID, "max_run_iter must be positive, value given: %d", max_run_iter);  // runner.py:51
@@ -1001,6 +1041,7 @@ int lnx_summarize_stats(const float* const* planes, const float* n_alive, int32_
 
 int lnx_update(const lnx_plan* p, int32_t n_worlds, const float* state, const void* table, const float* gf_params, const float* weights,
                const float* dt, float* state_out, float* field_out, float* potential_out, void* stream) {
+    if (p && p->stats_only) return fail(LNX_ERR_UNSUPPORTED, "this plan describes a world whose size is not a power of two: it serves lnx_compute_stats only (lnx_update_conv steps such worlds; the FFT scans need powers of two)");
     if (!p || !state || !table || !gf_params || !weights || !dt || !state_out || !field_out || !potential_out || n_worlds < 1)
         return fail(LNX_ERR_INVALID, "lnx_update: bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -32,6 +32,8 @@ struct Geom {
     long long cells;      // L * A1 * A2
     long long spec;       // rows * half complex values per (world, channel)
     int tc;          // pass B tile width (inner spectral columns per CTA)
+    int any_size;    // 1: dims are not all powers of two - only the stand-alone statistics accept such a geometry (division / modulo
+                     // instead of shifts / masks); the scan engines never see it
 };
 
 __device__ __forceinline__ int brev_n(int x, int logn) { return (int)(__brev((unsigned)x) >> (32 - logn)); }
@@ -559,7 +561,7 @@ __device__ __forceinline__ void pass_d_body(const PassDArgs& P, const int w, con
     out[ST_INERTIA] = inertia;
     for (int d = 0; d < nd; ++d) {
         const int s = trunc_to_int(cen[d]);
-        S.shift[d] = (S.shift[d] + s) & (g.dims[d] - 1);
+        S.shift[d] = py_mod(S.shift[d] + s, g.dims[d]);  // (= the mask for powers of two)
         S.centroid[d] = cen[d] - (float)s;
     }
     S.angle = angle;
@@ -629,12 +631,12 @@ __global__ void __launch_bounds__(TPB) stats_partials_kernel(StatsPartialArgs P)
         const float* fi = P.field + ((size_t)w * P.C + c) * g.cells + off;
         float m00 = 0.f;
         for (int i = threadIdx.x; i < slab_cells; i += blockDim.x) {
-            const size_t grow = (size_t)slab * g.slab_rows + (i >> g.logA2);
-            const int n = i & (g.A2 - 1);
+            const size_t grow = (size_t)slab * g.slab_rows + (g.any_size ? i / g.A2 : (i >> g.logA2));
+            const int n = g.any_size ? i % g.A2 : (i & (g.A2 - 1));
             int idx[3];
             if (g.nd == 3) {
-                idx[0] = (int)(grow >> g.logA1);
-                idx[1] = (int)(grow & (g.A1 - 1));
+                idx[0] = (int)(g.any_size ? grow / g.A1 : (grow >> g.logA1));
+                idx[1] = (int)(g.any_size ? grow % g.A1 : (grow & (g.A1 - 1)));
                 idx[2] = n;
             } else {
                 idx[0] = (int)grow;
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(TPB) stats_partials_kernel(StatsPartialArgs P)
             acc[1] += gp;
             acc[2] += gp > EPS ? 1.f : 0.f;
             for (int d = 0; d < g.nd; ++d) {
-                const float x = (float)(((idx[d] - cr.shift[d]) & (g.dims[d] - 1)) - g.dims[d] / 2);
+                const float x = (float)(py_mod(idx[d] - cr.shift[d], g.dims[d]) - g.dims[d] / 2);  // (= the mask for powers of two)
                 acc[4 + d] += a * x;
                 acc[4 + MAXD + d] += a * x * x;
                 acc[4 + 2 * MAXD + d] += gp * x;

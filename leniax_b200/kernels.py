@@ -328,6 +328,49 @@ def get_kernels_and_mapping(kernels_params: List, world_size: List[int], nb_chan
     return torch.cat(per_channel)[:, None], mapping  # [C*max_k, 1, kh, kw]
 
 
+def is_pow2_world(world_size) -> bool:
+    return all(int(n) >= 8 and (int(n) & (int(n) - 1)) == 0 for n in world_size)
+
+
+def spatial_from_spectrum(K_fft: torch.Tensor, nb_slots: int, world_size) -> torch.Tensor:
+    """The kernels of the direct-convolution path, ``[nb_slots, 1, kh, kw]`` float32 (the layout of ``get_kernels_and_mapping(fft=False)``,
+    kernels.py:116-117), recovered from the FFT kernels ``K = fftn(fftshift(centre-pad(kernel)))`` of a 2-D world of ANY size.
+
+    Worlds whose size is not a power of two (the reference's ``fftn`` takes any size, core.py:81) are stepped through
+    ``lnx_update_conv``: ``real(ifftn(K))`` is the circular-convolution kernel ``k[u]`` the FFT path applies, ``potential[y] = sum_u
+    state[y - u] k[u]``; the cross-correlation taps ``lnx_update_conv`` wants are ``taps[i] = k[(h - i) mod N]`` with the centre at ``h =
+    kh // 2``.  The inverse transform is two dense products with the DFT matrix in complex128 (a set-up step, once per scan); entries
+    below 2e-6 of the largest tap (ten times the rounding noise a complex64 spectrum leaves on the taps) are outside the measured support."""
+    if len(world_size) != 2:
+        raise NotImplementedError('worlds whose size is not a power of two are supported in 2-D only (direct-convolution potential, as in the '
+                                  'reference: core.py:136)')
+    H, W = int(world_size[0]), int(world_size[1])
+    K = K_fft.reshape(nb_slots, H, W).to(torch.complex128)
+    dev = K.device
+
+    def idft(n):
+        a = torch.arange(n, device=dev, dtype=torch.float64)
+        ang = 2 * torch.pi * torch.outer(a, a) / n
+        return torch.complex(torch.cos(ang), torch.sin(ang)) / n
+
+    k = (idft(H) @ K @ idft(W)).real  # [nb_slots, H, W]: k[u, v], the origin at index (0, 0)
+    mag = k.abs().amax(dim=0)
+    live = mag > 2e-6 * float(mag.max())
+    if not bool(live.any()):
+        return torch.zeros((nb_slots, 1, 1, 1), dtype=torch.float32, device=dev)
+    uy = torch.arange(H, device=dev)
+    ux = torch.arange(W, device=dev)
+    dy = torch.minimum(uy, H - uy)  # circular distance from the origin
+    dx = torch.minimum(ux, W - ux)
+    hy = int(dy[live.any(dim=1)].max())
+    hx = int(dx[live.any(dim=0)].max())
+    hy, hx = min(hy, (H - 1) // 2), min(hx, (W - 1) // 2)
+    iy = (hy - torch.arange(2 * hy + 1, device=dev)) % H  # taps[i] = k[(h - i) mod N]
+    ix = (hx - torch.arange(2 * hx + 1, device=dev)) % W
+    taps = k[:, iy][:, :, ix]
+    return taps.to(torch.float32)[:, None].contiguous()
+
+
 _K_CACHE: Dict[Tuple, torch.Tensor] = {}
 _K_CACHE_MAX = 64
 _UNCACHEABLE = object()

@@ -103,6 +103,19 @@ def _scan(cells0, K, gf_params, weights, T, max_run_iter, update_fn: UpdateFn, s
         if host_cells is not None:
             cells0 = host_cells.to(dev)
         return _scan_conv(cells0, K, gf_params, weights, T, max_run_iter, update_fn, stats_fn, keep_trajectory)
+    from . import kernels as _kernels
+    if not _kernels.is_pow2_world(world_size):
+        # The FFT engines need powers of two; the reference's fftn takes any size (core.py:81).  Such worlds (2-D) are stepped by direct
+        # convolution with the taps recovered from K, statistics by lnx_compute_stats: a host loop like the fft=False path - a
+        # compatibility path, not a throughput path.
+        import dataclasses
+        if host_cells is not None:
+            cells0 = host_cells.to(dev)
+        taps = [_kernels.spatial_from_spectrum(K[s], pf.nb_slots, world_size) for s in range(n_sols)]
+        kh, kw = max(t.shape[2] for t in taps), max(t.shape[3] for t in taps)
+        taps = [torch.nn.functional.pad(t, ((kw - t.shape[3]) // 2, ) * 2 + ((kh - t.shape[2]) // 2, ) * 2) for t in taps]  # odd sizes: centred
+        conv_fn = UpdateFn(dataclasses.replace(pf, fft=False), update_fn.get_field_fn, update_fn.get_state_fn)
+        return _scan_conv(cells0, torch.stack(taps), gf_params, weights, T, max_run_iter, conv_fn, stats_fn, keep_trajectory)
     slots, c_in, gf_ids = update_fn.kernel_layout(C)
     K = K.reshape((n_sols, pf.nb_slots) + world_size)
     gfp, wts = gf_params.reshape(n_sols, len(slots), 2), weights.reshape(n_sols, C, len(slots))

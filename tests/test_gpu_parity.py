@@ -660,6 +660,47 @@ def test_conv_path_matches_oracle_and_fft_path(golden_dir, name, steps):
     assert np.abs(cells.cpu().numpy() - fcells.cpu().numpy()).max() < 2e-5
 
 
+def test_fft_scan_of_a_non_power_of_two_world_matches_oracle():
+    """The reference's FFT potential takes any world size (core.py:81: jnp.fft.fftn); the FFT engines here need powers of two.  A 100 x 120
+    world with fft=True kernels runs through the direct-convolution path with the taps recovered from K (kernels.spatial_from_spectrum) and
+    the stand-alone statistics, and matches the oracle's FFT run: run_scan (trajectory) and run_scan_mem_optimized (statistics + N)."""
+    H, W, R, steps = 100, 120, 13, 12
+    kp = [dict(k_slug='circle_2d', k_params=[1., [1.]], kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1.,
+               c_in=0, c_out=0)]
+    K, mapping = kernels.get_kernels_and_mapping(copy.deepcopy(kp), [H, W], 1, R, device=DEV)
+    oK, om = lo.get_kernels_and_mapping(copy.deepcopy(kp), [H, W], 1, R)
+    assert np.abs(K.cpu().numpy() - oK).max() < 5e-6
+    rng = np.random.default_rng(5)
+    worlds = np.zeros((3, 1, H, W), np.float32)
+    for i in range(3):  # off-centre blobs: the centroid (hence total_shift_idx, modulo 100 / 120) moves
+        y, x = rng.integers(0, H - 40), rng.integers(0, W - 40)
+        worlds[i, 0, y:y + 40, x:x + 40] = rng.random((40, 40), dtype=np.float32) * (0.5 + 0.2 * i)
+    ufn = helpers.build_update_fn(K.shape, mapping)
+    wp, rp = {'R': R, 'T': 10}, {'world_size': [H, W]}
+    sfn = statistics.build_compute_stats_fn(wp, rp)
+    gf, w = mapping.get_gf_params(DEV), mapping.get_kernels_weight_per_channel(DEV)
+    c, f, p, stats = runner.run_scan(None, torch.from_numpy(worlds).to(DEV), K, gf, w, 10., steps, R, ufn, sfn)
+    oc, of, op, ostats = lo.run_scan(worlds, oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(10.), steps,
+                                     lo.build_update_fn(om), lo.build_compute_stats_fn(wp, rp))
+    assert np.abs(p.cpu().numpy() - op).max() < 3e-6
+    # (poly_quad4 with s = 0.015 has slopes up to ~60 per unit of potential: 3e-6 of potential is up to 2e-4 of field, times dt = 0.1 of state)
+    assert np.abs(f.cpu().numpy() - of).max() < 2e-4
+    assert np.abs(c.cpu().numpy() - oc).max() < 3e-5
+    for k in ('mass', 'mass_volume', 'growth', 'mass_density', 'mass_speed', 'mass_growth_dist', 'inertia'):
+        np.testing.assert_allclose(stats[k].cpu().numpy(), ostats[k], rtol=2e-3, atol=1e-4, err_msg=k)
+    assert stats['N'].cpu().numpy().tolist() == ostats['N'].tolist()
+    st2, fin = runner.run_scan_mem_optimized(None, torch.from_numpy(worlds).to(DEV)[None], K[None], gf[None], w[None], torch.tensor([10.], device=DEV),
+                                            steps, R, ufn, sfn)
+    assert torch.equal(st2['N'][0], stats['N'])
+    np.testing.assert_allclose(st2['mass'][0].cpu().numpy(), stats['mass'].cpu().numpy(), rtol=1e-6)
+    # the state after the last update
+    on, _, _ = lo.build_update_fn(om)(oc[-1], oK, om.get_gf_params(), om.get_kernels_weight_per_channel(), np.float32(0.1))
+    assert np.abs(fin[0].cpu().numpy() - on).max() < 5e-5
+    # one core.update on the same world
+    n1, f1, p1 = ufn(None, torch.from_numpy(worlds).to(DEV), K, gf, w, 0.1)
+    assert np.abs(p1.cpu().numpy() - op[0]).max() < 3e-6 and np.abs(n1.cpu().numpy() - oc[1]).max() < 3e-5
+
+
 def test_conv_update_on_a_non_power_of_two_world(golden_dir):
     """The conv path has no power-of-two restriction: one core.update on a 100 x 120 world, 2 channels, 3 kernels."""
     rng = np.random.default_rng(11)

@@ -52,7 +52,7 @@ def test_plan_validation_errors():
     lib = leniax_b200.load_library()
     handle = ctypes.c_void_p()
     d = _lib.LnxDesc(nb_dims=2, nb_channels=1, nb_kernels=1, nb_slots=1, R=13., stats_dt=.1)
-    d.dims[0], d.dims[1] = 100, 100  # not a power of two: neither the resident nor the tiled engine takes it
+    d.dims[0], d.dims[1] = 5000, 100  # beyond 4096 (a size that is merely not a power of two gives a statistics-only plan, on a GPU)
     assert lib.lnx_plan_create(ctypes.byref(d), ctypes.byref(handle)) == _lib.LNX_ERR_UNSUPPORTED
     d.dims[0] = d.dims[1] = 128
     d.nb_channels = 99
@@ -205,7 +205,7 @@ int main(void) {
     lnx_desc d;
     lnx_plan* plan = NULL;
     memset(&d, 0, sizeof d);
-    d.nb_dims = 2; d.dims[0] = 100; d.dims[1] = 100;
+    d.nb_dims = 2; d.dims[0] = 5000; d.dims[1] = 100;  /* (100 x 100 gives a statistics-only plan: any size up to 4096) */
     d.nb_channels = 1; d.nb_kernels = 1; d.nb_slots = 1; d.R = 13.f; d.stats_dt = .1f;
     d.gf_id[0] = LNX_GF_POLY_QUAD4; d.state_fn = LNX_STATE_V1;
     int rc = lnx_plan_create(&d, &plan);
@@ -219,7 +219,7 @@ int main(void) {
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(' ', 4)
     assert int(out[0]) == 100 and int(out[1]) == _lib.LNX_ERR_UNSUPPORTED and int(out[2]) == 1
     assert int(out[3]) == ctypes.sizeof(_lib.LnxDesc)  # the ctypes mirror and the C struct agree on the layout
-    assert 'power of two' in out[4]
+    assert 'must be in [1, 4096]' in out[4]
 
 
 def test_parallel_early_exit_oracle_equals_run_scan(golden_dir):
@@ -369,3 +369,28 @@ def test_param_summary_one_sync_flags_and_pattern():
     assert runner._param_summary(gf, torch.tensor([[[.5, 0., .7], [0., 0., 0.]]]), False)[0] is True        # ... fine for weighted_sum
     w.mul_(2.)                                                                         # in-place change invalidates the cache entry
     assert runner._param_summary(gf, w, True) == (True, (0, 1, 0))
+
+
+def test_taps_recovered_from_a_non_power_of_two_kernel_spectrum():
+    """kernels.spatial_from_spectrum: the direct-convolution taps recovered from K = fftn(fftshift(centre-pad(kernel))) of a 100 x 120 world
+    (the reference's FFT potential takes any size, core.py:81) reproduce real(ifftn(fftn(state) * K)) as the cross-correlation
+    lnx_update_conv computes (lnx_conv.cuh): potential[y][x] = sum_ij state[(y + i - kh/2) mod H][(x + j - kw/2) mod W] taps[i][j]."""
+    import torch
+    from leniax_b200 import kernels
+    from oracle import lenia_oracle as lo
+    H, W, R = 100, 120, 13
+    kp = [dict(k_slug='circle_2d', k_params=[1., [1., .5]], kf_slug='poly_quad', kf_params=[4], gf_slug='poly_quad4', gf_params=[.15, .015], h=1.,
+               c_in=0, c_out=0)]
+    oK, _ = lo.get_kernels_and_mapping(kp, [H, W], 1, R)
+    assert not kernels.is_pow2_world([H, W]) and kernels.is_pow2_world([64, 2048])
+    taps = kernels.spatial_from_spectrum(torch.from_numpy(oK.astype(np.complex64)), 1, [H, W]).numpy()[0, 0]
+    kh, kw = taps.shape
+    assert kh % 2 == 1 and kw % 2 == 1 and 2 * R - 3 <= kh <= 2 * R + 3 and abs(taps.sum() - 1.) < 1e-5
+    rng = np.random.default_rng(0)
+    state = rng.random((H, W))
+    ref = np.real(np.fft.ifft2(np.fft.fft2(state) * oK[0, 0, 0].astype(np.complex128)))
+    pot = np.zeros_like(state)
+    for i in range(kh):
+        for j in range(kw):
+            pot += np.roll(state, (-(i - kh // 2), -(j - kw // 2)), axis=(0, 1)) * taps[i, j]
+    assert np.abs(pot - ref).max() < 2e-6
