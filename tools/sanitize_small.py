@@ -3,7 +3,9 @@
     compute-sanitizer --tool racecheck python tools/sanitize_small.py [resident|tiled|setup]
 resident: lnx_world128_tm (1 channel, 1 kernel), lnx_world128_gen2 (orbium-scutium: 2 channels, 2 kernels; 3c6k), lnx_world128_gen_tm
           (same worlds, LNX_RUN_GENERIC_1CTA, and a trajectory scan), early stop on and off
-tiled:    64^3 thread-per-line engine, 2048^2 four-step engine (a 2048^2 world is big: 3 steps), generic tiled passes (256^2, 32^3)
+tiled:    2048^2 four-step engine with both rows kernels (a 2048^2 world is big: 3 steps); 64^3: whole-scan kernel, half-line kernels per
+          pass and step, round-1 thread-per-line kernels, generic tiled passes; generic tiled passes (256^2)
+anysize:  a 100 x 120 world: taps from the spectrum, lnx_update_conv, any-size lnx_compute_stats
 setup:    lnx_rasterize_kernels, lnx_kernel_spectrum (2-D, 3-D), lnx_init_perlin(_seeded), lnx_init_uniform, lnx_summarize_stats"""
 import copy
 import os
@@ -60,29 +62,40 @@ if what == 'resident':
 elif what == 'tiled':
     K, mapping, ufn, sfn = orbium([2048, 2048], 52)
     cells = torch.from_numpy(bench.d_world_numpy())[None, None, None].to(DEV)
-    stats, _ = runner.run_scan_mem_optimized(None, cells, K[None], mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None],
-                                             torch.tensor([10.], device=DEV), 3, 52, ufn, sfn)
-    torch.cuda.synchronize()
-    print('2048^2 mass', stats['mass'][0, :, 0].tolist())
+    for real_rows in (False, True):
+        runner.T2K_REAL_ROWS = real_rows
+        stats, _ = runner.run_scan_mem_optimized(None, cells, K[None], mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None],
+                                                 torch.tensor([10.], device=DEV), 3, 52, ufn, sfn)
+        torch.cuda.synchronize()
+        print('2048^2', 'real rows' if real_rows else 'row pairs', 'mass', stats['mass'][0, :, 0].tolist())
+    runner.T2K_REAL_ROWS = False
     kern = torch.from_numpy(bench.sphere_kernel_numpy(13)).to(DEV)
     kp = [dict(bench.ORBIUM_KP[0], k_slug='raw', k_params=kern)]
     K, mapping = kernels.get_kernels_and_mapping(kp, [64, 64, 64], 1, 13, device=DEV)
     ufn = helpers.build_update_fn(K.shape, mapping)
     sfn = statistics.build_compute_stats_fn({'R': 13, 'T': 10}, {'world_size': [64, 64, 64]})
     _, cells = initializations.random_uniform(initializations.RngKey(5), 3, [64, 64, 64], 13, [.15, .015], device=DEV)
-    for generic in (False, True):
-        runner.TILED_GENERIC = generic
+    for eng in ('whole_scan', 'stepwise', 'line64', 'generic'):
+        runner.TILED_GENERIC, runner.T64_STEPWISE, runner.T64_LINE = eng == 'generic', eng == 'stepwise', eng == 'line64'
         stats, _ = runner.run_scan_mem_optimized(None, cells[None, :, None], K[None], mapping.get_gf_params(DEV)[None],
                                                  mapping.get_kernels_weight_per_channel(DEV)[None], torch.tensor([10.], device=DEV), 9, 13, ufn, sfn)
         torch.cuda.synchronize()
-        print('64^3', 'generic passes' if generic else 'line engine', 'mass', [round(float(x), 4) for x in stats['mass'][0, -1]])
-    runner.TILED_GENERIC = False
+        print('64^3', eng, 'mass', [round(float(x), 4) for x in stats['mass'][0, -1]])
+    runner.TILED_GENERIC = runner.T64_STEPWISE = runner.T64_LINE = False
     K, mapping, ufn, sfn = orbium([256, 256], 13)
     cells = (torch.rand((1, 2, 1, 256, 256), device=DEV) * .4)
     stats, _ = runner.run_scan_mem_optimized(None, cells, K[None], mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None],
                                              torch.tensor([10.], device=DEV), 9, 13, ufn, sfn)
     torch.cuda.synchronize()
     print('256^2 generic passes mass', [round(float(x), 4) for x in stats['mass'][0, -1]])
+elif what == 'anysize':
+    K, mapping, ufn, sfn = orbium([100, 120], 13)
+    cells = torch.zeros((1, 2, 1, 100, 120), device=DEV)
+    cells[0, :, 0, 20:60, 30:70] = torch.rand((2, 40, 40), device=DEV) * .6
+    stats, _ = runner.run_scan_mem_optimized(None, cells, K[None], mapping.get_gf_params(DEV)[None], mapping.get_kernels_weight_per_channel(DEV)[None],
+                                             torch.tensor([10.], device=DEV), 5, 13, ufn, sfn)
+    torch.cuda.synchronize()
+    print('100 x 120 mass', [round(float(x), 4) for x in stats['mass'][0, -1]])
 else:
     kps = bench.c3_kernels_params(3)
     kps[1][0].update(k_slug='ellipse_2d', k_params=[1., [1., .5], .9, .6, .25])
