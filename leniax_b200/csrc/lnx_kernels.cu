@@ -167,20 +167,27 @@ static unsigned pass_d_threads(const Geom& g, long long worlds) {
 }
 static bool line2k_plan(const Geom& g, int C, int K) { return is_sq2k(g) && C == 1 && K == 1; }
 
-// Graph executables whose last launch may still be running: destroyed by a later call once their event has completed.
+// Executable graphs of the step loops.  One per (device, step-loop kind, steps per graph), kept for the life of the process: a scan
+// captures its step(s) again (host-only work), lets cudaGraphExecUpdate write the new kernel arguments into the cached executable and
+// launches that - no instantiation per scan (0.3 ms for two nodes, and the first instantiations of a 32-node graph in a process cost
+// tens of ms when earlier launches are still in flight: profiles/r2_t2k_graph_ab.txt).  An update only affects LATER launches of the
+// executable; the ones already enqueued keep the arguments they were enqueued with.  Executables an update refuses (another topology:
+// cannot happen for one kind) are replaced; the old one is destroyed by a later call once the event behind its last launch completed.
+struct CachedExec {
+    int device, kind, n;
+    cudaGraphExec_t exec;
+};
 struct RetiredGraph {
     cudaGraphExec_t exec;
-    cudaGraph_t graph;
     cudaEvent_t done;
 };
-static std::mutex g_retired_mu;
+static std::mutex g_graph_mu;  // the cache, the retired list, and update + launches of a cached executable as one unit
+static std::vector<CachedExec> g_exec_cache;
 static std::vector<RetiredGraph> g_retired;
-static void sweep_retired_graphs() {
-    std::lock_guard<std::mutex> lk(g_retired_mu);
+static void sweep_retired_graphs() {  // (g_graph_mu held)
     for (size_t i = 0; i < g_retired.size();) {
         if (cudaEventQuery(g_retired[i].done) == cudaSuccess) {
             cudaGraphExecDestroy(g_retired[i].exec);
-            cudaGraphDestroy(g_retired[i].graph);
             cudaEventDestroy(g_retired[i].done);
             g_retired[i] = g_retired.back();
             g_retired.pop_back();
@@ -190,41 +197,73 @@ static void sweep_retired_graphs() {
     }
     (void)cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
 }
-// One time step whose launches have step-independent arguments (the step index lives in the world's carry), captured once into a
-// CUDA graph and replayed `steps` times on `st`: the passes of small / single worlds take 10-30 us each and issuing them one by one
-// cost the host 14-20 us per launch (the loop was launch-bound).
-constexpr int GRAPH_MIN_STEPS = 8;  // shorter loops (lnx_update = one step) are launched directly: building a graph costs ~0.3 ms
+enum GraphKind { GRAPH_T2K_PAIRS = 1, GRAPH_T2K_REAL_ROWS = 2, GRAPH_GENERIC_PASSES = 3, GRAPH_T2K_PAIRS_PDL = 4 };
+// One time step whose launches have step-independent arguments (the step index lives in the world's carry), captured into a CUDA
+// graph and replayed on `st`: the passes of small / single worlds take 10-30 us each and issuing them one by one cost the host
+// 14-20 us per launch (the loop was launch-bound).
+constexpr int GRAPH_MIN_STEPS = 8;  // shorter loops (lnx_update = one step) are launched directly
+// Steps per graph.  A graph launch is a full dependency on the previous one, and crossing it costs more than an edge between two
+// kernel nodes of one graph: config D 10.08 -> 9.49 ms at 16 steps per graph (tools/ab_config_d.py).  LNX_GRAPH_UNROLL=1: one step
+// per graph (A/B; read per scan, not once per process: the A/B tool alternates the variants inside one process).
+static int graph_unroll() {
+    const char* e = getenv("LNX_GRAPH_UNROLL");
+    const int v = e ? atoi(e) : 16;
+    return v < 1 ? 1 : v > 64 ? 64 : v;
+}
+// enqueue_step(stream, u): u = position of the step inside its graph (0: no kernel of this loop precedes it in the capture)
 template <class EnqueueStep>
-static int replay_steps(EnqueueStep enqueue_step, int steps, cudaStream_t st) {
+static int replay_steps(EnqueueStep enqueue_step, int steps, int kind, cudaStream_t st) {
     if (steps < GRAPH_MIN_STEPS) {
-        for (int t = 0; t < steps; ++t) enqueue_step(st);
+        for (int t = 0; t < steps; ++t) enqueue_step(st, 0);
         const cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? LNX_OK : fail(LNX_ERR_CUDA, "tiled engine: launch failed: %s", cudaGetErrorString(e));
     }
-    sweep_retired_graphs();
+    const int unroll = steps >= 2 * graph_unroll() ? graph_unroll() : 1;
+    int device = 0;
     cudaStream_t cap = nullptr;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    cudaEvent_t done = nullptr;
-    cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
-    if (e == cudaSuccess) {
-        enqueue_step(cap);
-        e = cudaStreamEndCapture(cap, &graph);
+    cudaError_t e = cudaGetDevice(&device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+    // the main graph (unroll steps, launched steps / unroll times), then one of steps % unroll steps
+    for (int part = 0; part < 2 && e == cudaSuccess; ++part) {
+        const int n = part == 0 ? unroll : steps % unroll, reps = part == 0 ? steps / unroll : 1;
+        if (n == 0) break;
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            for (int u = 0; u < n; ++u) enqueue_step(cap, u);
+            e = cudaStreamEndCapture(cap, &graph);
+        }
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(g_graph_mu);
+            sweep_retired_graphs();
+            size_t slot = 0;
+            while (slot < g_exec_cache.size() &&
+                   !(g_exec_cache[slot].device == device && g_exec_cache[slot].kind == kind && g_exec_cache[slot].n == n))
+                ++slot;
+            cudaGraphExec_t exec = nullptr;
+            if (slot < g_exec_cache.size()) {
+                exec = g_exec_cache[slot].exec;
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(exec, graph, &info) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    cudaEvent_t done = nullptr;  // earlier launches of the old executable were enqueued on some stream of this device
+                    if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess && cudaEventRecord(done, nullptr) == cudaSuccess)
+                        g_retired.push_back({exec, done});  // (legacy default stream: behind every blocking stream; a leak otherwise)
+                    exec = nullptr;
+                    g_exec_cache[slot] = g_exec_cache.back();
+                    g_exec_cache.pop_back();
+                }
+            }
+            if (!exec) {
+                e = cudaGraphInstantiate(&exec, graph, 0);
+                if (e == cudaSuccess) g_exec_cache.push_back({device, kind, n, exec});
+            }
+            for (int t = 0; e == cudaSuccess && t < reps; ++t) e = cudaGraphLaunch(exec, st);
+        }
+        if (graph) cudaGraphDestroy(graph);  // (an executable graph does not refer to the graph it was instantiated / updated from)
     }
-    if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
-    for (int t = 0; e == cudaSuccess && t < steps; ++t) e = cudaGraphLaunch(exec, st);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventRecord(done, st);
     if (cap) cudaStreamDestroy(cap);
-    if (e != cudaSuccess) {
-        if (exec) cudaGraphExecDestroy(exec);
-        if (graph) cudaGraphDestroy(graph);
-        if (done) cudaEventDestroy(done);
-        return fail(LNX_ERR_CUDA, "tiled engine: graph capture / launch failed: %s", cudaGetErrorString(e));
-    }
-    std::lock_guard<std::mutex> lk(g_retired_mu);
-    g_retired.push_back({exec, graph, done});
+    if (e != cudaSuccess) return fail(LNX_ERR_CUDA, "tiled engine: graph capture / launch failed: %s", cudaGetErrorString(e));
     return LNX_OK;
 }
 // worlds per launch of the 64^3 line engine.  Default: all of them.  LNX_T64_BATCH=n runs every n worlds through ALL their steps
@@ -754,19 +793,26 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             // the chain, measured no faster: 10.7 ms against 10.4 ms for 256 steps) - same layouts, same lead kernel
             const bool pairs = (run_flags & LNX_RUN_T2K_REAL_ROWS) == 0;
             const bool finite = (run_flags & LNX_RUN_ASSUME_FINITE) != 0;
+            // LNX_T2K_PDL=1: programmatic dependent launches between the kernels of a graph - measured SLOWER (10.7 against 9.6 ms: the
+            // early-resident CTAs of the next kernel take registers and issue slots from the one-wave kernel that is still running,
+            // profiles/r2_t2k_graph_ab.txt); the default is a full dependency
+            const char* pdl_env = getenv("LNX_T2K_PDL");
+            const bool pdl = pdl_env && atoi(pdl_env) != 0;
             if (pairs)
                 rows_fwd_kernel<<<dim3(1024 / ROWS_WARPS, 1, nw), 32 * ROWS_WARPS, ROWS_SMEM, st>>>(a, x2k);  // the first step's forward rows
             else
                 rows1_fwd_kernel<<<dim3(N / RR_WARPS, 1, nw), 32 * RR_WARPS, RR_SMEM, st>>>(a, x2k);
             const int rc = th::replay_steps(
-                [&](cudaStream_t cap) {
-                    lnx::t2k::lead_kernel<<<dim3(1026, 1, nw), 32, 0, cap>>>(b, x2k, d);
+                [&](cudaStream_t cap, int u) {
+                    // programmatic edges (lnx_tiled2k.cuh: pdl_wait / pdl_launch) between the kernels of one graph; the real-row
+                    // kernels have no griddepcontrol.wait and are launched as full dependencies
+                    launch_lead(b, x2k, d, nw, pdl && pairs && u > 0, cap);
                     if (pairs)
-                        launch_rows_inv(c, x2k, a.spec, nw, finite, cap);
+                        launch_rows_inv(c, x2k, a.spec, nw, finite, pdl, cap);
                     else
                         launch_rows1_inv(c, x2k, a.spec, nw, finite, cap);
                 },
-                max_run_iter, st);
+                max_run_iter, pairs ? (pdl ? th::GRAPH_T2K_PAIRS_PDL : th::GRAPH_T2K_PAIRS) : th::GRAPH_T2K_REAL_ROWS, st);
             if (rc != LNX_OK) return rc;
             d.t = max_run_iter - 1;  // the last step's statistics
             pass_d_kernel<<<nw, 128, 0, st>>>(d);
@@ -850,13 +896,13 @@ static int run_scan_tiled(const lnx_plan* p, int32_t n_sols, int32_t n_init, int
             c.t = -1;
             d.t = -1;
             const int rc = th::replay_steps(
-                [&](cudaStream_t cap) {
+                [&](cudaStream_t cap, int) {
                     pass_a_kernel<<<grid_a, TPB, th::smem_a(g), cap>>>(a);
                     pass_b_kernel<<<grid_b, TPB, th::smem_b(g, b.two_buf != 0), cap>>>(b);
                     pass_c_kernel<<<grid_c, TPB, th::smem_c(g, C), cap>>>(c);
                     pass_d_kernel<<<(unsigned)worlds, th::pass_d_threads(g, worlds), 0, cap>>>(d);
                 },
-                max_run_iter, st);
+                max_run_iter, th::GRAPH_GENERIC_PASSES, st);
             if (rc != LNX_OK) return rc;
         }
     }

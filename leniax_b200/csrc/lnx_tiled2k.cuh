@@ -556,6 +556,38 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_fwd_kernel(PassAArgs P, 
     rf8_untangle_store(threadIdx.x, nat_all, P.spec + (size_t)w * SPEC + 2 * ROWS_WARPS * blockIdx.x);
 }
 
+// Programmatic dependent launch between the two kernels of a step (and between steps inside one captured graph).  A kernel launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor is still running; what it does
+// before pdl_wait() must not touch anything the predecessor writes.  Both step kernels call pdl_launch() right AFTER pdl_wait(): their
+// successor can then only start once the kernel BEFORE them has completed, i.e. at most two kernels of the chain overlap and a
+// prologue may read what the kernel two places back wrote (rows_inv(t): the state rows of rows_inv(t - 1)).  In a launch without the
+// attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900  // (the CPU emulator build of this header targets nvcc's default architecture)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+template <class... KArgs, class... Args>
+inline void launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);  // (errors surface through cudaGetLastError / the capture's end)
+}
+
 // grid (1025 columns + 1, 1, worlds).  CTA 1025 of world w finalises the statistics of the PREVIOUS step (pass D) if one is pending:
 // nothing before rows_inv needs the carry it updates, so that latency-bound single-CTA job leaves the critical path.  The step index
 // lives in the world's carry (WorldCarry::step / pending), so the three launches of a step have step-independent arguments and the
@@ -565,6 +597,8 @@ __global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArg
     __shared__ __align__(16) float2 sm[SMEM_C2];
     const int lane = threadIdx.x, k = blockIdx.x, w = blockIdx.z;
     if (k == HALF) {
+        pdl_wait();
+        pdl_launch();
         if (D.carry[w].pending) tiled::pass_d_body(D, w, D.carry[w].step);
         return;
     }
@@ -572,7 +606,9 @@ __global__ void __launch_bounds__(32) lead_kernel(PassBArgs P, Extra X, PassDArg
     const float2* kt = X.ktab + (size_t)sol * SPEC + (size_t)k * N;
 #pragma unroll
     for (int j = 0; j < 4; ++j)  // the 16 KB table line is needed after the forward transform: have it in L1 by then
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(kt + (j * 32 + lane) * 16));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(kt + (j * 32 + lane) * 16));  // (a constant of the scan: before pdl_wait)
+    pdl_wait();  // the spectrum of the rows kernel before this launch
+    pdl_launch();
     float2 v[64];
     ld_load(lane, P.spec + (size_t)w * SPEC + (size_t)k * N, v);
     fs_fwd_a(lane, v, X.tw);
@@ -612,7 +648,9 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
     float* st = P.state + (size_t)w * N * N + (size_t)(2 * p) * N;
 #pragma unroll
     for (int j = 0; j < 4; ++j)  // the state rows are needed after the transform: have them in L1 by then
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(st + (j * 32 + lane) * 32));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(st + (j * 32 + lane) * 32));  // (written two kernels back: legal before pdl_wait)
+    pdl_wait();  // the potential spectrum and the carry of the lead launch before this one
+    pdl_launch();
     ri8_gather(threadIdx.x, P.pot_spec + (size_t)w * SPEC + 2 * ROWS_WARPS * blockIdx.x, nat_all);
     __syncthreads();
     float2 v[64];
@@ -683,15 +721,20 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) rows_inv_kernel(PassCArgs P, 
 }
 
 // rows_inv in the compiled form of this plan (finite: LNX_RUN_ASSUME_FINITE)
-inline void launch_rows_inv(const PassCArgs& c, const Extra& x, float2* next_spec, unsigned nw, bool finite, cudaStream_t s) {
+// (pdl: launched as a programmatic dependent of the lead launch before it)
+inline void launch_rows_inv(const PassCArgs& c, const Extra& x, float2* next_spec, unsigned nw, bool finite, bool pdl, cudaStream_t s) {
     const dim3 grid(N / 2 / ROWS_WARPS, 1, nw);
     switch (t64h::select_mode(c.gf_id[0], c.state_fn, finite)) {
-        case t64h::MODE_PQ4: (rows_inv_kernel<t64h::MODE_PQ4>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
-        case t64h::MODE_PQ4_NP: (rows_inv_kernel<t64h::MODE_PQ4_NP>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
-        case t64h::MODE_GAUSS: (rows_inv_kernel<t64h::MODE_GAUSS>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
-        case t64h::MODE_GAUSS_NP: (rows_inv_kernel<t64h::MODE_GAUSS_NP>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
-        default: (rows_inv_kernel<t64h::MODE_DYN>)<<<grid, 32 * ROWS_WARPS, ROWS_SMEM, s>>>(c, x, next_spec); break;
+        case t64h::MODE_PQ4: launch_maybe_pdl(rows_inv_kernel<t64h::MODE_PQ4>, grid, 32 * ROWS_WARPS, ROWS_SMEM, s, pdl, c, x, next_spec); break;
+        case t64h::MODE_PQ4_NP: launch_maybe_pdl(rows_inv_kernel<t64h::MODE_PQ4_NP>, grid, 32 * ROWS_WARPS, ROWS_SMEM, s, pdl, c, x, next_spec); break;
+        case t64h::MODE_GAUSS: launch_maybe_pdl(rows_inv_kernel<t64h::MODE_GAUSS>, grid, 32 * ROWS_WARPS, ROWS_SMEM, s, pdl, c, x, next_spec); break;
+        case t64h::MODE_GAUSS_NP: launch_maybe_pdl(rows_inv_kernel<t64h::MODE_GAUSS_NP>, grid, 32 * ROWS_WARPS, ROWS_SMEM, s, pdl, c, x, next_spec); break;
+        default: launch_maybe_pdl(rows_inv_kernel<t64h::MODE_DYN>, grid, 32 * ROWS_WARPS, ROWS_SMEM, s, pdl, c, x, next_spec); break;
     }
+}
+// (pdl: a programmatic dependent of the rows kernel of the previous step in the same graph)
+inline void launch_lead(const PassBArgs& b, const Extra& x, const PassDArgs& d, unsigned nw, bool pdl, cudaStream_t s) {
+    launch_maybe_pdl(lead_kernel, dim3(1026, 1, nw), 32, 0, s, pdl, b, x, d);
 }
 
 // ---- real-row variant: grid (128, 1, worlds), 16 warps; warp j of CTA c owns row 16 c + j; dynamic shared memory RR_SMEM bytes ----
