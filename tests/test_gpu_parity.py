@@ -423,6 +423,21 @@ def test_2048_line2k_engine_agrees_with_generic_tiled_passes_over_a_long_run():
             tol = (dict(rtol=2e-3, atol=2e-3 * max(1., float(np.abs(b).max())))
                    if k in ('mass_angle_speed', 'mass_speed', 'mass_growth_dist', 'potential_volume') else dict(rtol=2e-4, atol=1e-5))
             np.testing.assert_allclose(a, b, err_msg=eng + ' ' + k, **tol)
+    # the step loop's graph (steps per captured graph, cached executables refreshed by cudaGraphExecUpdate, programmatic dependent
+    # launches; the switches are read at every scan) changes nothing: same kernels in the same order -> bit-identical results.
+    # 40 steps = two launches of a 16-step graph + one 8-step graph; 1 step per graph = forty launches of one executable.
+    import os
+    ref_stats, ref_final = res['line2k']
+    try:
+        for unroll, pdl in ((1, 0), (16, 1), (3, 1), (16, 0)):
+            os.environ['LNX_GRAPH_UNROLL'], os.environ['LNX_T2K_PDL'] = str(unroll), str(pdl)
+            st, fin = runner.run_scan_mem_optimized(None, cells, K[None], gf, w, torch.tensor([10.], device=DEV), steps, R, ufn, sfn)
+            assert torch.equal(fin, ref_final), (unroll, pdl)
+            for k in st:
+                assert torch.equal(st[k], ref_stats[k]), (unroll, pdl, k)
+    finally:
+        os.environ.pop('LNX_GRAPH_UNROLL', None)
+        os.environ.pop('LNX_T2K_PDL', None)
 
 
 def _check_large_2d_world(size, scale, steps):
