@@ -26,7 +26,7 @@ for line in out.splitlines():
     m = re.match(r'\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)', line)
     if m and fam:
         fams[fam][m.group(1)] += 1
-keys = ['LDTM', 'STTM', 'FADD2', 'FMUL2', 'FFMA2', 'FADD', 'FMUL', 'FFMA', 'LDGSTS', 'LDS', 'STS', 'LDG', 'STG', 'BAR', 'SHFL', 'UTMALDG', 'UTMASTG', 'UTCHMMA', 'UTCQMMA', 'HMMA']
+keys = ['LDTM', 'STTM', 'FADD2', 'FMUL2', 'FFMA2', 'FADD', 'FMUL', 'FFMA', 'LDGSTS', 'LDS', 'STS', 'LDG', 'STG', 'BAR', 'SHFL', 'ACQBULK', 'PREEXIT', 'UTMALDG', 'UTMASTG', 'UTCHMMA', 'UTCQMMA', 'HMMA']
 print('%-22s %8s %9s ' % ('kernel family', 'kernels', 'instr') + ' '.join('%7s' % k for k in keys))
 for k, c in fams.items():
     if n_kernels[k]:
