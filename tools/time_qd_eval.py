@@ -99,4 +99,4 @@ if __name__ == '__main__':
         pr.enable()
         generation()
         pr.disable()
-        pstats.Stats(pr).sort_stats('cumulative').print_stats(18)
+        pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
